@@ -1,0 +1,81 @@
+// Library-level entry points: version / status strings, device check, launch counter and the diagnostic
+// plain-GEMM path the tests use to validate the tcgen05 engine in isolation.
+#include <atomic>
+
+#include "epilogues.cuh"
+#include "prep.cuh"
+
+namespace bvlm {
+namespace {
+std::atomic<int64_t> g_launches{0};
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+}  // namespace bvlm
+
+using namespace bvlm;
+
+extern "C" {
+
+const char* bvlm_version(void) { return "bvlm 0.1.0 (sm_100a; tcgen05+TMA)"; }
+
+const char* bvlm_status_string(int status) {
+  switch (status) {
+    case BVLM_OK: return "ok";
+    case BVLM_EINVAL: return "invalid argument";
+    case BVLM_ENOTSUP: return "unsupported configuration";
+    case BVLM_EDRIVER: return "CUDA driver entry point unavailable (cuTensorMapEncodeTiled)";
+    case BVLM_EWORKSPACE: return "workspace too small";
+    default: break;
+  }
+  if (status > 0) return cudaGetErrorString(static_cast<cudaError_t>(status));
+  return "unknown status";
+}
+
+int bvlm_device_check(void) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  int major = 0;
+  e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  if (major != 10) return BVLM_ENOTSUP;
+  CUtensorMap probe;
+  static __half* dummy = nullptr;
+  if (dummy == nullptr) {
+    e = cudaMalloc(&dummy, 128 * 64 * 2);
+    if (e != cudaSuccess) return static_cast<int>(e);
+  }
+  return make_tmap_2d(&probe, dummy, TM_F16, 64, 128, 128, 64, 128, 1);
+}
+
+int64_t bvlm_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int bvlm_convert_rows_16(const float* in, int64_t R, int64_t d, int64_t ld, int fmt, void* out, int64_t k_pad,
+                         void* stream) {
+  if (in == nullptr || out == nullptr || (fmt != FMT_F16 && fmt != FMT_BF16)) return BVLM_EINVAL;
+  return launch_rows_to_16(in, R, d, ld, 0, fmt, 0, 1.0f, out, k_pad, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int bvlm_gemm_tn_f32(const void* A16, int64_t M, const void* B16, int64_t N, int64_t k_pad, int fmt, float alpha,
+                     float* D, int64_t ldd, int split_k, void* stream) {
+  if (A16 == nullptr || B16 == nullptr || D == nullptr || M <= 0 || N <= 0 || k_pad <= 0 || (k_pad % 64) != 0)
+    return BVLM_EINVAL;
+  if (fmt != FMT_F16 && fmt != FMT_BF16) return BVLM_EINVAL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  constexpr int BN = 256;
+  CUtensorMap tmA, tmB;
+  Operand16 opA{A16, M, k_pad, fmt};
+  Operand16 opB{B16, N, k_pad, fmt};
+  int rc;
+  if ((rc = operand_tmap<GEMM_BM>(&tmA, opA))) return rc;
+  if ((rc = operand_tmap<BN>(&tmB, opB))) return rc;
+  GemmPlan plan = make_plan<BN>(static_cast<int>(M), static_cast<int>(N), static_cast<int>(k_pad), SCHED_TILES,
+                                split_k < 1 ? 1 : split_k, fmt, fmt);
+  EpiStoreF32<BN>::Params ep{D, ldd, alpha, plan.splits > 1 ? 1 : 0, 0, nullptr};
+  if (plan.splits > 1) {
+    BVLM_CUDA_TRY(cudaMemset2DAsync(D, static_cast<size_t>(ldd) * 4, 0, static_cast<size_t>(N) * 4, static_cast<size_t>(M), st));
+  }
+  return launch_gemm<BN, 4, EpiStoreF32<BN>>(tmA, tmB, plan, ep, st);
+}
+
+}  // extern "C"

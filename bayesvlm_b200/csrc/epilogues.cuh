@@ -1,0 +1,341 @@
+// Epilogue functors for gemm_engine.cuh. Each thread of the four epilogue warps owns ONE accumulator row of the
+// 128-row tile (row = 128*m + 32*ew + lane) and receives it 32 columns at a time in registers.
+#pragma once
+#include "gemm_engine.cuh"
+
+namespace bvlm {
+
+__device__ __forceinline__ int epi_row(const EpiCtx& ctx, const TileCoord& tc) {
+  return tc.m * GEMM_BM + ctx.ew * 32 + ctx.lane;
+}
+
+// Store 32 consecutive fp32 of one row; vectorised when the slice is complete and 16-byte aligned.
+__device__ __forceinline__ void store_row32_f32(float* dst, const float (&v)[32], int n_valid, bool aligned16) {
+  if (n_valid >= 32 && aligned16) {
+    float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) __stcs(d4 + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < n_valid) __stcs(dst + j, v[j]);
+  }
+}
+__device__ __forceinline__ void store_row32_f16(__half* dst, const float (&v)[32], int n_valid, bool aligned16) {
+  if (n_valid >= 32 && aligned16) {
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      __half2 h0 = __floats2half2_rn(v[8 * j + 0], v[8 * j + 1]);
+      __half2 h1 = __floats2half2_rn(v[8 * j + 2], v[8 * j + 3]);
+      __half2 h2 = __floats2half2_rn(v[8 * j + 4], v[8 * j + 5]);
+      __half2 h3 = __floats2half2_rn(v[8 * j + 6], v[8 * j + 7]);
+      uint4 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&h0);
+      pk.y = *reinterpret_cast<uint32_t*>(&h1);
+      pk.z = *reinterpret_cast<uint32_t*>(&h2);
+      pk.w = *reinterpret_cast<uint32_t*>(&h3);
+      d4[j] = pk;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < n_valid) dst[j] = __float2half_rn(v[j]);
+  }
+}
+
+// After the call, v[0] of lane j holds sum over the 32 lanes of their v[j] (31 shuffles).
+__device__ __forceinline__ float warp_transpose_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = upper ? v[i] : v[i + off];
+      const float keep = upper ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Plain fp32 output:  C = alpha * acc   (store)   or   C += alpha * acc   (red.global.add; split-K, SYRK)
+// mirror=1 additionally accumulates the transposed element for off-diagonal tiles (lower-triangle SYRK).
+// ---------------------------------------------------------------------------------------------
+template <int BN>
+struct EpiStoreF32 {
+  static constexpr size_t SCRATCH_BYTES = 16;
+  struct Params {
+    float* C;
+    int64_t ldc;
+    float alpha;
+    int atomic;
+    int mirror;
+    const float* alpha_dev;  // optional device scalar multiplied into alpha
+  };
+  struct State {
+    float alpha;
+  };
+  __device__ static void item_begin(State& st, const Params& p, const EpiCtx&, const TileCoord&) {
+    st.alpha = p.alpha_dev != nullptr ? p.alpha * (*p.alpha_dev) : p.alpha;
+  }
+  __device__ static void tile_begin(State&, const Params&, const EpiCtx&, const TileCoord&) {}
+  __device__ static void chunk(State& st, const Params& p, const EpiCtx& ctx, const TileCoord& tc, float (&v)[32], int c) {
+    const int row = epi_row(ctx, tc);
+    const int col0 = tc.n * BN + c * 32;
+    const int n_valid = ctx.N - col0;
+    if (row >= ctx.M) return;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= st.alpha;
+    float* dst = p.C + static_cast<int64_t>(row) * p.ldc + col0;
+    if (!p.atomic) {
+      store_row32_f32(dst, v, n_valid, (p.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < n_valid) red_add_f32(dst + j, v[j]);
+      if (p.mirror && tc.m != tc.n) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < n_valid) red_add_f32(p.C + static_cast<int64_t>(col0 + j) * p.ldc + row, v[j]);
+      }
+    }
+  }
+  __device__ static void tile_end(State&, const Params&, const EpiCtx&, const TileCoord&) {}
+  __device__ static void item_end(State&, const Params&, const EpiCtx&, const TileCoord&) {}
+};
+
+// ---------------------------------------------------------------------------------------------
+// Row sum of squares over all N tiles of a row panel:  out[row] = scale * rowscale[row] * sum_n acc[row,n]^2
+// (quadratic forms a^T A^-1 a evaluated as |G a|^2 with A^-1 = G^T G;  vlm.py:662-663)
+// ---------------------------------------------------------------------------------------------
+template <int BN>
+struct EpiRowSumSq {
+  static constexpr size_t SCRATCH_BYTES = 16;
+  struct Params {
+    float* out;
+    const float* row_scale;  // optional per-row multiplier (undoes the per-row power-of-two operand scaling)
+    float scale;
+  };
+  struct State {
+    float acc;
+  };
+  __device__ static void item_begin(State& st, const Params&, const EpiCtx&, const TileCoord&) { st.acc = 0.f; }
+  __device__ static void tile_begin(State&, const Params&, const EpiCtx&, const TileCoord&) {}
+  __device__ static void chunk(State& st, const Params&, const EpiCtx&, const TileCoord&, float (&v)[32], int) {
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+      s0 = fmaf(v[j], v[j], s0);
+      s1 = fmaf(v[j + 1], v[j + 1], s1);
+    }
+    st.acc += s0 + s1;
+  }
+  __device__ static void tile_end(State&, const Params&, const EpiCtx&, const TileCoord&) {}
+  __device__ static void item_end(State& st, const Params& p, const EpiCtx& ctx, const TileCoord& tc) {
+    const int row = epi_row(ctx, tc);
+    if (row < ctx.M) {
+      float r = st.acc * p.scale;
+      if (p.row_scale != nullptr) r *= p.row_scale[row];
+      p.out[row] = r;
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Kronecker-Laplace predictive (vlm.py:630-684, collapsed):
+//   mean_ij = mean_scale * acc_ij
+//   var_ij  = u_i * a_j + v_i * b_j
+// with u_i = s^2 p_i / E_i, v_i = s^2 alpha_i / E_i, a_j = gamma_j / E_j, b_j = (gamma_j kappa + q_j) / E_j.
+// ---------------------------------------------------------------------------------------------
+template <int BN>
+struct EpiPredictive {
+  static constexpr size_t SCRATCH_BYTES = 4 * 2 * BN * sizeof(float);  // per-warp copy of a_j / b_j of the tile
+  struct Params {
+    float* mean;
+    float* var;
+    int64_t ld;
+    const float* u;
+    const float* v;
+    const float* a;
+    const float* b;
+    float mean_scale;
+  };
+  struct State {
+    float u, v;
+  };
+  __device__ static void item_begin(State&, const Params&, const EpiCtx&, const TileCoord&) {}
+  __device__ static void tile_begin(State& st, const Params& p, const EpiCtx& ctx, const TileCoord& tc) {
+    const int row = epi_row(ctx, tc);
+    st.u = row < ctx.M ? p.u[row] : 0.f;
+    st.v = row < ctx.M ? p.v[row] : 0.f;
+    float* sa = ctx.scratch + ctx.ew * 2 * BN;
+    float* sb = sa + BN;
+    __syncwarp();
+    for (int i = ctx.lane; i < BN; i += 32) {
+      const int col = tc.n * BN + i;
+      sa[i] = col < ctx.N ? p.a[col] : 0.f;
+      sb[i] = col < ctx.N ? p.b[col] : 0.f;
+    }
+    __syncwarp();
+  }
+  __device__ static void chunk(State& st, const Params& p, const EpiCtx& ctx, const TileCoord& tc, float (&v)[32], int c) {
+    const int row = epi_row(ctx, tc);
+    const int col0 = tc.n * BN + c * 32;
+    const int n_valid = ctx.N - col0;
+    const float* sa = ctx.scratch + ctx.ew * 2 * BN + c * 32;
+    const float* sb = sa + BN;
+    float var[32];
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 a4 = *reinterpret_cast<const float4*>(sa + j);
+      const float4 b4 = *reinterpret_cast<const float4*>(sb + j);
+      var[j + 0] = fmaf(st.u, a4.x, st.v * b4.x);
+      var[j + 1] = fmaf(st.u, a4.y, st.v * b4.y);
+      var[j + 2] = fmaf(st.u, a4.z, st.v * b4.z);
+      var[j + 3] = fmaf(st.u, a4.w, st.v * b4.w);
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= p.mean_scale;
+    if (row >= ctx.M) return;
+    const bool al = (p.ld & 3) == 0 && (reinterpret_cast<uintptr_t>(p.mean) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(p.var) & 15) == 0;
+    const int64_t off = static_cast<int64_t>(row) * p.ld + col0;
+    store_row32_f32(p.mean + off, v, n_valid, al);
+    store_row32_f32(p.var + off, var, n_valid, al);
+  }
+  __device__ static void tile_end(State&, const Params&, const EpiCtx&, const TileCoord&) {}
+  __device__ static void item_end(State&, const Params&, const EpiCtx&, const TileCoord&) {}
+};
+
+// ---------------------------------------------------------------------------------------------
+// InfoNCE pass 1 (hessians.py:24-27): base-2 log-sum-exp of s * <x_b, y_c> over all targets, kept online
+// in registers across the N tiles of a row panel.   lse2[b] = log2 sum_c 2^(s*log2e*L_bc)
+// ---------------------------------------------------------------------------------------------
+template <int BN>
+struct EpiRowLse {
+  static constexpr size_t SCRATCH_BYTES = 16;
+  struct Params {
+    float* lse2;
+    float s_log2e;  // exp(logit_scale) * log2(e) / (operand scaling)
+  };
+  struct State {
+    float m, l;
+  };
+  __device__ static void item_begin(State& st, const Params&, const EpiCtx&, const TileCoord&) {
+    st.m = -INFINITY;
+    st.l = 0.f;
+  }
+  __device__ static void tile_begin(State&, const Params&, const EpiCtx&, const TileCoord&) {}
+  __device__ static void chunk(State& st, const Params& p, const EpiCtx& ctx, const TileCoord& tc, float (&v)[32], int c) {
+    const int n_valid = ctx.N - (tc.n * BN + c * 32);
+    float cm = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      v[j] = j < n_valid ? v[j] * p.s_log2e : -INFINITY;
+      cm = fmaxf(cm, v[j]);
+    }
+    const float m_new = fmaxf(st.m, cm);
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+      s0 += fast_exp2(v[j] - m_new);
+      s1 += fast_exp2(v[j + 1] - m_new);
+    }
+    st.l = st.l * fast_exp2(st.m - m_new) + (s0 + s1);
+    st.m = m_new;
+  }
+  __device__ static void tile_end(State&, const Params&, const EpiCtx&, const TileCoord&) {}
+  __device__ static void item_end(State& st, const Params& p, const EpiCtx& ctx, const TileCoord& tc) {
+    const int row = epi_row(ctx, tc);
+    if (row < ctx.M) p.lse2[row] = st.m + log2f(st.l);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// GGN pass 2. For every (source b, target c) the per-pair curvature weight
+//     InfoNCE : omega = softmax_c(s L_b.)            (hessians.py:27)
+//     SigLIP  : omega = sigma(z)(1 - sigma(z)), z = s L + bias   (hessians.py:88-94, without the s^2 factor)
+// is written as fp16 (scaled by WSCALE so that 1/C-sized probabilities stay normal numbers), together with
+// omega * L; the weighted column sums q_c = sum_b w_b omega_bc are reduced in registers across the M tiles of
+// a column panel and written once (no atomics).
+// ---------------------------------------------------------------------------------------------
+constexpr float GGN_WSCALE = 4096.f;
+
+template <int BN, bool SIGLIP>
+struct EpiGgnWeights {
+  static constexpr size_t SCRATCH_BYTES = 4 * BN * sizeof(float);
+  struct Params {
+    const float* lse2;  // InfoNCE only
+    const float* w;     // per-source weight (1/|x|^2, normalised)
+    __half* W16;        // [M_pad, ld] omega * WSCALE
+    __half* WL16;       // [M_pad, ld] omega * L * WSCALE
+    int64_t ld;
+    float* q;           // [N]
+    float s_log2e;      // InfoNCE: s*log2e/opscale ; SigLIP: s/opscale
+    float l_scale;      // 1/opscale: acc -> cosine
+    float bias;         // SigLIP logit bias
+  };
+  struct State {
+    float q[BN / 32];
+    float lse2, w;
+  };
+  __device__ static void item_begin(State& st, const Params&, const EpiCtx&, const TileCoord&) {
+#pragma unroll
+    for (int i = 0; i < BN / 32; ++i) st.q[i] = 0.f;
+  }
+  __device__ static void tile_begin(State& st, const Params& p, const EpiCtx& ctx, const TileCoord& tc) {
+    const int row = epi_row(ctx, tc);
+    st.w = row < ctx.M ? p.w[row] : 0.f;
+    if constexpr (!SIGLIP) st.lse2 = row < ctx.M ? p.lse2[row] : 0.f;
+  }
+  __device__ static void chunk(State& st, const Params& p, const EpiCtx& ctx, const TileCoord& tc, float (&v)[32], int c) {
+    const int row = epi_row(ctx, tc);
+    const int col0 = tc.n * BN + c * 32;
+    const int n_valid = ctx.N - col0;
+    const bool row_ok = row < ctx.M;
+    float om[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float o;
+      if constexpr (SIGLIP) {
+        const float z = fmaf(v[j], p.s_log2e, p.bias);
+        const float t = fast_exp2(-fabsf(z) * 1.4426950408889634f);
+        const float d = 1.f + t;
+        o = __fdividef(t, d * d);
+      } else {
+        o = fast_exp2(fmaf(v[j], p.s_log2e, -st.lse2));
+      }
+      om[j] = (row_ok && j < n_valid) ? o : 0.f;
+    }
+    if (row_ok) {
+      const bool al = (p.ld & 7) == 0;
+      const int64_t off = static_cast<int64_t>(row) * p.ld + col0;
+      float t[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) t[j] = om[j] * GGN_WSCALE;
+      store_row32_f16(p.W16 + off, t, n_valid, al);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) t[j] *= v[j] * p.l_scale;
+      store_row32_f16(p.WL16 + off, t, n_valid, al);
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) om[j] *= st.w;
+    st.q[c] += warp_transpose_reduce32(om, ctx.lane);
+  }
+  __device__ static void tile_end(State&, const Params&, const EpiCtx&, const TileCoord&) {}
+  __device__ static void item_end(State& st, const Params& p, const EpiCtx& ctx, const TileCoord& tc) {
+    float* s = ctx.scratch;
+    epi_bar_sync();
+#pragma unroll
+    for (int i = 0; i < BN / 32; ++i) s[ctx.ew * BN + i * 32 + ctx.lane] = st.q[i];
+    epi_bar_sync();
+    for (int i = ctx.ew * 32 + ctx.lane; i < BN; i += 128) {
+      const int col = tc.n * BN + i;
+      if (col < ctx.N) p.q[col] = s[i] + s[BN + i] + s[2 * BN + i] + s[3 * BN + i];
+    }
+  }
+};
+
+}  // namespace bvlm

@@ -1,0 +1,334 @@
+// Persistent, warp-specialised tcgen05 GEMM engine for sm_100a:  D[M,N] = A[M,K] * B[N,K]^T
+//
+//   * both operands are 16-bit (fp16 or bf16), K-major, row pitch a multiple of 16 bytes;
+//   * TMA (128-byte swizzle) stages 128 x 64 / BN x 64 operand tiles into a STAGES-deep smem ring;
+//   * one elected thread issues tcgen05.mma (M=128, N=BN, K=16) into a double-buffered TMEM accumulator;
+//   * four epilogue warps drain TMEM with tcgen05.ld (32 lanes x 32 columns at a time) and hand every
+//     32-column slice to a pluggable epilogue functor -- that is where the Laplace math lives
+//     (rank-2 variance, row sum-of-squares, online log-sum-exp, softmax/sigmoid weights, EPIG xlogy ...).
+//
+// The schedule is described by a GemmPlan: plain output tiles (optionally split along K, optionally only the
+// lower triangle for SYRK), row panels (one M-tile, all N-tiles: row reductions keep state in registers) or
+// column panels (one N-tile, all M-tiles: column reductions keep state in registers).
+#pragma once
+#include "common.cuh"
+#include "tmap.cuh"
+
+namespace bvlm {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_UMMA_K = 16;
+constexpr int GEMM_THREADS = 256;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps4-7 epilogue
+constexpr int GEMM_EPI_WARP0 = 4;
+constexpr int GEMM_AUX_BYTES = 256;
+
+enum SchedMode : int { SCHED_TILES = 0, SCHED_ROW_PANEL = 1, SCHED_COL_PANEL = 2, SCHED_TRI_TILES = 3 };
+
+struct GemmPlan {
+  int M;         // valid output rows
+  int N;         // valid output columns
+  int kb_total;  // number of 64-wide K blocks
+  int m_tiles;
+  int n_tiles;
+  int mode;      // SchedMode
+  int splits;    // split-K factor (SCHED_TILES / SCHED_TRI_TILES)
+  int tri_k;     // 1: operand B is lower triangular in (n,k) -> K loop stops at the diagonal block
+  uint32_t idesc;
+  int a_is_3d;       // 1: operand A is fetched through a 3-D map at (k, 0, m * a_outer_step)
+  int a_outer_step;  // rows (2-D) or outer-dimension items (3-D) consumed per M tile
+  uint32_t a_tx_bytes;
+  uint32_t b_tx_bytes;
+};
+
+struct TileCoord {
+  int m, n, kb0, kb1;
+};
+
+template <int BN>
+__host__ __device__ inline int plan_num_items(const GemmPlan& p) {
+  switch (p.mode) {
+    case SCHED_ROW_PANEL: return p.m_tiles;
+    case SCHED_COL_PANEL: return p.n_tiles;
+    case SCHED_TRI_TILES: return (p.m_tiles * (p.m_tiles + 1) / 2) * p.splits;
+    default: return p.m_tiles * p.n_tiles * p.splits;
+  }
+}
+template <int BN>
+__host__ __device__ inline int plan_inner(const GemmPlan& p) {
+  switch (p.mode) {
+    case SCHED_ROW_PANEL: return p.n_tiles;
+    case SCHED_COL_PANEL: return p.m_tiles;
+    default: return 1;
+  }
+}
+template <int BN>
+__device__ __forceinline__ TileCoord plan_tile(const GemmPlan& p, int item, int inner) {
+  TileCoord t;
+  int split = 0;
+  if (p.mode == SCHED_ROW_PANEL) {
+    t.m = item;
+    t.n = inner;
+  } else if (p.mode == SCHED_COL_PANEL) {
+    t.n = item;
+    t.m = inner;
+  } else if (p.mode == SCHED_TRI_TILES) {
+    const int tri = p.m_tiles * (p.m_tiles + 1) / 2;
+    const int idx = item % tri;
+    split = item / tri;
+    int m = static_cast<int>((sqrtf(8.0f * static_cast<float>(idx) + 1.0f) - 1.0f) * 0.5f);
+    while ((m + 1) * (m + 2) / 2 <= idx) ++m;
+    while (m * (m + 1) / 2 > idx) --m;
+    t.m = m;
+    t.n = idx - m * (m + 1) / 2;
+  } else {
+    const int tiles = p.m_tiles * p.n_tiles;
+    const int idx = item % tiles;
+    split = item / tiles;
+    t.m = idx / p.n_tiles;
+    t.n = idx % p.n_tiles;
+  }
+  int kb_end = p.kb_total;
+  if (p.tri_k) {
+    const int lim = ((t.n + 1) * BN + GEMM_BK - 1) / GEMM_BK;
+    kb_end = lim < kb_end ? lim : kb_end;
+  }
+  t.kb0 = static_cast<int>(static_cast<long long>(split) * kb_end / p.splits);
+  t.kb1 = static_cast<int>(static_cast<long long>(split + 1) * kb_end / p.splits);
+  return t;
+}
+
+// Per-thread view the epilogue functors get.
+struct EpiCtx {
+  int ew;          // epilogue warp 0..3 (== TMEM lane quadrant)
+  int lane;        // lane in warp
+  int M, N;        // valid extents
+  float* scratch;  // Epi::SCRATCH_BYTES of shared memory, shared by the four epilogue warps
+};
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+template <int BN, int STAGES, class Epi>
+constexpr size_t gemm_smem_bytes() {
+  return 1024 + static_cast<size_t>(STAGES) * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) + GEMM_AUX_BYTES +
+         Epi::SCRATCH_BYTES;
+}
+
+template <int BN, int STAGES, class Epi>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmPlan plan,
+               const typename Epi::Params ep) {
+  static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN must be a multiple of 32 in [32,256]");
+  constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+  constexpr int B_BYTES = BN * GEMM_BK * 2;
+  constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_BYTES;
+  uint8_t* aux = sB + STAGES * B_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* scratch = reinterpret_cast<float*>(aux + GEMM_AUX_BYTES);
+  static_assert((2 * STAGES + 4) * 8 + 4 <= GEMM_AUX_BYTES, "aux region too small");
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_items = plan_num_items<BN>(plan);
+  const int n_inner = plan_inner<BN>(plan);
+
+  if (warp == 0) {
+    // ------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        for (int inner = 0; inner < n_inner; ++inner) {
+          const TileCoord tc = plan_tile<BN>(plan, item, inner);
+          for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            mbar_arrive_expect_tx(&full_bar[stage], plan.a_tx_bytes + plan.b_tx_bytes);
+            if (plan.a_is_3d) {
+              tma_load_3d(sA + stage * A_BYTES, &tmA, &full_bar[stage], kb * GEMM_BK, 0, tc.m * plan.a_outer_step);
+            } else {
+              tma_load_2d(sA + stage * A_BYTES, &tmA, &full_bar[stage], kb * GEMM_BK, tc.m * plan.a_outer_step);
+            }
+            tma_load_2d(sB + stage * B_BYTES, &tmB, &full_bar[stage], kb * GEMM_BK, tc.n * BN);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer (single thread)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        for (int inner = 0; inner < n_inner; ++inner) {
+          const TileCoord tc = plan_tile<BN>(plan, item, inner);
+          mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BN);
+          for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint64_t da = make_smem_desc_kmajor_sw128(smem_u32(sA + stage * A_BYTES));
+            const uint64_t db = make_smem_desc_kmajor_sw128(smem_u32(sB + stage * B_BYTES));
+#pragma unroll
+            for (int k = 0; k < GEMM_BK / GEMM_UMMA_K; ++k) {
+              // advance 16 elements (32 bytes) along K inside the 128-byte swizzle atom: +2 in 16-byte units
+              umma_f16_ss(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), plan.idesc,
+                          (kb > tc.kb0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+          umma_commit(&tfull_bar[acc]);
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp >= GEMM_EPI_WARP0) {
+    // ------------------------------------------------ epilogue warps
+    EpiCtx ctx;
+    ctx.ew = warp - GEMM_EPI_WARP0;
+    ctx.lane = lane;
+    ctx.M = plan.M;
+    ctx.N = plan.N;
+    ctx.scratch = scratch;
+    typename Epi::State st;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      Epi::item_begin(st, ep, ctx, plan_tile<BN>(plan, item, 0));
+      for (int inner = 0; inner < n_inner; ++inner) {
+        const TileCoord tc = plan_tile<BN>(plan, item, inner);
+        Epi::tile_begin(st, ep, ctx, tc);
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ctx.ew * 32) << 16) + static_cast<uint32_t>(acc * BN);
+        const int n_valid = plan.N - tc.n * BN;
+#pragma unroll
+        for (int c = 0; c < BN / 32; ++c) {
+          if (c * 32 >= n_valid) break;
+          float v[32];
+          tmem_ld_32x32(taddr + static_cast<uint32_t>(c * 32), v);
+          tmem_ld_wait();
+          Epi::chunk(st, ep, ctx, tc, v, c);
+        }
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[acc]);
+        Epi::tile_end(st, ep, ctx, tc);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+      Epi::item_end(st, ep, ctx, plan_tile<BN>(plan, item, 0));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-side launch helper
+// ---------------------------------------------------------------------------------------------
+template <int BN>
+inline GemmPlan make_plan(int M, int N, int K_padded, int mode, int splits, int a_fmt, int b_fmt) {
+  GemmPlan p{};
+  p.M = M;
+  p.N = N;
+  p.kb_total = K_padded / GEMM_BK;
+  p.m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
+  p.n_tiles = (N + BN - 1) / BN;
+  p.mode = mode;
+  p.splits = splits < 1 ? 1 : splits;
+  if (p.splits > p.kb_total) p.splits = p.kb_total;
+  p.tri_k = 0;
+  p.idesc = make_idesc_f16(GEMM_BM, BN, a_fmt, b_fmt);
+  p.a_is_3d = 0;
+  p.a_outer_step = GEMM_BM;
+  p.a_tx_bytes = GEMM_BM * GEMM_BK * 2;
+  p.b_tx_bytes = BN * GEMM_BK * 2;
+  return p;
+}
+
+template <int BN, int STAGES, class Epi>
+inline int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmPlan& plan,
+                       const typename Epi::Params& ep, cudaStream_t stream) {
+  if (plan.kb_total <= 0 || plan.M <= 0 || plan.N <= 0) return BVLM_EINVAL;
+  constexpr size_t smem = gemm_smem_bytes<BN, STAGES, Epi>();
+  static_assert(smem <= 232448, "shared memory budget exceeded");
+  auto kfn = gemm_tn_kernel<BN, STAGES, Epi>;
+  static bool configured = false;  // per instantiation
+  if (!configured) {
+    BVLM_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    configured = true;
+  }
+  const int items = plan_num_items<BN>(plan);
+  int grid = device_sm_count();
+  if (items < grid) grid = items;
+  kfn<<<grid, GEMM_THREADS, smem, stream>>>(tmA, tmB, plan, ep);
+  count_launch();
+  BVLM_CUDA_TRY(cudaGetLastError());
+  return BVLM_OK;
+}
+
+// 16-bit K-major operand descriptor handed around on the host.
+struct Operand16 {
+  const void* ptr;
+  int64_t rows;    // valid rows
+  int64_t k_pad;   // padded K (multiple of 64); also the row pitch in elements
+  int fmt;         // OperandFormat
+};
+
+template <int BOX_ROWS>
+inline int operand_tmap(CUtensorMap* out, const Operand16& op) {
+  return make_tmap_2d(out, op.ptr, op.fmt == FMT_BF16 ? TM_BF16 : TM_F16, static_cast<uint64_t>(op.k_pad),
+                      static_cast<uint64_t>(op.rows), static_cast<uint64_t>(op.k_pad) * 2, GEMM_BK, BOX_ROWS, 1);
+}
+
+}  // namespace bvlm

@@ -1,0 +1,274 @@
+// K1 / K2 / K3: KFAC factor kernels.
+//   K1  A += X^T X                       scripts/hessian_estimation.py:99-104
+//   K2  InfoNCE GGN w.r.t. embeddings    bayesvlm/hessians.py:10-48
+//   K3  SigLIP  GGN w.r.t. embeddings    bayesvlm/hessians.py:50-117
+//
+// K2/K3 never form the reference's [B,D,D] / [B,C,D] / [chunk,D,D] temporaries.  With L = Xh Yh^T (cosines),
+// omega = softmax(sL) (InfoNCE) or sigma(z)(1-sigma(z)) (SigLIP), w_b = 1/|x_b|^2:
+//   q = sum_b w_b omega_b.          m = omega Yh          r = (omega .* L) Yh
+//   t_b = m_b.xh_b    u_b = r_b - m_b t_b  (InfoNCE)  |  u_b = r_b (SigLIP)     a_b = u_b.xh_b
+//   H = s^2 [ Yh^T diag(q) Yh - (w m)^T m - (w xh)^T u - (w u)^T xh + (w a xh)^T xh ]
+// which is four tensor-core GEMM passes over the class batch plus one stacked [D x (C+4B)] x [(C+4B) x D] GEMM.
+#include "epilogues.cuh"
+#include "prep.cuh"
+
+using namespace bvlm;
+
+namespace {
+
+constexpr int GGN_BN = 256;
+constexpr int GGN_STAGES = 4;
+constexpr int SYRK_BN = 128;
+constexpr int SYRK_STAGES = 6;
+constexpr float GGN_OPSCALE = 256.f;  // unit vectors -> fp16
+constexpr float GGN_G = 16.f;         // scale of the stacked final-GEMM operands
+
+inline int64_t pad64(int64_t k) { return round_up_i64(k, 64); }
+inline int64_t pad128(int64_t k) { return round_up_i64(k, 128); }
+
+struct Carver {
+  uint8_t* base;
+  size_t off = 0;
+  explicit Carver(void* p) : base(static_cast<uint8_t*>(p)) {}
+  template <class T>
+  T* take(size_t count) {
+    off = (off + 255) & ~static_cast<size_t>(255);
+    T* r = reinterpret_cast<T*>(base + off);
+    off += count * sizeof(T);
+    return r;
+  }
+  size_t used() const { return (off + 255) & ~static_cast<size_t>(255); }
+};
+
+struct GgnLayout {
+  int64_t Dp, Cp, Bp, Bs, Ktot;
+  size_t bytes;
+  // offsets resolved by carve()
+  __half *Xh16, *Yh16, *YhT16, *W16, *L16, *R16;
+  float *inv_nx, *inv_ny, *w_raw, *w, *scalars, *lse2, *q, *mult_y, *mult_sw, *mult_x_sw, *mult_x_wa, *mult_x, *MR;
+};
+
+GgnLayout ggn_layout(int64_t B, int64_t C, int64_t D, int siglip, void* ws) {
+  GgnLayout g{};
+  g.Dp = pad64(D);
+  g.Cp = pad64(C);
+  g.Bp = pad64(B);
+  g.Bs = pad128(B);
+  g.Ktot = g.Cp + (siglip ? 3 : 4) * g.Bp;
+  Carver cv(ws);
+  g.Xh16 = cv.take<__half>(static_cast<size_t>(B) * g.Dp);
+  g.Yh16 = cv.take<__half>(static_cast<size_t>(C) * g.Dp);
+  g.YhT16 = cv.take<__half>(static_cast<size_t>(D) * g.Cp);
+  g.W16 = cv.take<__half>(static_cast<size_t>(2 * g.Bs) * g.Cp);
+  g.L16 = cv.take<__half>(static_cast<size_t>(D) * g.Ktot);
+  g.R16 = cv.take<__half>(static_cast<size_t>(D) * g.Ktot);
+  g.inv_nx = cv.take<float>(static_cast<size_t>(B));
+  g.inv_ny = cv.take<float>(static_cast<size_t>(C));
+  g.w_raw = cv.take<float>(static_cast<size_t>(B));
+  g.w = cv.take<float>(static_cast<size_t>(B));
+  g.scalars = cv.take<float>(64);
+  g.lse2 = cv.take<float>(static_cast<size_t>(B));
+  g.q = cv.take<float>(static_cast<size_t>(C));
+  g.mult_y = cv.take<float>(static_cast<size_t>(C));
+  g.mult_sw = cv.take<float>(static_cast<size_t>(B));
+  g.mult_x_sw = cv.take<float>(static_cast<size_t>(B));
+  g.mult_x_wa = cv.take<float>(static_cast<size_t>(B));
+  g.mult_x = cv.take<float>(static_cast<size_t>(B));
+  g.MR = cv.take<float>(static_cast<size_t>(2 * g.Bs) * D);
+  g.bytes = cv.used() + 256;
+  return g;
+}
+
+__global__ void k_mean_weight(const float* __restrict__ w_sum, float inv_count, float* __restrict__ wbar) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) *wbar = *w_sum * inv_count;
+}
+
+int ggn_impl(const float* X, int64_t B, int64_t ldx, const float* Y, int64_t C, int64_t ldy, int64_t D, float logit_scale,
+             float logit_bias, int siglip, float* H, int64_t ldh, int accumulate, void* ws, size_t ws_bytes,
+             cudaStream_t st) {
+  if (X == nullptr || Y == nullptr || H == nullptr || ws == nullptr) return BVLM_EINVAL;
+  if (B <= 0 || C <= 0 || D <= 0 || ldx < D || ldy < D || ldh < D) return BVLM_EINVAL;
+  if (B > (1 << 30) || C > (1 << 30)) return BVLM_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(ws) & 255) != 0) return BVLM_EINVAL;
+  GgnLayout g = ggn_layout(B, C, D, siglip, ws);
+  if (ws_bytes < g.bytes) return BVLM_EWORKSPACE;
+  int rc;
+  const float s = expf(logit_scale);
+  const float op2 = GGN_OPSCALE * GGN_OPSCALE;
+
+  if (!accumulate) {
+    BVLM_CUDA_TRY(cudaMemset2DAsync(H, static_cast<size_t>(ldh) * 4, 0, static_cast<size_t>(D) * 4, static_cast<size_t>(D), st));
+  }
+  BVLM_CUDA_TRY(cudaMemsetAsync(g.scalars, 0, 64 * sizeof(float), st));
+  float* w_sum = g.scalars;
+  float* wbar = g.scalars + 1;
+
+  // ---- operand preparation
+  if ((rc = launch_ggn_row_prep(X, B, D, ldx, GGN_OPSCALE, g.Xh16, g.Dp, g.inv_nx, g.w_raw, w_sum, st))) return rc;
+  if ((rc = launch_ggn_row_prep(Y, C, D, ldy, GGN_OPSCALE, g.Yh16, g.Dp, g.inv_ny, nullptr, nullptr, st))) return rc;
+  if ((rc = launch_normalize_weights(g.w_raw, w_sum, B, g.w, st))) return rc;
+  k_mean_weight<<<1, 32, 0, st>>>(w_sum, 1.0f / static_cast<float>(B), wbar);
+  count_launch();
+  if ((rc = launch_transpose_to_16(Y, C, D, ldy, g.inv_ny, 0, nullptr, GGN_OPSCALE, 0, FMT_F16, g.YhT16, g.Cp, 0, g.Cp, st)))
+    return rc;
+
+  CUtensorMap tmX, tmY;
+  Operand16 opX{g.Xh16, B, g.Dp, FMT_F16};
+  Operand16 opY{g.Yh16, C, g.Dp, FMT_F16};
+  if ((rc = operand_tmap<GEMM_BM>(&tmX, opX))) return rc;
+  if ((rc = operand_tmap<GGN_BN>(&tmY, opY))) return rc;
+
+  // ---- pass 1 (InfoNCE only): row log-sum-exp
+  if (!siglip) {
+    GemmPlan p1 = make_plan<GGN_BN>(static_cast<int>(B), static_cast<int>(C), static_cast<int>(g.Dp), SCHED_ROW_PANEL, 1,
+                                    FMT_F16, FMT_F16);
+    EpiRowLse<GGN_BN>::Params e1{g.lse2, s * 1.4426950408889634f / op2};
+    if ((rc = launch_gemm<GGN_BN, GGN_STAGES, EpiRowLse<GGN_BN>>(tmX, tmY, p1, e1, st))) return rc;
+  }
+
+  // ---- pass 2: curvature weights omega (fp16), omega*L (fp16), q
+  __half* W16 = g.W16;
+  __half* WL16 = g.W16 + static_cast<size_t>(g.Bs) * g.Cp;
+  {
+    GemmPlan p2 = make_plan<GGN_BN>(static_cast<int>(B), static_cast<int>(C), static_cast<int>(g.Dp), SCHED_COL_PANEL, 1,
+                                    FMT_F16, FMT_F16);
+    if (siglip) {
+      EpiGgnWeights<GGN_BN, true>::Params e2{nullptr, g.w, W16, WL16, g.Cp, g.q, s / op2, 1.0f / op2, logit_bias};
+      if ((rc = launch_gemm<GGN_BN, GGN_STAGES, EpiGgnWeights<GGN_BN, true>>(tmX, tmY, p2, e2, st))) return rc;
+    } else {
+      EpiGgnWeights<GGN_BN, false>::Params e2{g.lse2, g.w, W16, WL16, g.Cp, g.q, s * 1.4426950408889634f / op2,
+                                              1.0f / op2, 0.f};
+      if ((rc = launch_gemm<GGN_BN, GGN_STAGES, EpiGgnWeights<GGN_BN, false>>(tmX, tmY, p2, e2, st))) return rc;
+    }
+  }
+  if (g.Cp != C) {  // K padding of pass 3 must be exact zeros
+    BVLM_CUDA_TRY(cudaMemset2DAsync(W16 + C, static_cast<size_t>(g.Cp) * 2, 0, static_cast<size_t>(g.Cp - C) * 2,
+                                    static_cast<size_t>(B), st));
+    BVLM_CUDA_TRY(cudaMemset2DAsync(WL16 + C, static_cast<size_t>(g.Cp) * 2, 0, static_cast<size_t>(g.Cp - C) * 2,
+                                    static_cast<size_t>(B), st));
+  }
+
+  // ---- pass 3: [m ; r] = [omega ; omega*L] Yh      (M = Bs + B stacked rows, K = C)
+  {
+    CUtensorMap tmW, tmYT;
+    Operand16 opW{g.W16, g.Bs + B, g.Cp, FMT_F16};
+    Operand16 opYT{g.YhT16, D, g.Cp, FMT_F16};
+    if ((rc = operand_tmap<GEMM_BM>(&tmW, opW))) return rc;
+    if ((rc = operand_tmap<GGN_BN>(&tmYT, opYT))) return rc;
+    GemmPlan p3 = make_plan<GGN_BN>(static_cast<int>(g.Bs + B), static_cast<int>(D), static_cast<int>(g.Cp), SCHED_TILES, 1,
+                                    FMT_F16, FMT_F16);
+    EpiStoreF32<GGN_BN>::Params e3{g.MR, D, 1.0f, 0, 0, nullptr};
+    if ((rc = launch_gemm<GGN_BN, GGN_STAGES, EpiStoreF32<GGN_BN>>(tmW, tmYT, p3, e3, st))) return rc;
+  }
+
+  // ---- per-row finalisation and stacked operands
+  float* Mm = g.MR;
+  float* Ru = g.MR + static_cast<size_t>(g.Bs) * D;
+  if ((rc = launch_ggn_row_finalize(X, B, D, ldx, g.inv_nx, g.w, Mm, Ru, D, 1.0f / (GGN_WSCALE * GGN_OPSCALE), siglip,
+                                    GGN_G, g.mult_sw, g.mult_x_sw, g.mult_x_wa, g.mult_x, st)))
+    return rc;
+  if ((rc = launch_ggn_col_mult(g.q, g.inv_ny, C, GGN_G, g.mult_y, st))) return rc;
+
+  const int64_t K = g.Ktot;
+  int64_t off = 0;
+  // seg 0: Yh^T diag(q) Yh
+  if ((rc = launch_transpose_to_16(Y, C, D, ldy, g.mult_y, 0, nullptr, 1.f, 0, FMT_F16, g.L16, K, off, g.Cp, st))) return rc;
+  if ((rc = launch_transpose_to_16(Y, C, D, ldy, g.mult_y, 0, nullptr, 1.f, 0, FMT_F16, g.R16, K, off, g.Cp, st))) return rc;
+  off += g.Cp;
+  if (!siglip) {  // seg 1: -(w m)^T m
+    if ((rc = launch_transpose_to_16(Mm, B, D, D, g.mult_sw, 0, nullptr, -1.f, 0, FMT_F16, g.L16, K, off, g.Bp, st))) return rc;
+    if ((rc = launch_transpose_to_16(Mm, B, D, D, g.mult_sw, 0, nullptr, 1.f, 0, FMT_F16, g.R16, K, off, g.Bp, st))) return rc;
+    off += g.Bp;
+  }
+  // seg 2: -(w xh)^T u
+  if ((rc = launch_transpose_to_16(X, B, D, ldx, g.mult_x_sw, 0, nullptr, -1.f, 0, FMT_F16, g.L16, K, off, g.Bp, st))) return rc;
+  if ((rc = launch_transpose_to_16(Ru, B, D, D, g.mult_sw, 0, nullptr, 1.f, 0, FMT_F16, g.R16, K, off, g.Bp, st))) return rc;
+  off += g.Bp;
+  // seg 3: -(w u)^T xh
+  if ((rc = launch_transpose_to_16(Ru, B, D, D, g.mult_sw, 0, nullptr, -1.f, 0, FMT_F16, g.L16, K, off, g.Bp, st))) return rc;
+  if ((rc = launch_transpose_to_16(X, B, D, ldx, g.mult_x_sw, 0, nullptr, 1.f, 0, FMT_F16, g.R16, K, off, g.Bp, st))) return rc;
+  off += g.Bp;
+  // seg 4: (w a xh)^T xh
+  if ((rc = launch_transpose_to_16(X, B, D, ldx, g.mult_x_wa, 0, nullptr, 1.f, 0, FMT_F16, g.L16, K, off, g.Bp, st))) return rc;
+  if ((rc = launch_transpose_to_16(X, B, D, ldx, g.mult_x, 0, nullptr, 1.f, 0, FMT_F16, g.R16, K, off, g.Bp, st))) return rc;
+  off += g.Bp;
+
+  // ---- final stacked GEMM, split along K, accumulated into H with red.global.add
+  {
+    CUtensorMap tmL, tmR;
+    Operand16 opL{g.L16, D, K, FMT_F16};
+    Operand16 opR{g.R16, D, K, FMT_F16};
+    if ((rc = operand_tmap<GEMM_BM>(&tmL, opL))) return rc;
+    if ((rc = operand_tmap<GGN_BN>(&tmR, opR))) return rc;
+    const int tiles = static_cast<int>(ceil_div_i64(D, GEMM_BM) * ceil_div_i64(D, GGN_BN));
+    int splits = device_sm_count() / tiles;
+    if (splits < 1) splits = 1;
+    GemmPlan p4 = make_plan<GGN_BN>(static_cast<int>(D), static_cast<int>(D), static_cast<int>(K), SCHED_TILES, splits,
+                                    FMT_F16, FMT_F16);
+    EpiStoreF32<GGN_BN>::Params e4{H, ldh, s * s / (GGN_G * GGN_G), 1, 0, wbar};
+    if ((rc = launch_gemm<GGN_BN, GGN_STAGES, EpiStoreF32<GGN_BN>>(tmL, tmR, p4, e4, st))) return rc;
+  }
+  return BVLM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t bvlm_syrk_workspace_bytes(int64_t n, int64_t d, int append_one, int precision) {
+  (void)precision;
+  const int64_t dA = d + (append_one ? 1 : 0);
+  return static_cast<size_t>(round_up_i64(dA * pad64(n) * 2, 256)) + 512;
+}
+
+int bvlm_syrk_f32acc(const float* X, int64_t n, int64_t d, int64_t ldx, int append_one, int precision, float* C,
+                     int64_t ldc, float alpha, int accumulate, void* ws, size_t ws_bytes, void* stream) {
+  if (X == nullptr || C == nullptr || ws == nullptr || n <= 0 || d <= 0 || ldx < d) return BVLM_EINVAL;
+  if (precision != BVLM_PREC_X1) return BVLM_ENOTSUP;
+  const int64_t dA = d + (append_one ? 1 : 0);
+  if (ldc < dA) return BVLM_EINVAL;
+  if (ws_bytes < bvlm_syrk_workspace_bytes(n, d, append_one, precision)) return BVLM_EWORKSPACE;
+  if ((reinterpret_cast<uintptr_t>(ws) & 255) != 0) return BVLM_EINVAL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t Kp = pad64(n);
+  void* Xt16 = ws;
+  int rc;
+  if (!accumulate) {
+    BVLM_CUDA_TRY(cudaMemset2DAsync(C, static_cast<size_t>(ldc) * 4, 0, static_cast<size_t>(dA) * 4, static_cast<size_t>(dA), st));
+  }
+  // [X 1]^T as a bf16 K-major operand: rows = features, K = samples
+  if ((rc = launch_transpose_to_16(X, n, d, ldx, nullptr, 0, nullptr, 1.f, append_one, FMT_BF16, Xt16, Kp, 0, Kp, st)))
+    return rc;
+  CUtensorMap tmA, tmB;
+  Operand16 op{Xt16, dA, Kp, FMT_BF16};
+  if ((rc = operand_tmap<GEMM_BM>(&tmA, op))) return rc;
+  if ((rc = operand_tmap<SYRK_BN>(&tmB, op))) return rc;
+  const int m_tiles = static_cast<int>(ceil_div_i64(dA, GEMM_BM));
+  const int tri = m_tiles * (m_tiles + 1) / 2;
+  int splits = device_sm_count() / tri;
+  if (splits < 1) splits = 1;
+  GemmPlan plan = make_plan<SYRK_BN>(static_cast<int>(dA), static_cast<int>(dA), static_cast<int>(Kp), SCHED_TRI_TILES,
+                                     splits, FMT_BF16, FMT_BF16);
+  EpiStoreF32<SYRK_BN>::Params ep{C, ldc, alpha, 1, 1, nullptr};
+  return launch_gemm<SYRK_BN, SYRK_STAGES, EpiStoreF32<SYRK_BN>>(tmA, tmB, plan, ep, st);
+}
+
+size_t bvlm_ggn_workspace_bytes(int64_t B, int64_t C, int64_t D) {
+  if (B <= 0 || C <= 0 || D <= 0) return 0;
+  return ggn_layout(B, C, D, 0, nullptr).bytes;
+}
+
+int bvlm_ggn_infonce(const float* X, int64_t B, int64_t ldx, const float* Y, int64_t C, int64_t ldy, int64_t D,
+                     float logit_scale, float* H, int64_t ldh, int accumulate, void* ws, size_t ws_bytes, void* stream) {
+  return ggn_impl(X, B, ldx, Y, C, ldy, D, logit_scale, 0.f, 0, H, ldh, accumulate, ws, ws_bytes,
+                  static_cast<cudaStream_t>(stream));
+}
+
+int bvlm_ggn_siglip(const float* X, int64_t B, int64_t ldx, const float* Y, int64_t C, int64_t ldy, int64_t D,
+                    float logit_scale, float logit_bias, float* H, int64_t ldh, int accumulate, void* ws,
+                    size_t ws_bytes, void* stream) {
+  return ggn_impl(X, B, ldx, Y, C, ldy, D, logit_scale, logit_bias, 1, H, ldh, accumulate, ws, ws_bytes,
+                  static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,162 @@
+// P1 / P2 / P3: quadratic forms, fused Kronecker-Laplace predictive GEMM, probit softmax.
+// Reference: bayesvlm/vlm.py:630-684 (CLIP._compute_probabilistic_logits_smith), scripts/zeroshot.py:119-120.
+#include "../../include/bvlm.h"
+#include "epilogues.cuh"
+#include "prep.cuh"
+
+using namespace bvlm;
+
+namespace {
+
+constexpr int PRED_BN = 256;
+constexpr int PRED_STAGES = 4;
+constexpr float PRED_OPSCALE = 256.f;  // unit-energy embeddings are scaled into the fp16 sweet spot
+
+struct Carver {
+  uint8_t* base;
+  size_t off = 0;
+  explicit Carver(void* p) : base(static_cast<uint8_t*>(p)) {}
+  template <class T>
+  T* take(size_t count) {
+    off = (off + 255) & ~static_cast<size_t>(255);
+    T* r = reinterpret_cast<T*>(base + off);
+    off += count * sizeof(T);
+    return r;
+  }
+  size_t used() const { return (off + 255) & ~static_cast<size_t>(255); }
+};
+
+inline int64_t pad64(int64_t k) { return round_up_i64(k, 64); }
+
+// out[i] = | W16 act16_i |^2  through the row-panel GEMM with the sum-of-squares epilogue.
+int quadform_impl(const float* act, int64_t n, int64_t d, int64_t ld, int append_one, const void* W16, int64_t dA,
+                  int64_t k_pad, float w_scale, float* out, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (n <= 0) return BVLM_OK;
+  if (dA != d + (append_one ? 1 : 0) || k_pad != pad64(dA)) return BVLM_EINVAL;
+  if (ws_bytes < bvlm_quadform_workspace_bytes(n, d, append_one)) return BVLM_EWORKSPACE;
+  Carver cv(ws);
+  __half* act16 = cv.take<__half>(static_cast<size_t>(n) * k_pad);
+  float* row_unscale = cv.take<float>(static_cast<size_t>(n));
+  int rc = launch_rows_to_16(act, n, d, ld, append_one, FMT_F16, 1, 1.0f, act16, k_pad, row_unscale, st);
+  if (rc) return rc;
+  CUtensorMap tmA, tmB;
+  Operand16 opA{act16, n, k_pad, FMT_F16};
+  Operand16 opB{W16, dA, k_pad, FMT_F16};
+  if ((rc = operand_tmap<GEMM_BM>(&tmA, opA))) return rc;
+  if ((rc = operand_tmap<PRED_BN>(&tmB, opB))) return rc;
+  GemmPlan plan = make_plan<PRED_BN>(static_cast<int>(n), static_cast<int>(dA), static_cast<int>(k_pad), SCHED_ROW_PANEL,
+                                     1, FMT_F16, FMT_F16);
+  plan.tri_k = 1;
+  EpiRowSumSq<PRED_BN>::Params ep{out, row_unscale, 1.0f / (w_scale * w_scale)};
+  return launch_gemm<PRED_BN, PRED_STAGES, EpiRowSumSq<PRED_BN>>(tmA, tmB, plan, ep, st);
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t bvlm_padded_k(int64_t k) { return pad64(k); }
+
+int bvlm_factor_prepare(const float* W, int64_t dA, int64_t ldw, float w_scale, void* W16, int64_t k_pad, void* stream) {
+  if (W == nullptr || W16 == nullptr || dA <= 0 || k_pad != pad64(dA)) return BVLM_EINVAL;
+  return launch_rows_to_16(W, dA, dA, ldw, 0, FMT_F16, 0, w_scale, W16, k_pad, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+size_t bvlm_quadform_workspace_bytes(int64_t n, int64_t d, int append_one) {
+  const int64_t k_pad = pad64(d + (append_one ? 1 : 0));
+  size_t b = 0;
+  b += round_up_i64(static_cast<int64_t>(n) * k_pad * 2, 256) + 256;
+  b += round_up_i64(static_cast<int64_t>(n) * 4, 256) + 256;
+  return b;
+}
+
+int bvlm_quadform(const float* act, int64_t n, int64_t d, int64_t ld, int append_one, const void* W16, int64_t dA,
+                  int64_t k_pad, float w_scale, float* out, void* ws, size_t ws_bytes, void* stream) {
+  if (act == nullptr || W16 == nullptr || out == nullptr || ws == nullptr) return BVLM_EINVAL;
+  return quadform_impl(act, n, d, ld, append_one, W16, dA, k_pad, w_scale, out, ws, ws_bytes,
+                       static_cast<cudaStream_t>(stream));
+}
+
+size_t bvlm_predictive_target_workspace_bytes(int64_t C, int64_t D, int64_t d_act, int append_one) {
+  (void)D;
+  return bvlm_quadform_workspace_bytes(C, d_act, append_one) + round_up_i64(C * 4, 256) + 512;
+}
+
+int bvlm_predictive_target_prepare(const float* T, int64_t C, int64_t D, int64_t ldt, const float* Tact, int64_t d_act,
+                                   int64_t ldact, int append_one, const void* Wt16, int64_t dA, int64_t k_pad,
+                                   float w_scale, const float* beta, float sum_delta, float kappa, int precision,
+                                   void* T16, float* colA, float* colB, void* ws, size_t ws_bytes, void* stream) {
+  if (T == nullptr || Tact == nullptr || Wt16 == nullptr || beta == nullptr || T16 == nullptr || colA == nullptr ||
+      colB == nullptr || ws == nullptr)
+    return BVLM_EINVAL;
+  if (precision != BVLM_PREC_X1 && precision != BVLM_PREC_X3) return BVLM_EINVAL;
+  if (ws_bytes < bvlm_predictive_target_workspace_bytes(C, D, d_act, append_one)) return BVLM_EWORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Carver cv(ws);
+  float* gamma = cv.take<float>(static_cast<size_t>(C));
+  const size_t used = cv.used();
+  int rc = quadform_impl(Tact, C, d_act, ldact, append_one, Wt16, dA, k_pad, w_scale, gamma,
+                         static_cast<uint8_t*>(ws) + used, ws_bytes - used, st);
+  if (rc) return rc;
+  // side 1: out0 = gamma/E, out1 = (gamma*kappa + sum_d beta_d t_d^2)/E ; E = |t|^2 + gamma * sum(delta)
+  return launch_predictive_row_prep(T, C, D, ldt, gamma, beta, sum_delta, kappa, 0.f, /*side=*/1, precision,
+                                    PRED_OPSCALE, static_cast<__half*>(T16), pad64(D), colA, colB, st);
+}
+
+size_t bvlm_predictive_workspace_bytes(int64_t N, int64_t D, int64_t d_act, int append_one, int precision) {
+  size_t b = bvlm_quadform_workspace_bytes(N, d_act, append_one);
+  b += 3 * (round_up_i64(N * 4, 256) + 256);
+  b += round_up_i64(N * pad64(D) * precision * 2, 256) + 256;
+  return b;
+}
+
+int bvlm_predictive(const float* E, int64_t N, int64_t D, int64_t lde, const float* Eact, int64_t d_act, int64_t ldact,
+                    int append_one, const void* Wi16, int64_t dA, int64_t k_pad, float w_scale, const float* delta,
+                    float sum_beta, float logit_scale, const void* T16, const float* colA, const float* colB, int64_t C,
+                    int precision, float* mean, float* var, float* probs, int64_t ldo, void* ws, size_t ws_bytes,
+                    void* stream) {
+  if (E == nullptr || Eact == nullptr || Wi16 == nullptr || delta == nullptr || T16 == nullptr || colA == nullptr ||
+      colB == nullptr || mean == nullptr || var == nullptr || ws == nullptr)
+    return BVLM_EINVAL;
+  if (precision != BVLM_PREC_X1 && precision != BVLM_PREC_X3) return BVLM_EINVAL;
+  if (N <= 0 || C <= 0) return BVLM_OK;
+  if (ldo < C || N > 0x7fffffff || C > 0x7fffffff) return BVLM_EINVAL;
+  if (ws_bytes < bvlm_predictive_workspace_bytes(N, D, d_act, append_one, precision)) return BVLM_EWORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t seg = pad64(D);
+  const int64_t kp = seg * precision;
+  Carver cv(ws);
+  float* alpha = cv.take<float>(static_cast<size_t>(N));
+  float* rowU = cv.take<float>(static_cast<size_t>(N));
+  float* rowV = cv.take<float>(static_cast<size_t>(N));
+  __half* E16 = cv.take<__half>(static_cast<size_t>(N) * kp);
+  const size_t used = cv.used();
+  int rc = quadform_impl(Eact, N, d_act, ldact, append_one, Wi16, dA, k_pad, w_scale, alpha,
+                         static_cast<uint8_t*>(ws) + used, ws_bytes - used, st);
+  if (rc) return rc;
+  const float s = expf(logit_scale);
+  // side 0: out0 = s^2 (sum_d e_d^2 delta_d)/E, out1 = s^2 alpha/E ; E = |e|^2 + alpha * sum(beta)
+  rc = launch_predictive_row_prep(E, N, D, lde, alpha, delta, sum_beta, 0.f, s * s, /*side=*/0, precision, PRED_OPSCALE,
+                                  E16, seg, rowU, rowV, st);
+  if (rc) return rc;
+  CUtensorMap tmA, tmB;
+  Operand16 opA{E16, N, kp, FMT_F16};
+  Operand16 opB{T16, C, kp, FMT_F16};
+  if ((rc = operand_tmap<GEMM_BM>(&tmA, opA))) return rc;
+  if ((rc = operand_tmap<PRED_BN>(&tmB, opB))) return rc;
+  GemmPlan plan = make_plan<PRED_BN>(static_cast<int>(N), static_cast<int>(C), static_cast<int>(kp), SCHED_TILES, 1,
+                                     FMT_F16, FMT_F16);
+  EpiPredictive<PRED_BN>::Params ep{mean, var, ldo, rowU, rowV, colA, colB, s / (PRED_OPSCALE * PRED_OPSCALE)};
+  rc = launch_gemm<PRED_BN, PRED_STAGES, EpiPredictive<PRED_BN>>(tmA, tmB, plan, ep, st);
+  if (rc) return rc;
+  if (probs != nullptr) rc = launch_probit_softmax(mean, var, N, C, ldo, probs, st);
+  return rc;
+}
+
+int bvlm_probit_softmax(const float* mean, const float* var, int64_t N, int64_t C, int64_t ld, float* probs,
+                        void* stream) {
+  if (mean == nullptr || var == nullptr || probs == nullptr || ld < C) return BVLM_EINVAL;
+  return launch_probit_softmax(mean, var, N, C, ld, probs, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

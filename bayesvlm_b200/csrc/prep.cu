@@ -1,0 +1,405 @@
+#include "prep.cuh"
+
+namespace bvlm {
+
+namespace {
+
+constexpr int WARPS_PER_BLOCK = 8;
+constexpr int ROW_BLOCK = WARPS_PER_BLOCK * 32;
+
+__device__ __forceinline__ uint16_t to_16(float v, int fmt) {
+  if (fmt == FMT_BF16) {
+    __nv_bfloat16 b = __float2bfloat16_rn(v);
+    return *reinterpret_cast<uint16_t*>(&b);
+  }
+  __half h = __float2half_rn(v);
+  return *reinterpret_cast<uint16_t*>(&h);
+}
+
+inline unsigned row_grid(int64_t R) { return static_cast<unsigned>((R + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK); }
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ROW_BLOCK) k_rows_to_16(const float* __restrict__ in, int64_t R, int64_t d, int64_t ld,
+                                                          int append_one, int fmt, int row_pow2_scale, float gmult,
+                                                          uint16_t* __restrict__ out, int64_t k_pad,
+                                                          float* __restrict__ row_unscale) {
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= R) return;
+  const float* x = in + row * ld;
+  float sc = gmult;
+  if (row_pow2_scale) {
+    float amax = append_one ? 1.f : 0.f;
+    for (int64_t j = lane; j < d; j += 32) amax = fmaxf(amax, fabsf(x[j]));
+    amax = warp_max(amax);
+    int e = 0;
+    if (amax > 0.f && isfinite(amax)) {
+      int ex;
+      frexpf(amax, &ex);  // amax = f * 2^ex, f in [0.5, 1)
+      e = 10 - ex;        // scaled absmax lands in [512, 1024)
+      e = e < -30 ? -30 : (e > 30 ? 30 : e);
+    }
+    sc = ldexpf(gmult, e);
+    if (lane == 0 && row_unscale != nullptr) row_unscale[row] = ldexpf(1.f, -2 * e);
+  } else if (lane == 0 && row_unscale != nullptr) {
+    row_unscale[row] = 1.f;
+  }
+  uint16_t* o = out + row * k_pad;
+  for (int64_t j = 2 * lane; j < k_pad; j += 64) {
+    float v0 = 0.f, v1 = 0.f;
+    if (j < d) v0 = x[j] * sc;
+    else if (j == d && append_one) v0 = sc;
+    if (j + 1 < d) v1 = x[j + 1] * sc;
+    else if (j + 1 == d && append_one) v1 = sc;
+    const uint32_t pk = static_cast<uint32_t>(to_16(v0, fmt)) | (static_cast<uint32_t>(to_16(v1, fmt)) << 16);
+    *reinterpret_cast<uint32_t*>(o + j) = pk;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ROW_BLOCK)
+k_predictive_row_prep(const float* __restrict__ x, int64_t R, int64_t D, int64_t ld, const float* __restrict__ quad,
+                      const float* __restrict__ diag_other, float sum_diag_self, float kappa, float s2, int side,
+                      int nsplit, float opscale, __half* __restrict__ packed, int64_t seg_pad,
+                      float* __restrict__ out0, float* __restrict__ out1) {
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= R) return;
+  const float* xr = x + row * ld;
+  float n2 = 0.f, pd = 0.f;
+  for (int64_t j = lane; j < D; j += 32) {
+    const float v = xr[j];
+    const float v2 = v * v;
+    n2 += v2;
+    pd = fmaf(v2, diag_other[j], pd);
+  }
+  n2 = warp_sum(n2);
+  pd = warp_sum(pd);
+  const float qd = quad[row];
+  const float E = n2 + qd * sum_diag_self;
+  const float rinv = 1.0f / sqrtf(E);
+  const float mul = rinv * opscale;
+  const int64_t pitch = seg_pad * nsplit;
+  __half* o = packed + row * pitch;
+  for (int64_t j = 2 * lane; j < seg_pad; j += 64) {
+    const float v0 = j < D ? xr[j] * mul : 0.f;
+    const float v1 = j + 1 < D ? xr[j + 1] * mul : 0.f;
+    const __half2 hi = __floats2half2_rn(v0, v1);
+    *reinterpret_cast<__half2*>(o + j) = hi;
+    if (nsplit == 3) {
+      const float2 hf = __half22float2(hi);
+      const __half2 lo = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+      if (side == 0) {  // A operand: [hi | lo | hi]
+        *reinterpret_cast<__half2*>(o + seg_pad + j) = lo;
+        *reinterpret_cast<__half2*>(o + 2 * seg_pad + j) = hi;
+      } else {  // B operand: [hi | hi | lo]
+        *reinterpret_cast<__half2*>(o + seg_pad + j) = hi;
+        *reinterpret_cast<__half2*>(o + 2 * seg_pad + j) = lo;
+      }
+    }
+  }
+  if (lane == 0) {
+    if (side == 0) {
+      out0[row] = s2 * pd / E;
+      out1[row] = s2 * qd / E;
+    } else {
+      out0[row] = qd / E;
+      out1[row] = (qd * kappa + pd) / E;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ROW_BLOCK)
+k_ggn_row_prep(const float* __restrict__ x, int64_t R, int64_t D, int64_t ld, float opscale, __half* __restrict__ xhat,
+               int64_t d_pad, float* __restrict__ inv_norm, float* __restrict__ w_raw, float* __restrict__ w_sum) {
+  __shared__ float s_w[WARPS_PER_BLOCK];
+  const int warp = threadIdx.x >> 5;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * WARPS_PER_BLOCK + warp;
+  const int lane = threadIdx.x & 31;
+  float wr = 0.f;
+  if (row < R) {
+    const float* xr = x + row * ld;
+    float n2 = 0.f;
+    for (int64_t j = lane; j < D; j += 32) n2 = fmaf(xr[j], xr[j], n2);
+    n2 = warp_sum(n2);
+    const float inv = 1.0f / sqrtf(n2);
+    const float mul = inv * opscale;
+    __half* o = xhat + row * d_pad;
+    for (int64_t j = 2 * lane; j < d_pad; j += 64) {
+      const float v0 = j < D ? xr[j] * mul : 0.f;
+      const float v1 = j + 1 < D ? xr[j + 1] * mul : 0.f;
+      *reinterpret_cast<__half2*>(o + j) = __floats2half2_rn(v0, v1);
+    }
+    wr = inv * inv;
+    if (lane == 0) {
+      inv_norm[row] = inv;
+      if (w_raw != nullptr) w_raw[row] = wr;
+    }
+  }
+  if (w_sum != nullptr) {
+    if (lane == 0) s_w[warp] = wr;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < WARPS_PER_BLOCK; ++i) t += s_w[i];
+      atomicAdd(w_sum, t);
+    }
+  }
+}
+
+__global__ void k_normalize_weights(const float* __restrict__ w_raw, const float* __restrict__ w_sum, int64_t R,
+                                    float* __restrict__ w) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < R) w[i] = w_raw[i] * (static_cast<float>(R) / *w_sum);
+}
+
+// ------------------------------------------------------------------------------------------------
+// 64 (r) x 32 (j) tile; block (32, 8)
+__global__ void __launch_bounds__(256)
+k_transpose_to_16(const float* __restrict__ src, int64_t R, int64_t d, int64_t ld, const float* __restrict__ mult,
+                  int sqrt_mult, const float* __restrict__ mult2, float gmult, int append_one, int fmt,
+                  uint16_t* __restrict__ dst, int64_t ldo, int64_t col_off, int64_t R_pad) {
+  __shared__ float tile[64][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * 64;
+  const int64_t j0 = static_cast<int64_t>(blockIdx.y) * 32;
+  const int64_t d_rows = d + (append_one ? 1 : 0);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rr = ty + 8 * i;
+    const int64_t r = r0 + rr;
+    const int64_t j = j0 + tx;
+    float v = 0.f;
+    if (r < R) {
+      float m = gmult;
+      if (mult != nullptr) {
+        const float mv = mult[r];
+        m *= sqrt_mult ? sqrtf(fmaxf(mv, 0.f)) : mv;
+      }
+      if (mult2 != nullptr) m *= mult2[r];
+      if (j < d) v = src[r * ld + j] * m;
+      else if (j == d && append_one) v = m;
+    }
+    tile[rr][tx] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int jj = ty + 8 * i;
+    const int64_t j = j0 + jj;
+    const int64_t r = r0 + 2 * tx;
+    if (j < d_rows && r < R_pad) {
+      const uint32_t pk = static_cast<uint32_t>(to_16(tile[2 * tx][jj], fmt)) |
+                          (static_cast<uint32_t>(to_16(tile[2 * tx + 1][jj], fmt)) << 16);
+      *reinterpret_cast<uint32_t*>(dst + j * ldo + col_off + r) = pk;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ROW_BLOCK)
+k_ggn_row_finalize(const float* __restrict__ x, int64_t B, int64_t D, int64_t ldx, const float* __restrict__ inv_norm,
+                   const float* __restrict__ w, float* __restrict__ Mraw, float* __restrict__ Rraw, int64_t ldm,
+                   float unscale, int siglip, float g, float* __restrict__ mult_sw, float* __restrict__ mult_x_sw,
+                   float* __restrict__ mult_x_wa, float* __restrict__ mult_x) {
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= B) return;
+  const float inv = inv_norm[row];
+  const float* xr = x + row * ldx;
+  float* mr = Mraw + row * ldm;
+  float* rr = Rraw + row * ldm;
+  float t = 0.f, rx = 0.f;
+  for (int64_t j = lane; j < D; j += 32) {
+    const float xh = xr[j] * inv;
+    t = fmaf(mr[j] * unscale, xh, t);
+    rx = fmaf(rr[j] * unscale, xh, rx);
+  }
+  t = warp_sum(t);
+  rx = warp_sum(rx);
+  float a;
+  if (siglip) {
+    a = rx;
+    for (int64_t j = lane; j < D; j += 32) rr[j] = rr[j] * unscale;
+  } else {
+    float acc = 0.f;
+    for (int64_t j = lane; j < D; j += 32) {
+      const float m = mr[j] * unscale;
+      const float u = fmaf(-m, t, rr[j] * unscale);
+      mr[j] = m;
+      rr[j] = u;
+      acc = fmaf(u, xr[j] * inv, acc);
+    }
+    a = warp_sum(acc);
+  }
+  if (lane == 0) {
+    const float wv = w[row];
+    const float sw = sqrtf(fmaxf(wv, 0.f));
+    mult_sw[row] = g * sw;
+    mult_x_sw[row] = g * sw * inv;
+    mult_x_wa[row] = g * wv * a * inv;
+    mult_x[row] = g * inv;
+  }
+}
+
+__global__ void k_ggn_col_mult(const float* __restrict__ q, const float* __restrict__ inv_norm_y, int64_t C, float g,
+                               float* __restrict__ mult_y) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < C) mult_y[i] = g * sqrtf(fmaxf(q[i], 0.f)) * inv_norm_y[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ROW_BLOCK)
+k_probit_softmax(const float* __restrict__ mean, const float* __restrict__ var, int64_t N, int64_t C, int64_t ld,
+                 float* __restrict__ probs) {
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= N) return;
+  const float* m = mean + row * ld;
+  const float* v = var + row * ld;
+  float* p = probs + row * ld;
+  constexpr float kPi8 = 0.39269908169872414f;
+  constexpr float kLog2e = 1.4426950408889634f;
+  constexpr int CACHE = 32;  // rows up to 1024 classes stay in registers
+  float z[CACHE];
+  float zmax = -INFINITY;
+  if (C <= CACHE * 32) {
+#pragma unroll
+    for (int i = 0; i < CACHE; ++i) {
+      const int64_t j = lane + 32 * i;
+      z[i] = j < C ? m[j] / sqrtf(fmaf(kPi8, v[j], 1.0f)) * kLog2e : -INFINITY;
+      zmax = fmaxf(zmax, z[i]);
+    }
+    zmax = warp_max(zmax);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < CACHE; ++i) {
+      z[i] = exp2f(z[i] - zmax);
+      s += z[i];
+    }
+    s = warp_sum(s);
+    const float inv = 1.0f / s;
+#pragma unroll
+    for (int i = 0; i < CACHE; ++i) {
+      const int64_t j = lane + 32 * i;
+      if (j < C) p[j] = z[i] * inv;
+    }
+  } else {
+    for (int64_t j = lane; j < C; j += 32) zmax = fmaxf(zmax, m[j] / sqrtf(fmaf(kPi8, v[j], 1.0f)) * kLog2e);
+    zmax = warp_max(zmax);
+    float s = 0.f;
+    for (int64_t j = lane; j < C; j += 32) s += exp2f(m[j] / sqrtf(fmaf(kPi8, v[j], 1.0f)) * kLog2e - zmax);
+    s = warp_sum(s);
+    const float inv = 1.0f / s;
+    for (int64_t j = lane; j < C; j += 32) p[j] = exp2f(m[j] / sqrtf(fmaf(kPi8, v[j], 1.0f)) * kLog2e - zmax) * inv;
+  }
+}
+
+__global__ void k_symmetrize_scale(float* __restrict__ A, int64_t d, int64_t ld, float scale) {
+  const int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t i = blockIdx.y;
+  if (j > i || i >= d) return;
+  const float v = A[i * ld + j] * scale;
+  A[i * ld + j] = v;
+  if (i != j) A[j * ld + i] = v;
+}
+
+}  // namespace
+
+// ================================================================================================
+int launch_rows_to_16(const float* in, int64_t R, int64_t d, int64_t ld, int append_one, int fmt, int row_pow2_scale,
+                      float gmult, void* out, int64_t k_pad, float* row_unscale, cudaStream_t st) {
+  if (R <= 0) return BVLM_OK;
+  if (k_pad < d + (append_one ? 1 : 0) || (k_pad & 1)) return BVLM_EINVAL;
+  k_rows_to_16<<<row_grid(R), ROW_BLOCK, 0, st>>>(in, R, d, ld, append_one, fmt, row_pow2_scale, gmult,
+                                                  static_cast<uint16_t*>(out), k_pad, row_unscale);
+  count_launch();
+  BVLM_CUDA_TRY(cudaGetLastError());
+  return BVLM_OK;
+}
+
+int launch_predictive_row_prep(const float* x, int64_t R, int64_t D, int64_t ld, const float* quad,
+                               const float* diag_other, float sum_diag_self, float kappa, float s2, int side,
+                               int nsplit, float opscale, __half* packed, int64_t seg_pad, float* out0, float* out1,
+                               cudaStream_t st) {
+  if (R <= 0) return BVLM_OK;
+  if ((nsplit != 1 && nsplit != 3) || seg_pad < D || (seg_pad & 1)) return BVLM_EINVAL;
+  k_predictive_row_prep<<<row_grid(R), ROW_BLOCK, 0, st>>>(x, R, D, ld, quad, diag_other, sum_diag_self, kappa, s2, side,
+                                                           nsplit, opscale, packed, seg_pad, out0, out1);
+  count_launch();
+  BVLM_CUDA_TRY(cudaGetLastError());
+  return BVLM_OK;
+}
+
+int launch_ggn_row_prep(const float* x, int64_t R, int64_t D, int64_t ld, float opscale, __half* xhat, int64_t d_pad,
+                        float* inv_norm, float* w_raw, float* w_sum, cudaStream_t st) {
+  if (R <= 0) return BVLM_OK;
+  k_ggn_row_prep<<<row_grid(R), ROW_BLOCK, 0, st>>>(x, R, D, ld, opscale, xhat, d_pad, inv_norm, w_raw, w_sum);
+  count_launch();
+  BVLM_CUDA_TRY(cudaGetLastError());
+  return BVLM_OK;
+}
+
+int launch_normalize_weights(const float* w_raw, const float* w_sum, int64_t R, float* w, cudaStream_t st) {
+  if (R <= 0) return BVLM_OK;
+  k_normalize_weights<<<static_cast<unsigned>((R + 255) / 256), 256, 0, st>>>(w_raw, w_sum, R, w);
+  count_launch();
+  BVLM_CUDA_TRY(cudaGetLastError());
+  return BVLM_OK;
+}
+
+int launch_transpose_to_16(const float* src, int64_t R, int64_t d, int64_t ld, const float* mult, int sqrt_mult,
+                           const float* mult2, float gmult, int append_one, int fmt, void* dst, int64_t ldo,
+                           int64_t col_off, int64_t R_pad, cudaStream_t st) {
+  if (R_pad <= 0) return BVLM_OK;
+  if ((R_pad & 1) || (col_off & 1) || (ldo & 1)) return BVLM_EINVAL;
+  const int64_t d_rows = d + (append_one ? 1 : 0);
+  dim3 grid(static_cast<unsigned>((R_pad + 63) / 64), static_cast<unsigned>((d_rows + 31) / 32));
+  dim3 block(32, 8);
+  k_transpose_to_16<<<grid, block, 0, st>>>(src, R, d, ld, mult, sqrt_mult, mult2, gmult, append_one, fmt,
+                                            static_cast<uint16_t*>(dst), ldo, col_off, R_pad);
+  count_launch();
+  BVLM_CUDA_TRY(cudaGetLastError());
+  return BVLM_OK;
+}
+
+int launch_ggn_row_finalize(const float* x, int64_t B, int64_t D, int64_t ldx, const float* inv_norm, const float* w,
+                            float* Mraw, float* Rraw, int64_t ldm, float unscale, int siglip, float g, float* mult_sw,
+                            float* mult_x_sw, float* mult_x_wa, float* mult_x, cudaStream_t st) {
+  if (B <= 0) return BVLM_OK;
+  k_ggn_row_finalize<<<row_grid(B), ROW_BLOCK, 0, st>>>(x, B, D, ldx, inv_norm, w, Mraw, Rraw, ldm, unscale, siglip, g,
+                                                        mult_sw, mult_x_sw, mult_x_wa, mult_x);
+  count_launch();
+  BVLM_CUDA_TRY(cudaGetLastError());
+  return BVLM_OK;
+}
+
+int launch_ggn_col_mult(const float* q, const float* inv_norm_y, int64_t C, float g, float* mult_y, cudaStream_t st) {
+  if (C <= 0) return BVLM_OK;
+  k_ggn_col_mult<<<static_cast<unsigned>((C + 255) / 256), 256, 0, st>>>(q, inv_norm_y, C, g, mult_y);
+  count_launch();
+  BVLM_CUDA_TRY(cudaGetLastError());
+  return BVLM_OK;
+}
+
+int launch_probit_softmax(const float* mean, const float* var, int64_t N, int64_t C, int64_t ld, float* probs,
+                          cudaStream_t st) {
+  if (N <= 0 || C <= 0) return BVLM_OK;
+  k_probit_softmax<<<row_grid(N), ROW_BLOCK, 0, st>>>(mean, var, N, C, ld, probs);
+  count_launch();
+  BVLM_CUDA_TRY(cudaGetLastError());
+  return BVLM_OK;
+}
+
+int launch_symmetrize_scale(float* A, int64_t d, int64_t ld, float scale, cudaStream_t st) {
+  if (d <= 0) return BVLM_OK;
+  dim3 grid(static_cast<unsigned>((d + 255) / 256), static_cast<unsigned>(d));
+  k_symmetrize_scale<<<grid, 256, 0, st>>>(A, d, ld, scale);
+  count_launch();
+  BVLM_CUDA_TRY(cudaGetLastError());
+  return BVLM_OK;
+}
+
+}  // namespace bvlm

@@ -1,0 +1,56 @@
+// Operand preparation kernels: fp32 row-major activations / embeddings -> 16-bit K-major GEMM operands
+// (converted, normalised, optionally hi/lo split for ~fp32 accuracy, optionally transposed), plus the small
+// per-row statistics the epilogues need. All are HBM-bound, one warp per row or 32x32 smem-tiled transposes.
+#pragma once
+#include "common.cuh"
+
+namespace bvlm {
+
+// fp32 [R, d] (row pitch ld) -> 16-bit [R, k_pad]; optional ones column (SigLIP bias, vlm.py:650-654);
+// optional per-row power-of-two scaling with row_unscale[r] = 2^(-2 e_r) (undoes the scaling of a squared norm).
+int launch_rows_to_16(const float* in, int64_t R, int64_t d, int64_t ld, int append_one, int fmt, int row_pow2_scale,
+                      float gmult, void* out, int64_t k_pad, float* row_unscale, cudaStream_t st);
+
+// Predictive row statistics + operand packing (vlm.py:659-668).
+//   E_r   = |x_r|^2 + quad_r * sum_diag_self
+//   xhat  = x_r / sqrt(E_r) * opscale  -> 16-bit, nsplit in {1,3}: A side packs [hi|lo|hi], B side [hi|hi|lo]
+//   side 0 (source/image):  out0 = s2 * (sum_d x_d^2 * diag_other_d) / E_r ,  out1 = s2 * quad_r / E_r
+//   side 1 (target/text) :  out0 = quad_r / E_r ,  out1 = (quad_r * kappa + sum_d diag_other_d * x_d^2) / E_r
+int launch_predictive_row_prep(const float* x, int64_t R, int64_t D, int64_t ld, const float* quad,
+                               const float* diag_other, float sum_diag_self, float kappa, float s2, int side,
+                               int nsplit, float opscale, __half* packed, int64_t seg_pad, float* out0, float* out1,
+                               cudaStream_t st);
+
+// GGN row prep (hessians.py:15-21): xhat = x/|x| * opscale -> fp16 [R, d_pad]; inv_norm[r] = 1/|x_r|;
+// w_raw[r] = 1/|x_r|^2 ; *w_sum += sum_r w_raw[r] (atomic).
+int launch_ggn_row_prep(const float* x, int64_t R, int64_t D, int64_t ld, float opscale, __half* xhat, int64_t d_pad,
+                        float* inv_norm, float* w_raw, float* w_sum, cudaStream_t st);
+
+// w[r] = w_raw[r] * R / *w_sum   (mean-one weights keep the fp16 operands of the final GEMM in range)
+int launch_normalize_weights(const float* w_raw, const float* w_sum, int64_t R, float* w, cudaStream_t st);
+
+// Transposing writer: dst[j * ldo + col_off + r] = fmt( sign * src[r * ld + j] * mult[r] * gmult ), r < R, j < d;
+// an optional ones row (j == d) is appended when append_one; columns r in [R, R_pad) are zero-filled.
+// mult may be null (1). sqrt_mult=1 uses sqrt(max(mult,0)).
+int launch_transpose_to_16(const float* src, int64_t R, int64_t d, int64_t ld, const float* mult, int sqrt_mult,
+                           const float* mult2, float gmult, int append_one, int fmt, void* dst, int64_t ldo,
+                           int64_t col_off, int64_t R_pad, cudaStream_t st);
+
+// GGN per-row finalisation (collapsed form of hessians.py:30-46 / 103-113):
+//   m = Mraw[b] * unscale, r = Rraw[b] * unscale, t = m.xhat, u = r - m t (InfoNCE) or r (SigLIP), a = u.xhat
+// writes m and u back in place (fp32) and the row multipliers used by the transposing writer.
+int launch_ggn_row_finalize(const float* x, int64_t B, int64_t D, int64_t ldx, const float* inv_norm, const float* w,
+                            float* Mraw, float* Rraw, int64_t ldm, float unscale, int siglip, float g, float* mult_sw,
+                            float* mult_x_sw, float* mult_x_wa, float* mult_x, cudaStream_t st);
+
+// mult_y[c] = g * sqrt(max(q_c,0)) / |y_c|
+int launch_ggn_col_mult(const float* q, const float* inv_norm_y, int64_t C, float g, float* mult_y, cudaStream_t st);
+
+// Canonical probit softmax (scripts/zeroshot.py:119-120): probs = softmax_j(mean / sqrt(1 + pi/8 var)).
+int launch_probit_softmax(const float* mean, const float* var, int64_t N, int64_t C, int64_t ld, float* probs,
+                          cudaStream_t st);
+
+// Lower -> upper mirror of a square fp32 matrix, and scale:  A[i,j] = A[j,i] = scale * A[max,min].
+int launch_symmetrize_scale(float* A, int64_t d, int64_t ld, float scale, cudaStream_t st);
+
+}  // namespace bvlm

@@ -1,0 +1,243 @@
+"""EPIG acquisition on B200 kernels; mirrors the reference's ``bayesvlm/epig.py``.
+
+The scoring functions (reference :275-397) keep their names and rounding behaviour: for fp16 CUDA probabilities the
+marginal entropies run as a warp-shuffle reduction kernel and the joint-entropy term as a tcgen05 GEMM whose epilogue
+does ``/K -> xlogy -> sum -> /N_t`` with the reference's fp16 rounding points, so the [N_p, Cl, chunk] joint tile is
+never materialised (``csrc/epig.cu``).  The online greedy loop (reference :44-273) keeps its torch control flow.
+"""
+from __future__ import annotations
+
+import copy
+from typing import Literal, Optional
+
+import torch
+
+from . import _lib
+from ._lib import lib
+from .hessians import compute_covariances, compute_hessian_analytic_InfoNCE, optimize_prior_precision
+from .vlm import CLIP, EncoderResult, ProbabilisticLogits
+
+_JOINT_TILE_N = 256  # column tile of the joint-entropy kernel; chunk_size must be a multiple of it
+
+
+def _kernel_path_ok(probs: torch.Tensor) -> bool:
+    return probs.is_cuda and probs.dtype == torch.float16
+
+
+def entropy_from_probs(probs: torch.Tensor) -> torch.Tensor:
+    """H[p] = -sum_y p log p with 0 log 0 = 0 (reference epig.py:275-292)."""
+    return -torch.sum(torch.xlogy(probs, probs), dim=-1)
+
+
+def marginal_entropy_from_probs(probs: torch.Tensor) -> torch.Tensor:
+    """H[E_theta p(y|x,theta)] for probs [N, K, Cl] -> [N] (reference epig.py:294-311)."""
+    assert probs.ndim == 3
+    if _kernel_path_ok(probs):
+        n, k, cl = probs.shape
+        out = torch.empty(n, dtype=torch.float16, device=probs.device)
+        rc = lib.bvlm_epig_marginal_entropy_f16(_lib.ptr(probs.contiguous()), n, k, cl, _lib.ptr(out),
+                                                _lib.stream_ptr(probs.device))
+        _lib.check(rc, "bvlm_epig_marginal_entropy_f16")
+        return out
+    if not probs.is_cuda:
+        raise RuntimeError("bayesvlm_b200.epig runs on CUDA tensors only (no CPU fallback)")
+    return entropy_from_probs(torch.mean(probs, dim=1))
+
+
+def joint_entropy_from_probs(probs_pool: torch.Tensor, probs_targ: torch.Tensor, chunk_size: int) -> torch.Tensor:
+    """E_t H[p(y, y_t | x, x_t)] accumulated in fp32 over column chunks of the flattened (t, c) axis (epig.py:376-393)."""
+    n_p, k, cl = probs_pool.shape
+    n_t = probs_targ.shape[0]
+    if probs_targ.shape[1] != k or probs_targ.shape[2] != cl:
+        raise ValueError("pool and target probabilities must share [K, Cl]")
+    out = torch.empty(n_p, dtype=torch.float32, device=probs_pool.device)
+    ws = _lib.workspace(probs_pool.device, lib.bvlm_epig_joint_workspace_bytes(n_p, n_t, k, cl), tag="epig")
+    rc = lib.bvlm_epig_joint_entropy_f16(_lib.ptr(probs_pool.contiguous()), n_p, _lib.ptr(probs_targ.contiguous()), n_t, k,
+                                         cl, int(chunk_size), _lib.ptr(out), _lib.ptr(ws), ws.numel(),
+                                         _lib.stream_ptr(probs_pool.device))
+    _lib.check(rc, "bvlm_epig_joint_entropy_f16")
+    return out
+
+
+def _joint_entropy_torch(probs_pool, probs_targ, chunk_size):
+    """Generic-dtype device expression of the same term (used for fp32 'noise-free' scores and odd shapes)."""
+    n_t, k, cl = probs_targ.shape
+    pool = probs_pool.permute(0, 2, 1)
+    targ = probs_targ.permute(1, 0, 2).reshape(k, n_t * cl)
+    acc = torch.zeros(pool.shape[0], device=pool.device)
+    for lo in range(0, n_t * cl, chunk_size):
+        joint = pool @ targ[:, lo:lo + chunk_size] / k
+        acc += -torch.sum(torch.xlogy(joint, joint), dim=(-2, -1)) / n_t
+    return acc
+
+
+@torch.no_grad()
+def epig_from_probs_using_matmul(probs_pool: torch.Tensor, probs_targ: torch.Tensor, chunk_size: int = 8192):
+    """EPIG(x) = H[p(y|x)] + E_t H[p(y_t|x_t)] - E_t H[p(y,y_t|x,x_t)]  (reference epig.py:342-397).
+
+    probs_pool [N_p, K, Cl], probs_targ [N_t, K, Cl] -> [N_p].
+    """
+    assert probs_pool.ndim == probs_targ.ndim == 3
+    if not (probs_pool.is_cuda and probs_targ.is_cuda):
+        raise RuntimeError("bayesvlm_b200.epig runs on CUDA tensors only (no CPU fallback)")
+    cl = probs_targ.shape[2]
+    entropy_pool = marginal_entropy_from_probs(probs_pool)
+    entropy_targ_mean = torch.mean(marginal_entropy_from_probs(probs_targ))
+    fused = (_kernel_path_ok(probs_pool) and _kernel_path_ok(probs_targ) and cl <= 128 and
+             chunk_size % _JOINT_TILE_N == 0 and probs_pool.shape[1] * cl * 2 <= 48 * 1024)
+    if fused:
+        entropy_joint = joint_entropy_from_probs(probs_pool, probs_targ, chunk_size)
+    else:
+        entropy_joint = _joint_entropy_torch(probs_pool, probs_targ, chunk_size)
+    return entropy_pool + entropy_targ_mean - entropy_joint
+
+
+@torch.no_grad()
+def epig_from_logits_using_matmul(logits_pool: ProbabilisticLogits, logits_targ: ProbabilisticLogits, seed: int,
+                                  num_samples: int, chunk_size: int = 4096) -> torch.Tensor:
+    """Pool rows in chunks of ``chunk_size``; each chunk re-draws target AND pool samples under ``seed + row_offset``
+    (both calls re-seed torch's generator with the same value), casts to fp16 and scores (reference epig.py:313-340)."""
+    pieces = []
+    n_pool = logits_pool.mean.shape[0]
+    for lo in range(0, n_pool, chunk_size):
+        probs_targ = logits_targ.sample_probas_f16(num_samples, seed=seed + lo)
+        chunk = ProbabilisticLogits(mean=logits_pool.mean[lo:lo + chunk_size], var=logits_pool.var[lo:lo + chunk_size])
+        probs_pool = chunk.sample_probas_f16(num_samples, seed=seed + lo)
+        pieces.append(epig_from_probs_using_matmul(probs_pool, probs_targ, chunk_size=chunk_size).to(torch.float32))
+    return torch.cat(pieces, dim=0)
+
+
+def update_embeddings(projection: torch.nn.Module, outputs: EncoderResult, device: str = "cuda",
+                      keep_on_device: bool = False) -> EncoderResult:
+    """Re-project all activations with the current projection weights (reference epig.py:15-42), as one device GEMM
+    instead of a CPU DataLoader round trip.  Returns CPU tensors like the reference unless ``keep_on_device``."""
+    act = outputs.activations.to(device)
+    res = outputs.residuals.to(device)
+    with torch.no_grad():
+        embeds = projection(act) + res
+    new = EncoderResult(embeds=embeds, activations=act, residuals=res)
+    return new if keep_on_device else new.to("cpu")
+
+
+def _diag_embedding_cov(acts, cov, has_bias):
+    if has_bias:
+        acts = torch.cat([acts, torch.ones_like(acts[:, :1])], dim=1)
+    return ((acts @ cov.A_inv) * acts).sum(-1, keepdim=True) * cov.B_inv.diagonal()
+
+
+def select_epig_online(label_features: EncoderResult, pool_features: EncoderResult, target_features: EncoderResult,
+                       pool_class_ids: torch.Tensor, image_projection: torch.nn.Linear, clip: CLIP, A_img: torch.Tensor,
+                       A_txt: torch.Tensor, B_img: torch.Tensor, B_txt: torch.Tensor, cov_info: dict, budget: int,
+                       lr: float, hessian_update_scale: float, device: torch.device, num_samples: int, seed: int,
+                       pool_max_size: Optional[int] = None, target_max_size: Optional[int] = None,
+                       chunk_size: int = 4096, pool_subsampling: Literal["random", "knn"] = "random",
+                       k_nearest_neighbors: int = 1, proj_has_bias=False):
+    """Greedy online EPIG selection with a rank-one posterior update per pick (reference epig.py:44-273)."""
+    torch.manual_seed(seed)
+    n_pool_all, n_targ_all = len(pool_features.embeds), len(target_features.embeds)
+    if pool_max_size is not None:
+        pool_max_size = min(pool_max_size, n_pool_all)
+    if target_max_size is not None:
+        target_max_size = min(target_max_size, n_targ_all)
+
+    image_projection = copy.deepcopy(image_projection).to(device).train()
+    pool_features = pool_features.to(device)
+    target_features = target_features.to(device)
+    label_features = label_features.to(device)
+    pool_class_ids = pool_class_ids.to(device)
+    A_img, B_img, A_txt, B_txt = (t.to(device) for t in (A_img, B_img, A_txt, B_txt))
+
+    clip = clip.to(device).eval()
+    for p in clip.parameters():
+        p.requires_grad = False
+    cov_img, cov_txt = compute_covariances(A_img, B_img, A_txt, B_txt, cov_info)
+    clip.set_covariances(cov_img, cov_txt)
+
+    if target_max_size is not None and target_max_size < n_targ_all:
+        idx_targ = torch.randperm(n_targ_all)[:target_max_size]
+    else:
+        idx_targ = torch.arange(n_targ_all)
+
+    if pool_subsampling == "random":
+        if pool_max_size is not None and pool_max_size < n_pool_all:
+            idx_pool = torch.randperm(n_pool_all)[:pool_max_size]
+        else:
+            idx_pool = torch.arange(n_pool_all)
+    elif pool_subsampling in ("knn_cosine", "knn_wasserstein"):
+        mu_train, mu_test = pool_features.embeds, target_features.embeds[idx_targ]
+        cov_train = _diag_embedding_cov(pool_features.activations, cov_img, proj_has_bias)
+        cov_test = _diag_embedding_cov(target_features.activations[idx_targ], cov_img, proj_has_bias)
+        if pool_subsampling == "knn_cosine":
+            tr = mu_train / torch.sqrt((mu_train ** 2 + cov_train).sum(-1, keepdim=True))
+            te = mu_test / torch.sqrt((mu_test ** 2 + cov_test).sum(-1, keepdim=True))
+            sim = te @ tr.t()
+        else:  # negative diagonal 2-Wasserstein distance (reference knn.py:6-20)
+            sim = -(torch.cdist(mu_test, mu_train) ** 2 + cov_test.sum(-1)[:, None] + cov_train.sum(-1)[None, :]
+                    - 2 * cov_test.sqrt() @ cov_train.sqrt().t())
+        nearest = torch.argsort(sim, descending=True, dim=1)
+        idx_pool = nearest[:, :k_nearest_neighbors].flatten().unique().cpu()
+        if len(idx_pool) < budget:
+            raise ValueError(f"Could not find enough samples in the pool. Found {len(idx_pool)}, expected at least {budget}.")
+    else:
+        raise ValueError(f"Unknown subsampling method: {pool_subsampling}")
+
+    selected_indices, epig_scores = [], []
+    for step in range(budget):
+        pool_sub = EncoderResult(embeds=pool_features.embeds[idx_pool], activations=pool_features.activations[idx_pool])
+        pool_ids_sub = pool_class_ids[idx_pool]
+        targ_sub = EncoderResult(embeds=target_features.embeds[idx_targ], activations=target_features.activations[idx_targ])
+
+        logits_pool = clip(pool_sub.to(device), label_features.to(device)).detach()
+        logits_targ = clip(targ_sub.to(device), label_features.to(device)).detach()
+        scores = epig_from_logits_using_matmul(logits_pool, logits_targ, num_samples=num_samples, chunk_size=chunk_size,
+                                               seed=seed + step)
+
+        best = None
+        for cand in torch.argsort(scores, descending=True):
+            if idx_pool[cand].item() in selected_indices:
+                print(f"Skipping {cand} as it has already been selected.")
+                continue
+            best = cand
+            break
+
+        best_act = pool_sub.activations[best].unsqueeze(0)
+        best_res = pool_sub.residuals[best].unsqueeze(0)
+        best_cls = pool_ids_sub[best].unsqueeze(0)
+        selected_indices.append(idx_pool[best].item())
+        epig_scores.append(scores[best].item())
+
+        # one SGD step on the projection weight with the CE of the mean logits of the picked sample
+        for p in image_projection.parameters():
+            p.requires_grad = True
+        image_projection.zero_grad()
+        best_embed = image_projection(best_act) + best_res
+        best_logits = clip(EncoderResult(embeds=best_embed, activations=best_act, residuals=best_res), label_features)
+        loss = torch.nn.functional.cross_entropy(input=best_logits.mean, target=best_cls)
+        loss.backward()
+        with torch.no_grad():
+            image_projection.weight.data -= lr * image_projection.weight.grad
+            image_projection.weight.grad.zero_()
+
+        pool_features = update_embeddings(image_projection, pool_features, device, keep_on_device=True)
+        target_features = update_embeddings(image_projection, target_features, device, keep_on_device=True)
+
+        picked_embed = pool_sub.embeds[best]
+        picked_act = pool_sub.activations[best]
+        # reference quirk (epig.py:240): a 1-D activation makes `a @ a.T` the SCALAR |a|^2, broadcast over A_img
+        A_new = picked_act @ picked_act.T
+        B_new = compute_hessian_analytic_InfoNCE(source_embeds=picked_embed.unsqueeze(0).to(device),
+                                                 target_embeds=label_features.embeds.to(device),
+                                                 logit_scale=clip.logit_scale.data.to(device))
+        n_prev = 327_680 + step  # reference hard-codes the size of the initial estimate (epig.py:250)
+        s0, s1 = torch.sqrt(torch.tensor(n_prev)), torch.sqrt(torch.tensor(n_prev + 1))
+        A_img = (s0 * A_img + A_new * hessian_update_scale) / s1
+        B_img = (s0 * B_img + B_new * hessian_update_scale) / s1
+
+        lmbda_img = optimize_prior_precision(projection=image_projection, A=A_img, B=B_img,
+                                             lmbda_init=cov_info["lambda_img"], n=cov_info["n_img"], lr=1e-3,
+                                             num_steps=20, device=device, retain_graph=True)
+        cov_info["lambda_img"] = lmbda_img.item()
+        cov_img, cov_txt = compute_covariances(A_img, B_img, A_txt, B_txt, cov_info)
+        clip.set_covariances(cov_img, cov_txt)
+
+    return selected_indices, epig_scores

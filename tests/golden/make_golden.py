@@ -1,0 +1,175 @@
+"""Generate the golden fixtures under tests/golden/ by RUNNING THE REFERENCE ITSELF.
+
+Run once in the build container (the reference tree is mounted read-only at /root/reference; it does not exist on the
+GPU box, which is why the outputs are committed):
+
+    python tests/golden/make_golden.py
+
+The reference ships no tests or golden vectors for the Laplace hot path, so parity of `oracle/` (and through it of the
+CUDA kernels) is pinned on these outputs: every array below is produced by calling the unmodified reference functions
+(bayesvlm/hessians.py, bayesvlm/vlm.py, bayesvlm/epig.py, scripts/hessian_estimation.py::kfac_ggn) on seeded inputs with
+CPU fp32 torch; inputs are stored next to the outputs.
+"""
+from __future__ import annotations
+
+import importlib.util
+import json
+import math
+import sys
+import types
+from pathlib import Path
+
+import numpy as np
+import torch
+
+REF = Path("/root/reference")
+OUT = Path(__file__).resolve().parent
+
+
+def load_reference():
+    sys.path.insert(0, str(REF))
+    import bayesvlm.epig as r_epig
+    import bayesvlm.hessians as r_hess
+    import bayesvlm.vlm as r_vlm
+
+    # scripts/hessian_estimation.py imports bayesvlm.data.factory (needs pytorch_lightning, absent): stub it.
+    stub = types.ModuleType("bayesvlm.data.factory")
+    stub.DataModuleFactory = type("DataModuleFactory", (), {})
+    sys.modules["bayesvlm.data.factory"] = stub
+    spec = importlib.util.spec_from_file_location("ref_hessian_estimation", REF / "scripts" / "hessian_estimation.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return r_hess, r_vlm, r_epig, mod
+
+
+def randn(gen, *shape):
+    return torch.randn(*shape, generator=gen, dtype=torch.float32)
+
+
+def spd(gen, d, scale):
+    w = randn(gen, 4 * d, d)
+    return (w.T @ w) / math.sqrt(4 * d) * scale
+
+
+def paired(gen, n, d):
+    z = randn(gen, n, d)
+    return z + 1.5 * randn(gen, n, d), z + 1.5 * randn(gen, n, d)
+
+
+def main():
+    torch.set_num_threads(8)
+    r_hess, r_vlm, r_epig, r_est = load_reference()
+    ls = math.log(100.0)
+    out = {}
+
+    # ---- K2 / K3: analytic GGNs -------------------------------------------------------------------------------------
+    g = torch.Generator().manual_seed(101)
+    X, Y = paired(g, 40, 24)
+    X = X[:7]
+    out["ggn_X"], out["ggn_Y"] = X.numpy(), Y.numpy()
+    out["ggn_infonce_H"] = r_hess.compute_hessian_analytic_InfoNCE(X, Y, torch.tensor(ls)).numpy()
+    sl_scale, sl_bias = 2.3, -3.0
+    idx = torch.arange(7)
+    out["ggn_siglip_H"] = r_hess.compute_hessian_analytic_SigLIP(X, idx, Y, torch.tensor(sl_scale), torch.tensor(sl_bias),
+                                                                 chunk_size_j=16).numpy()
+    out["ggn_siglip_params"] = np.array([sl_scale, sl_bias], np.float64)
+    torch.set_default_dtype(torch.float64)  # hessians.py:39 uses the default dtype for eye()
+    out["ggn_infonce_H64"] = r_hess.compute_hessian_analytic_InfoNCE(X.double(), Y.double(), torch.tensor(ls).double()).numpy()
+    out["ggn_siglip_H64"] = r_hess.compute_hessian_analytic_SigLIP(X.double(), idx, Y.double(), torch.tensor(sl_scale).double(),
+                                                                   torch.tensor(sl_bias).double()).numpy()
+    torch.set_default_dtype(torch.float32)
+
+    # ---- K0: the accumulation loop with its dropped remainders ------------------------------------------------------
+    g = torch.Generator().manual_seed(202)
+    n, ncls, bs, D, d_in = 138, 64, 5, 16, 24
+    emb_s, emb_t = paired(g, n, D)
+    act_s = randn(g, n, d_in)
+    out["kfac_emb_s"], out["kfac_emb_t"], out["kfac_act_s"] = emb_s.numpy(), emb_t.numpy(), act_s.numpy()
+    out["kfac_cfg"] = np.array([ncls, bs], np.int64)
+    clip = r_vlm.CLIP(logit_scale=ls)
+    A, B = r_est.kfac_ggn(clip, ncls, bs, emb_s, act_s, emb_t, "cpu", "info_nce")
+    out["kfac_infonce_A"], out["kfac_infonce_B"] = A.numpy(), B.numpy()
+    sig = r_vlm.SIGLIP(logit_scale=sl_scale, logit_bias=sl_bias)
+    A, B = r_est.kfac_ggn(sig, ncls, bs, emb_s, act_s, emb_t, "cpu", "siglip", siglip_chunk_size_j=20)
+    out["kfac_siglip_A"], out["kfac_siglip_B"] = A.numpy(), B.numpy()
+
+    # ---- C1 + P2: covariances and the predictive (CLIP and SIGLIP flavours, surrogate factors) ----------------------
+    g = torch.Generator().manual_seed(303)
+    N, C, D, d_img, d_txt = 37, 11, 32, 40, 24
+    info = {"n_img": 1.0, "n_txt": 1.0, "lambda_img": 600.0, "lambda_txt": 220.0}
+    for tag, cls, bias in (("clip", r_vlm.CLIP, 0), ("siglip", r_vlm.SIGLIP, 1)):
+        A_img, B_img = spd(g, d_img + bias, 3e3), spd(g, D, 20.0)
+        A_txt, B_txt = spd(g, d_txt + bias, 3e3), spd(g, D, 20.0)
+        cov_img, cov_txt = r_hess.compute_covariances(A_img, B_img, A_txt, B_txt, info)
+        img = r_vlm.EncoderResult(embeds=randn(g, N, D), activations=randn(g, N, d_img))
+        txt = r_vlm.EncoderResult(embeds=randn(g, C, D), activations=randn(g, C, d_txt))
+        model = cls(logit_scale=ls) if bias == 0 else cls(logit_scale=sl_scale, logit_bias=sl_bias)
+        model.set_covariances(cov_img, cov_txt)
+        with torch.no_grad():
+            pl = model(img, txt)
+            pm = model(img, txt, map_estimate=True)
+        pre = f"pred_{tag}_"
+        for k_, v_ in dict(A_img=A_img, B_img=B_img, A_txt=A_txt, B_txt=B_txt, A_img_inv=cov_img.A_inv,
+                           B_img_inv=cov_img.B_inv, A_txt_inv=cov_txt.A_inv, B_txt_inv=cov_txt.B_inv, img_emb=img.embeds,
+                           img_act=img.activations, txt_emb=txt.embeds, txt_act=txt.activations, mean=pl.mean, var=pl.var,
+                           map=pm.mean).items():
+            out[pre + k_] = v_.numpy()
+        kappa = 1 / torch.sqrt(1.0 + torch.pi / 8 * pl.var)
+        out[pre + "probit"] = torch.softmax(kappa * pl.mean, dim=-1).numpy()             # zeroshot.py:119-120
+        out[pre + "softmax0"] = pl.softmax(num_samples=0).numpy()                        # method quirk, vlm.py:74-78
+    out["pred_info"] = np.array([info["n_img"], info["n_txt"], info["lambda_img"], info["lambda_txt"]], np.float64)
+
+    # ---- config 1: shipped CLIP ViT-B-32 factors, 10k x 10 (rows subsampled for the fixture) ------------------------
+    la_dir = REF / "hessians" / "hessian_CLIP-ViT-B-32-laion2B-s34B-b79K"
+    cov_img, cov_txt, info32 = r_hess.load_covariances(str(la_dir), return_info=True)
+    g = torch.Generator().manual_seed(1000)
+    img = r_vlm.EncoderResult(embeds=randn(g, 10000, 512), activations=randn(g, 10000, 768))
+    txt = r_vlm.EncoderResult(embeds=randn(g, 10, 512), activations=randn(g, 10, 512))
+    model = r_vlm.CLIP(logit_scale=ls)
+    model.set_covariances(cov_img, cov_txt)
+    with torch.no_grad():
+        pl = model(img, txt)
+    b32 = {}
+    for tag in ("A_img", "A_txt", "B_img", "B_txt"):
+        b32[tag] = torch.load(la_dir / f"{tag}_analytic.pt", map_location="cpu").numpy()
+    b32["info"] = np.array([info32["n_img"], info32["n_txt"], info32["lambda_img"], info32["lambda_txt"]], np.float64)
+    b32["mean"], b32["var"] = pl.mean.numpy(), pl.var.numpy()
+    b32["seed"] = np.array([1000], np.int64)
+    np.savez_compressed(OUT / "b32_config1.npz", **b32)
+
+    # ---- E0 / E1 / E2: EPIG on fp16 probabilities --------------------------------------------------------------------
+    g = torch.Generator().manual_seed(404)
+    Np, Nt, K, Cl, chunk = 45, 30, 16, 5, 64
+    mean_p, var_p = randn(g, Np, Cl) * 2, torch.rand(Np, Cl, generator=g) * 3 + 0.1
+    mean_t, var_t = randn(g, Nt, Cl) * 2, torch.rand(Nt, Cl, generator=g) * 3 + 0.1
+    eps_p, eps_t = randn(g, K, Np, Cl), randn(g, K, Nt, Cl)
+    probs_p = torch.softmax((eps_p * var_p.sqrt() + mean_p).permute(1, 0, 2), dim=2)       # vlm.py:121-123
+    probs_t = torch.softmax((eps_t * var_t.sqrt() + mean_t).permute(1, 0, 2), dim=2)
+    p16, t16 = probs_p.half(), probs_t.half()
+    out.update(epig_mean_p=mean_p.numpy(), epig_var_p=var_p.numpy(), epig_eps_p=eps_p.numpy(), epig_mean_t=mean_t.numpy(),
+               epig_var_t=var_t.numpy(), epig_eps_t=eps_t.numpy(), epig_probs_p=probs_p.numpy(), epig_probs_t=probs_t.numpy(),
+               epig_cfg=np.array([chunk], np.int64))
+    out["epig_marginal_p16"] = r_epig.marginal_entropy_from_probs(p16).numpy()
+    out["epig_marginal_p32"] = r_epig.marginal_entropy_from_probs(probs_p).numpy()
+    out["epig_scores_f16"] = r_epig.epig_from_probs_using_matmul(p16, t16, chunk_size=chunk).numpy()
+    out["epig_scores_f32"] = r_epig.epig_from_probs_using_matmul(probs_p, probs_t, chunk_size=chunk).numpy()
+
+    # ---- prior precision optimisation ---------------------------------------------------------------------------------
+    g = torch.Generator().manual_seed(505)
+    proj = torch.nn.Linear(24, 16, bias=False)
+    with torch.no_grad():
+        proj.weight.copy_(randn(g, 16, 24) * 0.05)
+    A, B = spd(g, 24, 30.0), spd(g, 16, 2.0)
+    lam = r_hess.optimize_prior_precision(proj, A, B, lmbda_init=50.0, n=10.0, lr=1e-2, num_steps=60, device="cpu")
+    out.update(prior_W=proj.weight.detach().numpy(), prior_A=A.numpy(), prior_B=B.numpy(),
+               prior_cfg=np.array([50.0, 10.0, 1e-2, 60], np.float64), prior_lambda=np.array([lam.item()], np.float64))
+
+    np.savez_compressed(OUT / "reference_small.npz", **out)
+    meta = {"torch": torch.__version__, "reference": "MridulPandey17/BayesVLM @ /root/reference",
+            "files": ["reference_small.npz", "b32_config1.npz"], "keys": sorted(out)}
+    (OUT / "golden_meta.json").write_text(json.dumps(meta, indent=1))
+    print("wrote", OUT)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,139 @@
+"""The CPU oracle against outputs of the reference implementation itself (tests/golden/make_golden.py)."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import laplace_oracle as O
+from conftest import relerr
+
+LS = math.log(100.0)
+
+
+def test_infonce_naive_and_collapsed_match_reference(golden):
+    X, Y = golden["ggn_X"], golden["ggn_Y"]
+    ref64, ref32 = golden["ggn_infonce_H64"], golden["ggn_infonce_H"]
+    assert relerr(O.infonce_ggn_naive(X, Y, LS), ref64) < 1e-12
+    assert relerr(O.infonce_ggn_collapsed(X, Y, LS), ref64) < 1e-12
+    assert relerr(O.infonce_ggn_collapsed(X, Y, LS, np.float32), ref32) < 5e-6
+    H = O.infonce_ggn_collapsed(X, Y, LS)
+    assert np.abs(H - H.T).max() <= 1e-12 * np.abs(H).max()
+
+
+def test_siglip_naive_and_collapsed_match_reference(golden):
+    X, Y = golden["ggn_X"], golden["ggn_Y"]
+    s, b = golden["ggn_siglip_params"]
+    ref64, ref32 = golden["ggn_siglip_H64"], golden["ggn_siglip_H"]
+    idx = np.arange(X.shape[0])
+    assert relerr(O.siglip_ggn_naive(X, idx, Y, s, b), ref64) < 1e-12
+    assert relerr(O.siglip_ggn_collapsed(X, Y, s, b), ref64) < 1e-12
+    assert relerr(O.siglip_ggn_collapsed(X, Y, s, b, np.float32), ref32) < 5e-6
+    # labels only flip the sign inside sigma(1-sigma): result independent of indices_batch
+    assert relerr(O.siglip_ggn_naive(X, idx[::-1].copy(), Y, s, b), ref64) < 1e-12
+
+
+def test_siglip_dim_mismatch_asserts(golden):
+    with pytest.raises(AssertionError):
+        O.siglip_ggn_naive(golden["ggn_X"], np.arange(7), golden["ggn_Y"][:, :-1], 1.0, 0.0)
+
+
+@pytest.mark.parametrize("likelihood", ["info_nce", "siglip"])
+@pytest.mark.parametrize("literal", [False, True])
+def test_kfac_loop_quirks(golden, likelihood, literal):
+    ncls, bs = (int(v) for v in golden["kfac_cfg"])
+    if likelihood == "info_nce":
+        ls, lb, tag = LS, 0.0, "infonce"
+    else:
+        (ls, lb), tag = golden["ggn_siglip_params"], "siglip"
+    A, B = O.kfac_ggn(golden["kfac_emb_s"], golden["kfac_act_s"], golden["kfac_emb_t"], ncls, bs, ls, lb, likelihood,
+                      literal_batches=literal)
+    assert relerr(A, golden[f"kfac_{tag}_A"]) < 1e-6
+    assert relerr(B, golden[f"kfac_{tag}_B"]) < 1e-5
+    if likelihood == "siglip":  # ones column appended: (d_in+1)^2 and A[-1,-1]*sqrt(n) == n
+        n = (len(golden["kfac_emb_t"]) // ncls) * ncls
+        assert A.shape[0] == golden["kfac_act_s"].shape[1] + 1
+        assert abs(A[-1, -1] * math.sqrt(n) - n) < 1e-9
+
+
+def test_kfac_data_batch_remainder_is_load_bearing(golden):
+    """Keeping the last num_classes % batch_size sources changes B by tens of percent (quirk ii of K0)."""
+    ncls, bs = (int(v) for v in golden["kfac_cfg"])
+    _, B_keep = O.kfac_ggn(golden["kfac_emb_s"], golden["kfac_act_s"], golden["kfac_emb_t"], ncls, 1, LS)
+    assert relerr(B_keep, golden["kfac_infonce_B"]) > 1e-2
+
+
+def test_kfac_errors():
+    x = np.zeros((10, 4))
+    with pytest.raises(ValueError):
+        O.kfac_ggn(x, x, x, 64, 5, 0.0)
+    with pytest.raises(ValueError):
+        O.kfac_ggn(x, x, x, 5, 5, 0.0, likelihood="bogus")
+
+
+@pytest.mark.parametrize("tag", ["clip", "siglip"])
+def test_covariance_and_predictive(golden, tag):
+    g = {k[len(f"pred_{tag}_"):]: v for k, v in golden.items() if k.startswith(f"pred_{tag}_")}
+    n_img, n_txt, l_img, l_txt = golden["pred_info"]
+    Ai, Bi = O.covariance(g["A_img"], g["B_img"], n_img, l_img)
+    At, Bt = O.covariance(g["A_txt"], g["B_txt"], n_txt, l_txt)
+    assert relerr(Ai, g["A_img_inv"]) < 1e-4 and relerr(Bi, g["B_img_inv"]) < 1e-4
+    assert relerr(At, g["A_txt_inv"]) < 1e-4 and relerr(Bt, g["B_txt_inv"]) < 1e-4
+    bias = tag == "siglip"
+    ls = golden["ggn_siglip_params"][0] if bias else LS
+    lb = golden["ggn_siglip_params"][1] if bias else 0.0
+    mean, var = O.predictive(g["img_emb"], g["img_act"], g["txt_emb"], g["txt_act"], g["A_img_inv"], g["B_img_inv"],
+                             g["A_txt_inv"], g["B_txt_inv"], ls, bias, bias)
+    np.testing.assert_allclose(mean, g["mean"], rtol=2e-5, atol=2e-5 * np.abs(g["mean"]).max())
+    np.testing.assert_allclose(var, g["var"], rtol=2e-5)
+    np.testing.assert_allclose(O.map_logits(g["img_emb"], g["txt_emb"], ls, lb), g["map"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(O.probit_softmax(g["mean"], g["var"]), g["probit"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(O.probit_softmax_method_quirk(g["mean"], g["var"]), g["softmax0"], rtol=1e-5, atol=1e-7)
+    # the method's diagonal quirk is NOT the canonical probit
+    if tag == "clip":  # (with SigLIP's small logit scale the variances are tiny and the two nearly coincide)
+        assert np.abs(g["softmax0"] - g["probit"]).max() > 1e-4
+
+
+def test_predictive_config1_shipped_b32_factors(golden_b32):
+    """Config 1 (CPU-runnable): shipped CLIP ViT-B-32 factors, seeded 10k x 10 synthetic features."""
+    import torch
+
+    b = golden_b32
+    n_img, n_txt, l_img, l_txt = b["info"]
+    Ai, Bi = O.covariance(b["A_img"], b["B_img"], n_img, l_img)
+    At, Bt = O.covariance(b["A_txt"], b["B_txt"], n_txt, l_txt)
+    g = torch.Generator().manual_seed(int(b["seed"][0]))
+    rn = lambda *s: torch.randn(*s, generator=g, dtype=torch.float32).numpy()
+    img_e, img_a, txt_e, txt_a = rn(10000, 512), rn(10000, 768), rn(10, 512), rn(10, 512)
+    mean, var = O.predictive(img_e, img_a, txt_e, txt_a, Ai, Bi, At, Bt, LS, dtype=np.float64)
+    assert np.abs(mean - b["mean"]).max() <= 1e-3 * max(np.abs(b["mean"]).max(), 1.0) * 0.1
+    np.testing.assert_allclose(var, b["var"], rtol=1e-3)
+
+
+def test_epig_fp16_rounding_points(golden):
+    p32, t32 = golden["epig_probs_p"], golden["epig_probs_t"]
+    np.testing.assert_allclose(O.sample_probas(golden["epig_mean_p"], golden["epig_var_p"], golden["epig_eps_p"]), p32,
+                               rtol=2e-6, atol=1e-7)
+    p16, t16 = p32.astype(np.float16), t32.astype(np.float16)
+    chunk = int(golden["epig_cfg"][0])
+    me = O.marginal_entropy_f16(p16)
+    assert me.dtype == np.float16
+    ref_me = golden["epig_marginal_p16"]
+    ulp = np.abs(me.astype(np.float32) - ref_me.astype(np.float32)) / np.spacing(np.abs(ref_me)).astype(np.float32)
+    assert (ulp == 0).mean() >= 0.95 and ulp.max() <= 1
+    scores = O.epig_from_probs_f16(p16, t16, chunk)
+    ref = golden["epig_scores_f16"]
+    assert scores.dtype == np.float32
+    # identical up to rare one-fp16-ulp flips caused by the fp32 summation order inside the reductions
+    diff = np.abs(scores - ref)
+    assert (diff == 0).mean() >= 0.8, (diff == 0).mean()
+    assert diff.max() <= 2 * 2.0 ** -10 * np.abs(golden["epig_marginal_p16"].astype(np.float32)).max()
+    # noise-free definition agrees with the reference evaluated on fp32 probabilities
+    np.testing.assert_allclose(O.epig_from_probs_f32(p32, t32), golden["epig_scores_f32"], atol=5e-6)
+
+
+def test_log_marglik_objective_is_maximised_by_reference_lambda(golden):
+    lam0, n, _, _ = golden["prior_cfg"]
+    lam = float(golden["prior_lambda"][0])
+    W = golden["prior_W"]
+    f = lambda l: O.log_marglik(golden["prior_A"], golden["prior_B"], n, l, float((W ** 2).sum()), W.size)
+    assert f(lam) > f(lam0)  # 60 Adam ascent steps improved the objective the oracle restates
