@@ -45,9 +45,9 @@ SIGNATURES = {
     "bvlm_device_check": (c_int, []),
     "bvlm_syrk_workspace_bytes": (c_size_t, [_I, _I, c_int, c_int]),
     "bvlm_syrk_f32acc": (c_int, [_P, _I, _I, _I, c_int, c_int, _P, _I, c_float, c_int, _P, c_size_t, _P]),
-    "bvlm_ggn_workspace_bytes": (c_size_t, [_I, _I, _I]),
-    "bvlm_ggn_infonce": (c_int, [_P, _I, _I, _P, _I, _I, _I, c_float, _P, _I, c_int, _P, c_size_t, _P]),
-    "bvlm_ggn_siglip": (c_int, [_P, _I, _I, _P, _I, _I, _I, c_float, c_float, _P, _I, c_int, _P, c_size_t, _P]),
+    "bvlm_ggn_workspace_bytes": (c_size_t, [_I, _I, _I, c_int]),
+    "bvlm_ggn_infonce": (c_int, [_P, _I, _I, _P, _I, _I, _I, c_float, c_int, _P, _I, c_int, _P, c_size_t, _P]),
+    "bvlm_ggn_siglip": (c_int, [_P, _I, _I, _P, _I, _I, _I, c_float, c_float, c_int, _P, _I, c_int, _P, c_size_t, _P]),
     "bvlm_padded_k": (c_int64, [_I]),
     "bvlm_factor_prepare": (c_int, [_P, _I, _I, c_float, _P, _I, _P]),
     "bvlm_quadform_workspace_bytes": (c_size_t, [_I, _I, c_int]),

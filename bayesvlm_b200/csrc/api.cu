@@ -71,7 +71,7 @@ int bvlm_gemm_tn_f32(const void* A16, int64_t M, const void* B16, int64_t N, int
   if ((rc = operand_tmap<BN>(&tmB, opB))) return rc;
   GemmPlan plan = make_plan<BN>(static_cast<int>(M), static_cast<int>(N), static_cast<int>(k_pad), SCHED_TILES,
                                 split_k < 1 ? 1 : split_k, fmt, fmt);
-  EpiStoreF32<BN>::Params ep{D, ldd, alpha, plan.splits > 1 ? 1 : 0, 0, nullptr};
+  EpiStoreF32<BN>::Params ep{D, ldd, alpha, plan.splits > 1 ? 1 : 0, 0, nullptr, nullptr};
   if (plan.splits > 1) {
     BVLM_CUDA_TRY(cudaMemset2DAsync(D, static_cast<size_t>(ldd) * 4, 0, static_cast<size_t>(N) * 4, static_cast<size_t>(M), st));
   }

@@ -70,9 +70,10 @@ struct EpiStoreF32 {
     float* C;
     int64_t ldc;
     float alpha;
-    int atomic;
-    int mirror;
+    int atomic;              // 1: red.global.add (split-K / accumulate), 0: plain store
+    int lower_only;          // 1: only elements with row >= col are written (SYRK; mirrored by a later pass)
     const float* alpha_dev;  // optional device scalar multiplied into alpha
+    const float* unscale;    // optional per-index multiplier u: C[i,j] (+)= alpha * u[i] * u[j] * acc (SYRK operand scaling)
   };
   struct State {
     float alpha;
@@ -84,10 +85,22 @@ struct EpiStoreF32 {
   __device__ static void chunk(State& st, const Params& p, const EpiCtx& ctx, const TileCoord& tc, float (&v)[32], int c) {
     const int row = epi_row(ctx, tc);
     const int col0 = tc.n * BN + c * 32;
-    const int n_valid = ctx.N - col0;
+    int n_valid = ctx.N - col0;
     if (row >= ctx.M) return;
+    if (p.lower_only) {
+      const int lim = row - col0 + 1;  // columns col0 .. row
+      n_valid = n_valid < lim ? n_valid : lim;
+      if (n_valid <= 0) return;
+    }
+    float a = st.alpha;
+    if (p.unscale != nullptr) {
+      a *= p.unscale[row];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] *= st.alpha;
+      for (int j = 0; j < 32; ++j) v[j] *= a * ((j < n_valid) ? p.unscale[col0 + j] : 0.f);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] *= a;
+    }
     float* dst = p.C + static_cast<int64_t>(row) * p.ldc + col0;
     if (!p.atomic) {
       store_row32_f32(dst, v, n_valid, (p.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
@@ -95,11 +108,6 @@ struct EpiStoreF32 {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
         if (j < n_valid) red_add_f32(dst + j, v[j]);
-      if (p.mirror && tc.m != tc.n) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j < n_valid) red_add_f32(p.C + static_cast<int64_t>(col0 + j) * p.ldc + row, v[j]);
-      }
     }
   }
   __device__ static void tile_end(State&, const Params&, const EpiCtx&, const TileCoord&) {}
@@ -210,56 +218,81 @@ struct EpiPredictive {
 };
 
 // ---------------------------------------------------------------------------------------------
-// InfoNCE pass 1 (hessians.py:24-27): base-2 log-sum-exp of s * <x_b, y_c> over all targets, kept online
-// in registers across the N tiles of a row panel.   lse2[b] = log2 sum_c 2^(s*log2e*L_bc)
+// InfoNCE pass 1 (hessians.py:24-27): per source row, over all targets (online across the N tiles of a row panel):
+//   pivot = argmax_c l_bc,  m = max_c l_bc,  rest = sum_{c != pivot} 2^(l_bc - m)      with l = s*log2(e)*<xh_b, yh_c>
+// so that softmax(pivot) = 1/(1+rest) and 1 - softmax(pivot) = rest/(1+rest) are known WITHOUT cancellation.
+// (Peaked softmaxes make Yh^T diag(p) Yh - (Yh^T p)(Yh^T p)^T cancel catastrophically; the GGN pipeline therefore
+//  centres every row on its pivot target -- see kfac.cu.)
 // ---------------------------------------------------------------------------------------------
 template <int BN>
 struct EpiRowLse {
   static constexpr size_t SCRATCH_BYTES = 16;
   struct Params {
-    float* lse2;
-    float s_log2e;  // exp(logit_scale) * log2(e) / (operand scaling)
+    float* rowmax2;  // [B] m   (log2 units)
+    float* rest;     // [B]
+    int* pivot;      // [B]
+    float s_log2e;   // exp(logit_scale) * log2(e) / (operand scaling)
   };
   struct State {
-    float m, l;
+    float m, rest;
+    int piv;
   };
   __device__ static void item_begin(State& st, const Params&, const EpiCtx&, const TileCoord&) {
     st.m = -INFINITY;
-    st.l = 0.f;
+    st.rest = 0.f;
+    st.piv = 0;
   }
   __device__ static void tile_begin(State&, const Params&, const EpiCtx&, const TileCoord&) {}
   __device__ static void chunk(State& st, const Params& p, const EpiCtx& ctx, const TileCoord& tc, float (&v)[32], int c) {
-    const int n_valid = ctx.N - (tc.n * BN + c * 32);
+    const int col0 = tc.n * BN + c * 32;
+    const int n_valid = ctx.N - col0;
     float cm = -INFINITY;
+    int ci = 0;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       v[j] = j < n_valid ? v[j] * p.s_log2e : -INFINITY;
-      cm = fmaxf(cm, v[j]);
+      if (v[j] > cm) {
+        cm = v[j];
+        ci = j;
+      }
     }
-    const float m_new = fmaxf(st.m, cm);
+    const bool is_new = cm > st.m;  // strict: the first maximum stays the pivot on ties
+    const float m_new = is_new ? cm : st.m;
+    if (is_new) {
+      st.rest = (st.rest + 1.f) * fast_exp2(st.m - m_new);  // the old pivot joins the rest (0 on the first chunk)
+      st.piv = col0 + ci;
+    }
     float s0 = 0.f, s1 = 0.f;
 #pragma unroll
     for (int j = 0; j < 32; j += 2) {
-      s0 += fast_exp2(v[j] - m_new);
-      s1 += fast_exp2(v[j + 1] - m_new);
+      const float e0 = fast_exp2(v[j] - m_new);
+      const float e1 = fast_exp2(v[j + 1] - m_new);
+      s0 += (is_new && j == ci) ? 0.f : e0;
+      s1 += (is_new && j + 1 == ci) ? 0.f : e1;
     }
-    st.l = st.l * fast_exp2(st.m - m_new) + (s0 + s1);
+    st.rest += s0 + s1;
     st.m = m_new;
   }
   __device__ static void tile_end(State&, const Params&, const EpiCtx&, const TileCoord&) {}
   __device__ static void item_end(State& st, const Params& p, const EpiCtx& ctx, const TileCoord& tc) {
     const int row = epi_row(ctx, tc);
-    if (row < ctx.M) p.lse2[row] = st.m + log2f(st.l);
+    if (row < ctx.M) {
+      p.rowmax2[row] = st.m;
+      p.rest[row] = st.rest;
+      p.pivot[row] = st.piv;
+    }
   }
 };
 
 // ---------------------------------------------------------------------------------------------
 // GGN pass 2. For every (source b, target c) the per-pair curvature weight
-//     InfoNCE : omega = softmax_c(s L_b.)            (hessians.py:27)
+//     InfoNCE : omega = softmax_c(s L_b.) with the pivot target of the row masked to 0     (hessians.py:27)
 //     SigLIP  : omega = sigma(z)(1 - sigma(z)), z = s L + bias   (hessians.py:88-94, without the s^2 factor)
-// is written as fp16 (scaled by WSCALE so that 1/C-sized probabilities stay normal numbers), together with
-// omega * L; the weighted column sums q_c = sum_b w_b omega_bc are reduced in registers across the M tiles of
-// a column panel and written once (no atomics).
+// is written as fp16 (scaled by WSCALE so that 1/C-sized probabilities stay normal numbers) together with
+//     InfoNCE : omega * d,  d = l_bc - m_b  (log2-unit logit distance to the pivot, <= 0)
+//     SigLIP  : omega * L   (cosine)
+// and the weighted column sums q_c = sum_b w_b omega_bc are reduced in registers across the M tiles of a column
+// panel and written once (no atomics).
 // ---------------------------------------------------------------------------------------------
 constexpr float GGN_WSCALE = 4096.f;
 
@@ -267,19 +300,22 @@ template <int BN, bool SIGLIP>
 struct EpiGgnWeights {
   static constexpr size_t SCRATCH_BYTES = 4 * BN * sizeof(float);
   struct Params {
-    const float* lse2;  // InfoNCE only
-    const float* w;     // per-source weight (1/|x|^2, normalised)
-    __half* W16;        // [M_pad, ld] omega * WSCALE
-    __half* WL16;       // [M_pad, ld] omega * L * WSCALE
+    const float* rowmax2;  // InfoNCE only
+    const float* rest;     // InfoNCE only
+    const int* pivot;      // InfoNCE only
+    const float* w;        // per-source weight (1/|x|^2, normalised)
+    __half* W16;           // [M_pad, ld] omega * WSCALE           (InfoNCE only)
+    __half* WL16;          // [M_pad, ld] omega * (d | L) * WSCALE
     int64_t ld;
-    float* q;           // [N]
-    float s_log2e;      // InfoNCE: s*log2e/opscale ; SigLIP: s/opscale
-    float l_scale;      // 1/opscale: acc -> cosine
-    float bias;         // SigLIP logit bias
+    float* q;              // [N]
+    float s_log2e;         // InfoNCE: s*log2e/opscale ; SigLIP: s/opscale
+    float l_scale;         // 1/opscale: acc -> cosine
+    float bias;            // SigLIP logit bias
   };
   struct State {
     float q[BN / 32];
-    float lse2, w;
+    float m2, lg1pr, w;
+    int piv;
   };
   __device__ static void item_begin(State& st, const Params&, const EpiCtx&, const TileCoord&) {
 #pragma unroll
@@ -287,8 +323,13 @@ struct EpiGgnWeights {
   }
   __device__ static void tile_begin(State& st, const Params& p, const EpiCtx& ctx, const TileCoord& tc) {
     const int row = epi_row(ctx, tc);
-    st.w = row < ctx.M ? p.w[row] : 0.f;
-    if constexpr (!SIGLIP) st.lse2 = row < ctx.M ? p.lse2[row] : 0.f;
+    const bool ok = row < ctx.M;
+    st.w = ok ? p.w[row] : 0.f;
+    if constexpr (!SIGLIP) {
+      st.m2 = ok ? p.rowmax2[row] : 0.f;
+      st.lg1pr = ok ? log2f(1.f + p.rest[row]) : 0.f;
+      st.piv = ok ? p.pivot[row] : -1;
+    }
   }
   __device__ static void chunk(State& st, const Params& p, const EpiCtx& ctx, const TileCoord& tc, float (&v)[32], int c) {
     const int row = epi_row(ctx, tc);
@@ -304,8 +345,11 @@ struct EpiGgnWeights {
         const float t = fast_exp2(-fabsf(z) * 1.4426950408889634f);
         const float d = 1.f + t;
         o = __fdividef(t, d * d);
+        v[j] *= p.l_scale;  // cosine
       } else {
-        o = fast_exp2(fmaf(v[j], p.s_log2e, -st.lse2));
+        const float d = fmaf(v[j], p.s_log2e, -st.m2);  // <= 0, exactly 0 at the pivot
+        o = (col0 + j == st.piv) ? 0.f : fast_exp2(d - st.lg1pr);
+        v[j] = d;
       }
       om[j] = (row_ok && j < n_valid) ? o : 0.f;
     }
@@ -315,9 +359,9 @@ struct EpiGgnWeights {
       float t[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) t[j] = om[j] * GGN_WSCALE;
-      store_row32_f16(p.W16 + off, t, n_valid, al);
+      if constexpr (!SIGLIP) store_row32_f16(p.W16 + off, t, n_valid, al);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) t[j] *= v[j] * p.l_scale;
+      for (int j = 0; j < 32; ++j) t[j] *= v[j];
       store_row32_f16(p.WL16 + off, t, n_valid, al);
     }
 #pragma unroll

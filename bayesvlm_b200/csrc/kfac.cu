@@ -4,11 +4,22 @@
 //   K3  SigLIP  GGN w.r.t. embeddings    bayesvlm/hessians.py:50-117
 //
 // K2/K3 never form the reference's [B,D,D] / [B,C,D] / [chunk,D,D] temporaries.  With L = Xh Yh^T (cosines),
-// omega = softmax(sL) (InfoNCE) or sigma(z)(1-sigma(z)) (SigLIP), w_b = 1/|x_b|^2:
-//   q = sum_b w_b omega_b.          m = omega Yh          r = (omega .* L) Yh
-//   t_b = m_b.xh_b    u_b = r_b - m_b t_b  (InfoNCE)  |  u_b = r_b (SigLIP)     a_b = u_b.xh_b
-//   H = s^2 [ Yh^T diag(q) Yh - (w m)^T m - (w xh)^T u - (w u)^T xh + (w a xh)^T xh ]
-// which is four tensor-core GEMM passes over the class batch plus one stacked [D x (C+4B)] x [(C+4B) x D] GEMM.
+// w_b = 1/|x_b|^2, J_b = (I - xh xh^T)/|x_b| and the per-source curvature S_b in embedding space,
+//     H = s^2 sum_b w_b (I - xh xh^T) S_b (I - xh xh^T) = s^2 sum_b w_b [ S_b - xh u^T - u xh^T + a xh xh^T ],
+//     u = S_b xh,  a = xh^T S_b xh.
+// SigLIP:   S_b = Yh^T diag(lambda_b) Yh,  lambda = sigma(z)(1-sigma(z)).
+// InfoNCE:  S_b = Yh^T (diag p_b - p_b p_b^T) Yh is the covariance of the targets under softmax p_b.  For a peaked
+//   softmax the two terms cancel catastrophically (fp32 already loses digits, 16-bit operands lose everything), so
+//   every row is centred on its pivot target g = yh[argmax_c L_bc]:  with rho = 1 - p*, e = sum_{c!=piv} p_c (yh_c - g)
+//     S_b = sum_{c != piv} p_c yh_c yh_c^T  -  sym[ (e + (1-sqrt p*) g) (e + (1+sqrt p*) g)^T ]
+//   in which every term is O(rho) (rho itself comes from the online softmax of pass 1 without forming 1 - p*).
+// Pipeline per class batch (all GEMMs on the tcgen05 engine):
+//   pass 1 (InfoNCE)  row panels of Xh Yh^T  -> row max, pivot, rest = sum_{c!=piv} exp(l - max)
+//   pass 2            column panels of Xh Yh^T -> omega (fp16), omega*(d | L) (fp16), q_c = sum_b w_b omega_bc
+//   pass 3            [n ; r] = [omega ; omega*d] Yh
+//   finalise          per-source vectors e, u, a -> stacked operands
+//   pass 4            Hinc = [Yh sqrt(q) | L_A | L_B]^T [Yh sqrt(q) | R_A | R_B]   (K = C + 2B, split-K)
+//   H (+)= s^2 (Hinc + Hinc^T)/2
 #include "epilogues.cuh"
 #include "prep.cuh"
 
@@ -43,23 +54,23 @@ struct Carver {
 struct GgnLayout {
   int64_t Dp, Cp, Bp, Bs, Ktot;
   size_t bytes;
-  // offsets resolved by carve()
   __half *Xh16, *Yh16, *YhT16, *W16, *L16, *R16;
-  float *inv_nx, *inv_ny, *w_raw, *w, *scalars, *lse2, *q, *mult_y, *mult_sw, *mult_x_sw, *mult_x_wa, *mult_x, *MR;
+  float *inv_nx, *inv_ny, *w_raw, *w, *scalars, *rowmax2, *rest, *q, *mult_y, *mult_x, *MR, *RA, *Hinc;
+  int* pivot;
 };
 
-GgnLayout ggn_layout(int64_t B, int64_t C, int64_t D, int siglip, void* ws) {
+GgnLayout ggn_layout(int64_t B, int64_t C, int64_t D, int siglip, int prec, void* ws) {
   GgnLayout g{};
   g.Dp = pad64(D);
   g.Cp = pad64(C);
   g.Bp = pad64(B);
   g.Bs = pad128(B);
-  g.Ktot = g.Cp + (siglip ? 3 : 4) * g.Bp;
+  g.Ktot = g.Cp + (siglip ? 1 : 2) * g.Bp;
   Carver cv(ws);
-  g.Xh16 = cv.take<__half>(static_cast<size_t>(B) * g.Dp);
-  g.Yh16 = cv.take<__half>(static_cast<size_t>(C) * g.Dp);
+  g.Xh16 = cv.take<__half>(static_cast<size_t>(B) * g.Dp * prec);
+  g.Yh16 = cv.take<__half>(static_cast<size_t>(C) * g.Dp * prec);
   g.YhT16 = cv.take<__half>(static_cast<size_t>(D) * g.Cp);
-  g.W16 = cv.take<__half>(static_cast<size_t>(2 * g.Bs) * g.Cp);
+  g.W16 = cv.take<__half>(static_cast<size_t>(2 * g.Bs) * g.Cp);  // [omega ; omega*d] stacked (SigLIP uses the 2nd half)
   g.L16 = cv.take<__half>(static_cast<size_t>(D) * g.Ktot);
   g.R16 = cv.take<__half>(static_cast<size_t>(D) * g.Ktot);
   g.inv_nx = cv.take<float>(static_cast<size_t>(B));
@@ -67,14 +78,15 @@ GgnLayout ggn_layout(int64_t B, int64_t C, int64_t D, int siglip, void* ws) {
   g.w_raw = cv.take<float>(static_cast<size_t>(B));
   g.w = cv.take<float>(static_cast<size_t>(B));
   g.scalars = cv.take<float>(64);
-  g.lse2 = cv.take<float>(static_cast<size_t>(B));
+  g.rowmax2 = cv.take<float>(static_cast<size_t>(B));
+  g.rest = cv.take<float>(static_cast<size_t>(B));
+  g.pivot = cv.take<int>(static_cast<size_t>(B));
   g.q = cv.take<float>(static_cast<size_t>(C));
   g.mult_y = cv.take<float>(static_cast<size_t>(C));
-  g.mult_sw = cv.take<float>(static_cast<size_t>(B));
-  g.mult_x_sw = cv.take<float>(static_cast<size_t>(B));
-  g.mult_x_wa = cv.take<float>(static_cast<size_t>(B));
   g.mult_x = cv.take<float>(static_cast<size_t>(B));
   g.MR = cv.take<float>(static_cast<size_t>(2 * g.Bs) * D);
+  g.RA = cv.take<float>(static_cast<size_t>(B) * D);
+  g.Hinc = cv.take<float>(static_cast<size_t>(D) * D);
   g.bytes = cv.used() + 256;
   return g;
 }
@@ -84,28 +96,28 @@ __global__ void k_mean_weight(const float* __restrict__ w_sum, float inv_count, 
 }
 
 int ggn_impl(const float* X, int64_t B, int64_t ldx, const float* Y, int64_t C, int64_t ldy, int64_t D, float logit_scale,
-             float logit_bias, int siglip, float* H, int64_t ldh, int accumulate, void* ws, size_t ws_bytes,
+             float logit_bias, int siglip, int prec, float* H, int64_t ldh, int accumulate, void* ws, size_t ws_bytes,
              cudaStream_t st) {
   if (X == nullptr || Y == nullptr || H == nullptr || ws == nullptr) return BVLM_EINVAL;
+  if (prec != BVLM_PREC_X1 && prec != BVLM_PREC_X3) return BVLM_EINVAL;
   if (B <= 0 || C <= 0 || D <= 0 || ldx < D || ldy < D || ldh < D) return BVLM_EINVAL;
   if (B > (1 << 30) || C > (1 << 30)) return BVLM_EINVAL;
   if ((reinterpret_cast<uintptr_t>(ws) & 255) != 0) return BVLM_EINVAL;
-  GgnLayout g = ggn_layout(B, C, D, siglip, ws);
+  GgnLayout g = ggn_layout(B, C, D, siglip, prec, ws);
   if (ws_bytes < g.bytes) return BVLM_EWORKSPACE;
   int rc;
   const float s = expf(logit_scale);
   const float op2 = GGN_OPSCALE * GGN_OPSCALE;
+  constexpr float kLog2e = 1.4426950408889634f;
 
-  if (!accumulate) {
-    BVLM_CUDA_TRY(cudaMemset2DAsync(H, static_cast<size_t>(ldh) * 4, 0, static_cast<size_t>(D) * 4, static_cast<size_t>(D), st));
-  }
   BVLM_CUDA_TRY(cudaMemsetAsync(g.scalars, 0, 64 * sizeof(float), st));
+  BVLM_CUDA_TRY(cudaMemsetAsync(g.Hinc, 0, static_cast<size_t>(D) * D * sizeof(float), st));
   float* w_sum = g.scalars;
   float* wbar = g.scalars + 1;
 
   // ---- operand preparation
-  if ((rc = launch_ggn_row_prep(X, B, D, ldx, GGN_OPSCALE, g.Xh16, g.Dp, g.inv_nx, g.w_raw, w_sum, st))) return rc;
-  if ((rc = launch_ggn_row_prep(Y, C, D, ldy, GGN_OPSCALE, g.Yh16, g.Dp, g.inv_ny, nullptr, nullptr, st))) return rc;
+  if ((rc = launch_ggn_row_prep(X, B, D, ldx, GGN_OPSCALE, prec, 0, g.Xh16, g.Dp, g.inv_nx, g.w_raw, w_sum, st))) return rc;
+  if ((rc = launch_ggn_row_prep(Y, C, D, ldy, GGN_OPSCALE, prec, 1, g.Yh16, g.Dp, g.inv_ny, nullptr, nullptr, st))) return rc;
   if ((rc = launch_normalize_weights(g.w_raw, w_sum, B, g.w, st))) return rc;
   k_mean_weight<<<1, 32, 0, st>>>(w_sum, 1.0f / static_cast<float>(B), wbar);
   count_launch();
@@ -113,59 +125,64 @@ int ggn_impl(const float* X, int64_t B, int64_t ldx, const float* Y, int64_t C, 
     return rc;
 
   CUtensorMap tmX, tmY;
-  Operand16 opX{g.Xh16, B, g.Dp, FMT_F16};
-  Operand16 opY{g.Yh16, C, g.Dp, FMT_F16};
+  const int64_t Kl = g.Dp * prec;  // logit GEMM: X1 = one fp16 pass, X3 = hi.hi + lo.hi + hi.lo along K
+  Operand16 opX{g.Xh16, B, Kl, FMT_F16};
+  Operand16 opY{g.Yh16, C, Kl, FMT_F16};
   if ((rc = operand_tmap<GEMM_BM>(&tmX, opX))) return rc;
   if ((rc = operand_tmap<GGN_BN>(&tmY, opY))) return rc;
 
-  // ---- pass 1 (InfoNCE only): row log-sum-exp
+  // ---- pass 1 (InfoNCE only): row max, pivot, rest
   if (!siglip) {
-    GemmPlan p1 = make_plan<GGN_BN>(static_cast<int>(B), static_cast<int>(C), static_cast<int>(g.Dp), SCHED_ROW_PANEL, 1,
+    GemmPlan p1 = make_plan<GGN_BN>(static_cast<int>(B), static_cast<int>(C), static_cast<int>(Kl), SCHED_ROW_PANEL, 1,
                                     FMT_F16, FMT_F16);
-    EpiRowLse<GGN_BN>::Params e1{g.lse2, s * 1.4426950408889634f / op2};
+    EpiRowLse<GGN_BN>::Params e1{g.rowmax2, g.rest, g.pivot, s * kLog2e / op2};
     if ((rc = launch_gemm<GGN_BN, GGN_STAGES, EpiRowLse<GGN_BN>>(tmX, tmY, p1, e1, st))) return rc;
   }
 
-  // ---- pass 2: curvature weights omega (fp16), omega*L (fp16), q
+  // ---- pass 2: curvature weights omega (fp16), omega*(d|L) (fp16), q
   __half* W16 = g.W16;
   __half* WL16 = g.W16 + static_cast<size_t>(g.Bs) * g.Cp;
   {
-    GemmPlan p2 = make_plan<GGN_BN>(static_cast<int>(B), static_cast<int>(C), static_cast<int>(g.Dp), SCHED_COL_PANEL, 1,
+    GemmPlan p2 = make_plan<GGN_BN>(static_cast<int>(B), static_cast<int>(C), static_cast<int>(Kl), SCHED_COL_PANEL, 1,
                                     FMT_F16, FMT_F16);
     if (siglip) {
-      EpiGgnWeights<GGN_BN, true>::Params e2{nullptr, g.w, W16, WL16, g.Cp, g.q, s / op2, 1.0f / op2, logit_bias};
+      EpiGgnWeights<GGN_BN, true>::Params e2{nullptr, nullptr, nullptr, g.w, nullptr, WL16, g.Cp, g.q, s / op2, 1.0f / op2,
+                                             logit_bias};
       if ((rc = launch_gemm<GGN_BN, GGN_STAGES, EpiGgnWeights<GGN_BN, true>>(tmX, tmY, p2, e2, st))) return rc;
     } else {
-      EpiGgnWeights<GGN_BN, false>::Params e2{g.lse2, g.w, W16, WL16, g.Cp, g.q, s * 1.4426950408889634f / op2,
+      EpiGgnWeights<GGN_BN, false>::Params e2{g.rowmax2, g.rest, g.pivot, g.w, W16, WL16, g.Cp, g.q, s * kLog2e / op2,
                                               1.0f / op2, 0.f};
       if ((rc = launch_gemm<GGN_BN, GGN_STAGES, EpiGgnWeights<GGN_BN, false>>(tmX, tmY, p2, e2, st))) return rc;
     }
   }
   if (g.Cp != C) {  // K padding of pass 3 must be exact zeros
-    BVLM_CUDA_TRY(cudaMemset2DAsync(W16 + C, static_cast<size_t>(g.Cp) * 2, 0, static_cast<size_t>(g.Cp - C) * 2,
-                                    static_cast<size_t>(B), st));
+    if (!siglip)
+      BVLM_CUDA_TRY(cudaMemset2DAsync(W16 + C, static_cast<size_t>(g.Cp) * 2, 0, static_cast<size_t>(g.Cp - C) * 2,
+                                      static_cast<size_t>(B), st));
     BVLM_CUDA_TRY(cudaMemset2DAsync(WL16 + C, static_cast<size_t>(g.Cp) * 2, 0, static_cast<size_t>(g.Cp - C) * 2,
                                     static_cast<size_t>(B), st));
   }
 
-  // ---- pass 3: [m ; r] = [omega ; omega*L] Yh      (M = Bs + B stacked rows, K = C)
+  // ---- pass 3: InfoNCE [n ; r] = [omega ; omega*d] Yh (M = Bs + B stacked rows) | SigLIP r = (omega*L) Yh ; K = C
+  float* Nn = g.MR;
+  float* Rr = siglip ? g.MR : g.MR + static_cast<size_t>(g.Bs) * D;
   {
     CUtensorMap tmW, tmYT;
-    Operand16 opW{g.W16, g.Bs + B, g.Cp, FMT_F16};
+    Operand16 opW{siglip ? WL16 : W16, siglip ? B : g.Bs + B, g.Cp, FMT_F16};
     Operand16 opYT{g.YhT16, D, g.Cp, FMT_F16};
     if ((rc = operand_tmap<GEMM_BM>(&tmW, opW))) return rc;
     if ((rc = operand_tmap<GGN_BN>(&tmYT, opYT))) return rc;
-    GemmPlan p3 = make_plan<GGN_BN>(static_cast<int>(g.Bs + B), static_cast<int>(D), static_cast<int>(g.Cp), SCHED_TILES, 1,
+    GemmPlan p3 = make_plan<GGN_BN>(static_cast<int>(opW.rows), static_cast<int>(D), static_cast<int>(g.Cp), SCHED_TILES, 1,
                                     FMT_F16, FMT_F16);
-    EpiStoreF32<GGN_BN>::Params e3{g.MR, D, 1.0f, 0, 0, nullptr};
+    EpiStoreF32<GGN_BN>::Params e3{g.MR, D, 1.0f, 0, 0, nullptr, nullptr};
     if ((rc = launch_gemm<GGN_BN, GGN_STAGES, EpiStoreF32<GGN_BN>>(tmW, tmYT, p3, e3, st))) return rc;
   }
 
-  // ---- per-row finalisation and stacked operands
-  float* Mm = g.MR;
-  float* Ru = g.MR + static_cast<size_t>(g.Bs) * D;
-  if ((rc = launch_ggn_row_finalize(X, B, D, ldx, g.inv_nx, g.w, Mm, Ru, D, 1.0f / (GGN_WSCALE * GGN_OPSCALE), siglip,
-                                    GGN_G, g.mult_sw, g.mult_x_sw, g.mult_x_wa, g.mult_x, st)))
+  // ---- per-source finalisation and stacked operands of pass 4
+  const float unscale_n = 1.0f / (GGN_WSCALE * GGN_OPSCALE);
+  const float unscale_r = siglip ? unscale_n : unscale_n / (s * kLog2e);  // InfoNCE: d is in log2-logit units
+  if ((rc = launch_ggn_row_finalize(X, B, D, ldx, g.inv_nx, g.w, Y, ldy, g.inv_ny, g.pivot, g.rest, Nn, Rr, g.RA, D, unscale_n,
+                                    unscale_r, siglip, g.mult_x, st)))
     return rc;
   if ((rc = launch_ggn_col_mult(g.q, g.inv_ny, C, GGN_G, g.mult_y, st))) return rc;
 
@@ -175,25 +192,17 @@ int ggn_impl(const float* X, int64_t B, int64_t ldx, const float* Y, int64_t C, 
   if ((rc = launch_transpose_to_16(Y, C, D, ldy, g.mult_y, 0, nullptr, 1.f, 0, FMT_F16, g.L16, K, off, g.Cp, st))) return rc;
   if ((rc = launch_transpose_to_16(Y, C, D, ldy, g.mult_y, 0, nullptr, 1.f, 0, FMT_F16, g.R16, K, off, g.Cp, st))) return rc;
   off += g.Cp;
-  if (!siglip) {  // seg 1: -(w m)^T m
-    if ((rc = launch_transpose_to_16(Mm, B, D, D, g.mult_sw, 0, nullptr, -1.f, 0, FMT_F16, g.L16, K, off, g.Bp, st))) return rc;
-    if ((rc = launch_transpose_to_16(Mm, B, D, D, g.mult_sw, 0, nullptr, 1.f, 0, FMT_F16, g.R16, K, off, g.Bp, st))) return rc;
+  if (!siglip) {  // seg A: L_A^T R_A
+    if ((rc = launch_transpose_to_16(Nn, B, D, D, nullptr, 0, nullptr, GGN_G, 0, FMT_F16, g.L16, K, off, g.Bp, st))) return rc;
+    if ((rc = launch_transpose_to_16(g.RA, B, D, D, nullptr, 0, nullptr, GGN_G, 0, FMT_F16, g.R16, K, off, g.Bp, st))) return rc;
     off += g.Bp;
   }
-  // seg 2: -(w xh)^T u
-  if ((rc = launch_transpose_to_16(X, B, D, ldx, g.mult_x_sw, 0, nullptr, -1.f, 0, FMT_F16, g.L16, K, off, g.Bp, st))) return rc;
-  if ((rc = launch_transpose_to_16(Ru, B, D, D, g.mult_sw, 0, nullptr, 1.f, 0, FMT_F16, g.R16, K, off, g.Bp, st))) return rc;
-  off += g.Bp;
-  // seg 3: -(w u)^T xh
-  if ((rc = launch_transpose_to_16(Ru, B, D, D, g.mult_sw, 0, nullptr, -1.f, 0, FMT_F16, g.L16, K, off, g.Bp, st))) return rc;
-  if ((rc = launch_transpose_to_16(X, B, D, ldx, g.mult_x_sw, 0, nullptr, 1.f, 0, FMT_F16, g.R16, K, off, g.Bp, st))) return rc;
-  off += g.Bp;
-  // seg 4: (w a xh)^T xh
-  if ((rc = launch_transpose_to_16(X, B, D, ldx, g.mult_x_wa, 0, nullptr, 1.f, 0, FMT_F16, g.L16, K, off, g.Bp, st))) return rc;
-  if ((rc = launch_transpose_to_16(X, B, D, ldx, g.mult_x, 0, nullptr, 1.f, 0, FMT_F16, g.R16, K, off, g.Bp, st))) return rc;
+  // seg B: (-2 sqrt(w) xh)^T (sqrt(w) (u - a/2 xh))
+  if ((rc = launch_transpose_to_16(X, B, D, ldx, g.mult_x, 0, nullptr, GGN_G, 0, FMT_F16, g.L16, K, off, g.Bp, st))) return rc;
+  if ((rc = launch_transpose_to_16(Rr, B, D, D, nullptr, 0, nullptr, GGN_G, 0, FMT_F16, g.R16, K, off, g.Bp, st))) return rc;
   off += g.Bp;
 
-  // ---- final stacked GEMM, split along K, accumulated into H with red.global.add
+  // ---- pass 4: stacked GEMM, split along K, accumulated into Hinc with red.global.add
   {
     CUtensorMap tmL, tmR;
     Operand16 opL{g.L16, D, K, FMT_F16};
@@ -205,10 +214,11 @@ int ggn_impl(const float* X, int64_t B, int64_t ldx, const float* Y, int64_t C, 
     if (splits < 1) splits = 1;
     GemmPlan p4 = make_plan<GGN_BN>(static_cast<int>(D), static_cast<int>(D), static_cast<int>(K), SCHED_TILES, splits,
                                     FMT_F16, FMT_F16);
-    EpiStoreF32<GGN_BN>::Params e4{H, ldh, s * s / (GGN_G * GGN_G), 1, 0, wbar};
+    EpiStoreF32<GGN_BN>::Params e4{g.Hinc, D, 1.0f, 1, 0, nullptr, nullptr};
     if ((rc = launch_gemm<GGN_BN, GGN_STAGES, EpiStoreF32<GGN_BN>>(tmL, tmR, p4, e4, st))) return rc;
   }
-  return BVLM_OK;
+  // ---- H (+)= s^2 wbar / g^2 * (Hinc + Hinc^T)/2
+  return launch_sym_add(g.Hinc, D, D, H, ldh, s * s / (GGN_G * GGN_G), wbar, accumulate, st);
 }
 
 }  // namespace
@@ -218,7 +228,7 @@ extern "C" {
 size_t bvlm_syrk_workspace_bytes(int64_t n, int64_t d, int append_one, int precision) {
   (void)precision;
   const int64_t dA = d + (append_one ? 1 : 0);
-  return static_cast<size_t>(round_up_i64(dA * pad64(n) * 2, 256)) + 512;
+  return static_cast<size_t>(round_up_i64(dA * pad64(n) * 2, 256)) + 3 * static_cast<size_t>(round_up_i64(dA * 4, 256)) + 512;
 }
 
 int bvlm_syrk_f32acc(const float* X, int64_t n, int64_t d, int64_t ldx, int append_one, int precision, float* C,
@@ -231,16 +241,22 @@ int bvlm_syrk_f32acc(const float* X, int64_t n, int64_t d, int64_t ldx, int appe
   if ((reinterpret_cast<uintptr_t>(ws) & 255) != 0) return BVLM_EINVAL;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t Kp = pad64(n);
-  void* Xt16 = ws;
+  Carver cv(ws);
+  __half* Xt16 = cv.take<__half>(static_cast<size_t>(dA) * Kp);
+  float* scale = cv.take<float>(static_cast<size_t>(dA));
+  float* unscale = cv.take<float>(static_cast<size_t>(dA));
+  unsigned int* amax = cv.take<unsigned int>(static_cast<size_t>(dA));
   int rc;
   if (!accumulate) {
     BVLM_CUDA_TRY(cudaMemset2DAsync(C, static_cast<size_t>(ldc) * 4, 0, static_cast<size_t>(dA) * 4, static_cast<size_t>(dA), st));
   }
-  // [X 1]^T as a bf16 K-major operand: rows = features, K = samples
-  if ((rc = launch_transpose_to_16(X, n, d, ldx, nullptr, 0, nullptr, 1.f, append_one, FMT_BF16, Xt16, Kp, 0, Kp, st)))
+  // per-feature power-of-two scaling keeps every feature inside fp16's normal range whatever its magnitude
+  if ((rc = launch_col_pow2_scale(X, n, d, ldx, append_one, amax, scale, unscale, st))) return rc;
+  // [X 1]^T as an fp16 K-major operand: rows = features, K = samples
+  if ((rc = launch_transpose_to_16(X, n, d, ldx, nullptr, 0, scale, 1.f, append_one, FMT_F16, Xt16, Kp, 0, Kp, st)))
     return rc;
   CUtensorMap tmA, tmB;
-  Operand16 op{Xt16, dA, Kp, FMT_BF16};
+  Operand16 op{Xt16, dA, Kp, FMT_F16};
   if ((rc = operand_tmap<GEMM_BM>(&tmA, op))) return rc;
   if ((rc = operand_tmap<SYRK_BN>(&tmB, op))) return rc;
   const int m_tiles = static_cast<int>(ceil_div_i64(dA, GEMM_BM));
@@ -248,26 +264,29 @@ int bvlm_syrk_f32acc(const float* X, int64_t n, int64_t d, int64_t ldx, int appe
   int splits = device_sm_count() / tri;
   if (splits < 1) splits = 1;
   GemmPlan plan = make_plan<SYRK_BN>(static_cast<int>(dA), static_cast<int>(dA), static_cast<int>(Kp), SCHED_TRI_TILES,
-                                     splits, FMT_BF16, FMT_BF16);
-  EpiStoreF32<SYRK_BN>::Params ep{C, ldc, alpha, 1, 1, nullptr};
-  return launch_gemm<SYRK_BN, SYRK_STAGES, EpiStoreF32<SYRK_BN>>(tmA, tmB, plan, ep, st);
+                                     splits, FMT_F16, FMT_F16);
+  // lower triangle accumulated with red.global.add, then mirrored: C stays exactly symmetric
+  EpiStoreF32<SYRK_BN>::Params ep{C, ldc, alpha, 1, 1, nullptr, unscale};
+  if ((rc = launch_gemm<SYRK_BN, SYRK_STAGES, EpiStoreF32<SYRK_BN>>(tmA, tmB, plan, ep, st))) return rc;
+  return launch_symmetrize_scale(C, dA, ldc, 1.0f, st);
 }
 
-size_t bvlm_ggn_workspace_bytes(int64_t B, int64_t C, int64_t D) {
-  if (B <= 0 || C <= 0 || D <= 0) return 0;
-  return ggn_layout(B, C, D, 0, nullptr).bytes;
+size_t bvlm_ggn_workspace_bytes(int64_t B, int64_t C, int64_t D, int precision) {
+  if (B <= 0 || C <= 0 || D <= 0 || (precision != BVLM_PREC_X1 && precision != BVLM_PREC_X3)) return 0;
+  return ggn_layout(B, C, D, 0, precision, nullptr).bytes;
 }
 
 int bvlm_ggn_infonce(const float* X, int64_t B, int64_t ldx, const float* Y, int64_t C, int64_t ldy, int64_t D,
-                     float logit_scale, float* H, int64_t ldh, int accumulate, void* ws, size_t ws_bytes, void* stream) {
-  return ggn_impl(X, B, ldx, Y, C, ldy, D, logit_scale, 0.f, 0, H, ldh, accumulate, ws, ws_bytes,
+                     float logit_scale, int precision, float* H, int64_t ldh, int accumulate, void* ws, size_t ws_bytes,
+                     void* stream) {
+  return ggn_impl(X, B, ldx, Y, C, ldy, D, logit_scale, 0.f, 0, precision, H, ldh, accumulate, ws, ws_bytes,
                   static_cast<cudaStream_t>(stream));
 }
 
 int bvlm_ggn_siglip(const float* X, int64_t B, int64_t ldx, const float* Y, int64_t C, int64_t ldy, int64_t D,
-                    float logit_scale, float logit_bias, float* H, int64_t ldh, int accumulate, void* ws,
+                    float logit_scale, float logit_bias, int precision, float* H, int64_t ldh, int accumulate, void* ws,
                     size_t ws_bytes, void* stream) {
-  return ggn_impl(X, B, ldx, Y, C, ldy, D, logit_scale, logit_bias, 1, H, ldh, accumulate, ws, ws_bytes,
+  return ggn_impl(X, B, ldx, Y, C, ldy, D, logit_scale, logit_bias, 1, precision, H, ldh, accumulate, ws, ws_bytes,
                   static_cast<cudaStream_t>(stream));
 }
 

@@ -111,8 +111,9 @@ k_predictive_row_prep(const float* __restrict__ x, int64_t R, int64_t D, int64_t
 
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(ROW_BLOCK)
-k_ggn_row_prep(const float* __restrict__ x, int64_t R, int64_t D, int64_t ld, float opscale, __half* __restrict__ xhat,
-               int64_t d_pad, float* __restrict__ inv_norm, float* __restrict__ w_raw, float* __restrict__ w_sum) {
+k_ggn_row_prep(const float* __restrict__ x, int64_t R, int64_t D, int64_t ld, float opscale, int nsplit, int side,
+               __half* __restrict__ xhat, int64_t d_pad, float* __restrict__ inv_norm, float* __restrict__ w_raw,
+               float* __restrict__ w_sum) {
   __shared__ float s_w[WARPS_PER_BLOCK];
   const int warp = threadIdx.x >> 5;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * WARPS_PER_BLOCK + warp;
@@ -125,11 +126,18 @@ k_ggn_row_prep(const float* __restrict__ x, int64_t R, int64_t D, int64_t ld, fl
     n2 = warp_sum(n2);
     const float inv = 1.0f / sqrtf(n2);
     const float mul = inv * opscale;
-    __half* o = xhat + row * d_pad;
+    __half* o = xhat + row * d_pad * nsplit;
     for (int64_t j = 2 * lane; j < d_pad; j += 64) {
       const float v0 = j < D ? xr[j] * mul : 0.f;
       const float v1 = j + 1 < D ? xr[j + 1] * mul : 0.f;
-      *reinterpret_cast<__half2*>(o + j) = __floats2half2_rn(v0, v1);
+      const __half2 hi = __floats2half2_rn(v0, v1);
+      *reinterpret_cast<__half2*>(o + j) = hi;
+      if (nsplit == 3) {  // hi/lo split: A side packs [hi|lo|hi], B side [hi|hi|lo] -> hi.hi + lo.hi + hi.lo
+        const float2 hf = __half22float2(hi);
+        const __half2 lo = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+        *reinterpret_cast<__half2*>(o + d_pad + j) = side == 0 ? lo : hi;
+        *reinterpret_cast<__half2*>(o + 2 * d_pad + j) = side == 0 ? hi : lo;
+      }
     }
     wr = inv * inv;
     if (lane == 0) {
@@ -159,7 +167,7 @@ __global__ void k_normalize_weights(const float* __restrict__ w_raw, const float
 // 64 (r) x 32 (j) tile; block (32, 8)
 __global__ void __launch_bounds__(256)
 k_transpose_to_16(const float* __restrict__ src, int64_t R, int64_t d, int64_t ld, const float* __restrict__ mult,
-                  int sqrt_mult, const float* __restrict__ mult2, float gmult, int append_one, int fmt,
+                  int sqrt_mult, const float* __restrict__ jmult, float gmult, int append_one, int fmt,
                   uint16_t* __restrict__ dst, int64_t ldo, int64_t col_off, int64_t R_pad) {
   __shared__ float tile[64][33];
   const int tx = threadIdx.x, ty = threadIdx.y;
@@ -178,7 +186,7 @@ k_transpose_to_16(const float* __restrict__ src, int64_t R, int64_t d, int64_t l
         const float mv = mult[r];
         m *= sqrt_mult ? sqrtf(fmaxf(mv, 0.f)) : mv;
       }
-      if (mult2 != nullptr) m *= mult2[r];
+      if (jmult != nullptr && j < d + (append_one ? 1 : 0)) m *= jmult[j];
       if (j < d) v = src[r * ld + j] * m;
       else if (j == d && append_one) v = m;
     }
@@ -199,49 +207,103 @@ k_transpose_to_16(const float* __restrict__ src, int64_t R, int64_t d, int64_t l
 }
 
 // ------------------------------------------------------------------------------------------------
+// Per-source finalisation of the pivot-centred GGN (see kfac.cu). One warp per source row.
 __global__ void __launch_bounds__(ROW_BLOCK)
 k_ggn_row_finalize(const float* __restrict__ x, int64_t B, int64_t D, int64_t ldx, const float* __restrict__ inv_norm,
-                   const float* __restrict__ w, float* __restrict__ Mraw, float* __restrict__ Rraw, int64_t ldm,
-                   float unscale, int siglip, float g, float* __restrict__ mult_sw, float* __restrict__ mult_x_sw,
-                   float* __restrict__ mult_x_wa, float* __restrict__ mult_x) {
+                   const float* __restrict__ w, const float* __restrict__ y, int64_t ldy,
+                   const float* __restrict__ inv_norm_y, const int* __restrict__ pivot, const float* __restrict__ rest,
+                   float* __restrict__ Nraw, float* __restrict__ Rraw, float* __restrict__ RA, int64_t ldm,
+                   float unscale_n, float unscale_r, int siglip, float* __restrict__ mult_x) {
   const int64_t row = static_cast<int64_t>(blockIdx.x) * WARPS_PER_BLOCK + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= B) return;
   const float inv = inv_norm[row];
+  const float sw = sqrtf(fmaxf(w[row], 0.f));
   const float* xr = x + row * ldx;
-  float* mr = Mraw + row * ldm;
   float* rr = Rraw + row * ldm;
-  float t = 0.f, rx = 0.f;
-  for (int64_t j = lane; j < D; j += 32) {
-    const float xh = xr[j] * inv;
-    t = fmaf(mr[j] * unscale, xh, t);
-    rx = fmaf(rr[j] * unscale, xh, rx);
-  }
-  t = warp_sum(t);
-  rx = warp_sum(rx);
-  float a;
   if (siglip) {
-    a = rx;
-    for (int64_t j = lane; j < D; j += 32) rr[j] = rr[j] * unscale;
+    // u = r (cosine-weighted), a = u.xh ;  R_B = sqrt(w) (u - a/2 xh)
+    float a = 0.f;
+    for (int64_t j = lane; j < D; j += 32) a = fmaf(rr[j] * unscale_r, xr[j] * inv, a);
+    a = warp_sum(a);
+    for (int64_t j = lane; j < D; j += 32) rr[j] = sw * fmaf(-0.5f * a, xr[j] * inv, rr[j] * unscale_r);
   } else {
-    float acc = 0.f;
+    const int pv = pivot[row];
+    const float* gr = y + static_cast<int64_t>(pv) * ldy;
+    const float ginv = inv_norm_y[pv];
+    const float rs = rest[row];
+    const float rho = rs / (1.f + rs);         // 1 - softmax(pivot), no cancellation
+    const float sq = sqrtf(1.f / (1.f + rs));  // sqrt(softmax(pivot))
+    const float c1 = rho / (1.f + sq);         // 1 - sqrt(p*)
+    const float c2 = 1.f + sq;
+    float* nr = Nraw + row * ldm;
+    float* ra = RA + row * ldm;
+    // e = n - rho g ; tau = e.xh
+    float tau = 0.f;
     for (int64_t j = lane; j < D; j += 32) {
-      const float m = mr[j] * unscale;
-      const float u = fmaf(-m, t, rr[j] * unscale);
-      mr[j] = m;
-      rr[j] = u;
-      acc = fmaf(u, xr[j] * inv, acc);
+      const float e = fmaf(-rho, gr[j] * ginv, nr[j] * unscale_n);
+      tau = fmaf(e, xr[j] * inv, tau);
     }
-    a = warp_sum(acc);
+    tau = warp_sum(tau);
+    // u = r'' - tau (g + e) ; a = u.xh
+    float a = 0.f;
+    for (int64_t j = lane; j < D; j += 32) {
+      const float g = gr[j] * ginv;
+      const float e = fmaf(-rho, g, nr[j] * unscale_n);
+      const float u = fmaf(-tau, g + e, rr[j] * unscale_r);
+      a = fmaf(u, xr[j] * inv, a);
+    }
+    a = warp_sum(a);
+    for (int64_t j = lane; j < D; j += 32) {
+      const float g = gr[j] * ginv;
+      const float e = fmaf(-rho, g, nr[j] * unscale_n);
+      const float u = fmaf(-tau, g + e, rr[j] * unscale_r);
+      nr[j] = -sw * fmaf(c1, g, e);                       // L_A
+      ra[j] = sw * fmaf(c2, g, e);                        // R_A
+      rr[j] = sw * fmaf(-0.5f * a, xr[j] * inv, u);       // R_B
+    }
   }
-  if (lane == 0) {
-    const float wv = w[row];
-    const float sw = sqrtf(fmaxf(wv, 0.f));
-    mult_sw[row] = g * sw;
-    mult_x_sw[row] = g * sw * inv;
-    mult_x_wa[row] = g * wv * a * inv;
-    mult_x[row] = g * inv;
+  if (lane == 0) mult_x[row] = -2.f * sw * inv;           // L_B = -2 sqrt(w) xh, written by the transposing writer
+}
+
+// out (+)= alpha * alpha_dev * (S + S^T) / 2
+__global__ void k_sym_add(const float* __restrict__ S, int64_t d, int64_t lds, float* __restrict__ out, int64_t ldo,
+                          float alpha, const float* __restrict__ alpha_dev, int accumulate) {
+  const int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t i = blockIdx.y;
+  if (j >= d || i >= d) return;
+  const float a = alpha_dev != nullptr ? alpha * (*alpha_dev) : alpha;
+  const float v = 0.5f * a * (S[i * lds + j] + S[j * lds + i]);
+  out[i * ldo + j] = accumulate ? out[i * ldo + j] + v : v;
+}
+
+// per-feature |max| over the rows (atomicMax on the bit pattern of non-negative floats)
+__global__ void __launch_bounds__(256) k_col_absmax(const float* __restrict__ x, int64_t n, int64_t d, int64_t ld,
+                                                    int rows_per_block, unsigned int* __restrict__ amax_bits) {
+  const int64_t j = static_cast<int64_t>(blockIdx.x) * 32 + threadIdx.x;
+  const int64_t r0 = static_cast<int64_t>(blockIdx.y) * rows_per_block;
+  if (j >= d) return;
+  float m = 0.f;
+  const int64_t r1 = r0 + rows_per_block < n ? r0 + rows_per_block : n;
+  for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) m = fmaxf(m, fabsf(x[r * ld + j]));
+  if (m > 0.f && isfinite(m)) atomicMax(amax_bits + j, __float_as_uint(m));
+}
+
+// scale[j] = 2^e with absmax * 2^e in [512, 1024); unscale[j] = 2^-e. Feature d (the ones column) gets absmax 1.
+__global__ void k_col_pow2_scale(const unsigned int* __restrict__ amax_bits, int64_t d, int append_one,
+                                 float* __restrict__ scale, float* __restrict__ unscale) {
+  const int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (j >= d + (append_one ? 1 : 0)) return;
+  const float amax = j < d ? __uint_as_float(amax_bits[j]) : 1.f;
+  int e = 0;
+  if (amax > 0.f) {
+    int ex;
+    frexpf(amax, &ex);
+    e = 10 - ex;
+    e = e < -60 ? -60 : (e > 60 ? 60 : e);
   }
+  scale[j] = ldexpf(1.f, e);
+  unscale[j] = ldexpf(1.f, -e);
 }
 
 __global__ void k_ggn_col_mult(const float* __restrict__ q, const float* __restrict__ inv_norm_y, int64_t C, float g,
@@ -333,10 +395,11 @@ int launch_predictive_row_prep(const float* x, int64_t R, int64_t D, int64_t ld,
   return BVLM_OK;
 }
 
-int launch_ggn_row_prep(const float* x, int64_t R, int64_t D, int64_t ld, float opscale, __half* xhat, int64_t d_pad,
-                        float* inv_norm, float* w_raw, float* w_sum, cudaStream_t st) {
+int launch_ggn_row_prep(const float* x, int64_t R, int64_t D, int64_t ld, float opscale, int nsplit, int side, __half* xhat,
+                        int64_t d_pad, float* inv_norm, float* w_raw, float* w_sum, cudaStream_t st) {
   if (R <= 0) return BVLM_OK;
-  k_ggn_row_prep<<<row_grid(R), ROW_BLOCK, 0, st>>>(x, R, D, ld, opscale, xhat, d_pad, inv_norm, w_raw, w_sum);
+  if (nsplit != 1 && nsplit != 3) return BVLM_EINVAL;
+  k_ggn_row_prep<<<row_grid(R), ROW_BLOCK, 0, st>>>(x, R, D, ld, opscale, nsplit, side, xhat, d_pad, inv_norm, w_raw, w_sum);
   count_launch();
   BVLM_CUDA_TRY(cudaGetLastError());
   return BVLM_OK;
@@ -351,14 +414,14 @@ int launch_normalize_weights(const float* w_raw, const float* w_sum, int64_t R, 
 }
 
 int launch_transpose_to_16(const float* src, int64_t R, int64_t d, int64_t ld, const float* mult, int sqrt_mult,
-                           const float* mult2, float gmult, int append_one, int fmt, void* dst, int64_t ldo,
+                           const float* jmult, float gmult, int append_one, int fmt, void* dst, int64_t ldo,
                            int64_t col_off, int64_t R_pad, cudaStream_t st) {
   if (R_pad <= 0) return BVLM_OK;
   if ((R_pad & 1) || (col_off & 1) || (ldo & 1)) return BVLM_EINVAL;
   const int64_t d_rows = d + (append_one ? 1 : 0);
   dim3 grid(static_cast<unsigned>((R_pad + 63) / 64), static_cast<unsigned>((d_rows + 31) / 32));
   dim3 block(32, 8);
-  k_transpose_to_16<<<grid, block, 0, st>>>(src, R, d, ld, mult, sqrt_mult, mult2, gmult, append_one, fmt,
+  k_transpose_to_16<<<grid, block, 0, st>>>(src, R, d, ld, mult, sqrt_mult, jmult, gmult, append_one, fmt,
                                             static_cast<uint16_t*>(dst), ldo, col_off, R_pad);
   count_launch();
   BVLM_CUDA_TRY(cudaGetLastError());
@@ -366,11 +429,37 @@ int launch_transpose_to_16(const float* src, int64_t R, int64_t d, int64_t ld, c
 }
 
 int launch_ggn_row_finalize(const float* x, int64_t B, int64_t D, int64_t ldx, const float* inv_norm, const float* w,
-                            float* Mraw, float* Rraw, int64_t ldm, float unscale, int siglip, float g, float* mult_sw,
-                            float* mult_x_sw, float* mult_x_wa, float* mult_x, cudaStream_t st) {
+                            const float* y, int64_t ldy, const float* inv_norm_y, const int* pivot, const float* rest,
+                            float* Nraw, float* Rraw, float* RA, int64_t ldm, float unscale_n, float unscale_r, int siglip,
+                            float* mult_x, cudaStream_t st) {
   if (B <= 0) return BVLM_OK;
-  k_ggn_row_finalize<<<row_grid(B), ROW_BLOCK, 0, st>>>(x, B, D, ldx, inv_norm, w, Mraw, Rraw, ldm, unscale, siglip, g,
-                                                        mult_sw, mult_x_sw, mult_x_wa, mult_x);
+  k_ggn_row_finalize<<<row_grid(B), ROW_BLOCK, 0, st>>>(x, B, D, ldx, inv_norm, w, y, ldy, inv_norm_y, pivot, rest, Nraw,
+                                                        Rraw, RA, ldm, unscale_n, unscale_r, siglip, mult_x);
+  count_launch();
+  BVLM_CUDA_TRY(cudaGetLastError());
+  return BVLM_OK;
+}
+
+int launch_sym_add(const float* S, int64_t d, int64_t lds, float* out, int64_t ldo, float alpha, const float* alpha_dev,
+                   int accumulate, cudaStream_t st) {
+  if (d <= 0) return BVLM_OK;
+  dim3 grid(static_cast<unsigned>((d + 255) / 256), static_cast<unsigned>(d));
+  k_sym_add<<<grid, 256, 0, st>>>(S, d, lds, out, ldo, alpha, alpha_dev, accumulate);
+  count_launch();
+  BVLM_CUDA_TRY(cudaGetLastError());
+  return BVLM_OK;
+}
+
+int launch_col_pow2_scale(const float* x, int64_t n, int64_t d, int64_t ld, int append_one, unsigned int* amax_bits,
+                          float* scale, float* unscale, cudaStream_t st) {
+  if (n <= 0 || d <= 0) return BVLM_OK;
+  BVLM_CUDA_TRY(cudaMemsetAsync(amax_bits, 0, static_cast<size_t>(d) * sizeof(unsigned int), st));
+  const int rows_per_block = 256;
+  dim3 grid(static_cast<unsigned>((d + 31) / 32), static_cast<unsigned>((n + rows_per_block - 1) / rows_per_block));
+  k_col_absmax<<<grid, dim3(32, 8), 0, st>>>(x, n, d, ld, rows_per_block, amax_bits);
+  count_launch();
+  const int64_t dA = d + (append_one ? 1 : 0);
+  k_col_pow2_scale<<<static_cast<unsigned>((dA + 255) / 256), 256, 0, st>>>(amax_bits, d, append_one, scale, unscale);
   count_launch();
   BVLM_CUDA_TRY(cudaGetLastError());
   return BVLM_OK;

@@ -21,27 +21,40 @@ int launch_predictive_row_prep(const float* x, int64_t R, int64_t D, int64_t ld,
                                int nsplit, float opscale, __half* packed, int64_t seg_pad, float* out0, float* out1,
                                cudaStream_t st);
 
-// GGN row prep (hessians.py:15-21): xhat = x/|x| * opscale -> fp16 [R, d_pad]; inv_norm[r] = 1/|x_r|;
+// GGN row prep (hessians.py:15-21): xhat = x/|x| * opscale -> fp16 [R, nsplit * d_pad] (nsplit 3: hi/lo packing as in
+// launch_predictive_row_prep, side 0 = A operand, 1 = B operand); inv_norm[r] = 1/|x_r|;
 // w_raw[r] = 1/|x_r|^2 ; *w_sum += sum_r w_raw[r] (atomic).
-int launch_ggn_row_prep(const float* x, int64_t R, int64_t D, int64_t ld, float opscale, __half* xhat, int64_t d_pad,
-                        float* inv_norm, float* w_raw, float* w_sum, cudaStream_t st);
+int launch_ggn_row_prep(const float* x, int64_t R, int64_t D, int64_t ld, float opscale, int nsplit, int side, __half* xhat,
+                        int64_t d_pad, float* inv_norm, float* w_raw, float* w_sum, cudaStream_t st);
 
 // w[r] = w_raw[r] * R / *w_sum   (mean-one weights keep the fp16 operands of the final GEMM in range)
 int launch_normalize_weights(const float* w_raw, const float* w_sum, int64_t R, float* w, cudaStream_t st);
 
-// Transposing writer: dst[j * ldo + col_off + r] = fmt( sign * src[r * ld + j] * mult[r] * gmult ), r < R, j < d;
+// Transposing writer: dst[j * ldo + col_off + r] = fmt( src[r * ld + j] * mult[r] * jmult[j] * gmult ), r < R, j < d;
 // an optional ones row (j == d) is appended when append_one; columns r in [R, R_pad) are zero-filled.
-// mult may be null (1). sqrt_mult=1 uses sqrt(max(mult,0)).
+// mult / jmult may be null (1). sqrt_mult=1 uses sqrt(max(mult,0)).
 int launch_transpose_to_16(const float* src, int64_t R, int64_t d, int64_t ld, const float* mult, int sqrt_mult,
-                           const float* mult2, float gmult, int append_one, int fmt, void* dst, int64_t ldo,
+                           const float* jmult, float gmult, int append_one, int fmt, void* dst, int64_t ldo,
                            int64_t col_off, int64_t R_pad, cudaStream_t st);
 
-// GGN per-row finalisation (collapsed form of hessians.py:30-46 / 103-113):
-//   m = Mraw[b] * unscale, r = Rraw[b] * unscale, t = m.xhat, u = r - m t (InfoNCE) or r (SigLIP), a = u.xhat
-// writes m and u back in place (fp32) and the row multipliers used by the transposing writer.
+// Per-source finalisation of the pivot-centred GGN (collapsed form of hessians.py:30-46 / 103-113; see kfac.cu).
+//   InfoNCE: n = Nraw*unscale_n, r'' = Rraw*unscale_r, g = yh[pivot], rho = rest/(1+rest), p* = 1/(1+rest)
+//            e = n - rho g, tau = e.xh, u = r'' - tau (g + e), a = u.xh
+//            Nraw <- L_A = -sqrt(w)(e + (1-sqrt p*) g),  RA <- R_A = sqrt(w)(e + (1+sqrt p*) g),  Rraw <- R_B = sqrt(w)(u - a/2 xh)
+//   SigLIP : u = Rraw*unscale_r, a = u.xh, Rraw <- R_B
+//   mult_x[b] = -2 sqrt(w_b)/|x_b|   (row multiplier that turns X into L_B)
 int launch_ggn_row_finalize(const float* x, int64_t B, int64_t D, int64_t ldx, const float* inv_norm, const float* w,
-                            float* Mraw, float* Rraw, int64_t ldm, float unscale, int siglip, float g, float* mult_sw,
-                            float* mult_x_sw, float* mult_x_wa, float* mult_x, cudaStream_t st);
+                            const float* y, int64_t ldy, const float* inv_norm_y, const int* pivot, const float* rest,
+                            float* Nraw, float* Rraw, float* RA, int64_t ldm, float unscale_n, float unscale_r, int siglip,
+                            float* mult_x, cudaStream_t st);
+
+// out (+)= alpha * (*alpha_dev) * (S + S^T) / 2
+int launch_sym_add(const float* S, int64_t d, int64_t lds, float* out, int64_t ldo, float alpha, const float* alpha_dev,
+                   int accumulate, cudaStream_t st);
+
+// per-feature power-of-two scale: scale[j] = 2^e_j with max_r |x_rj| 2^e_j in [512,1024); unscale[j] = 2^-e_j
+int launch_col_pow2_scale(const float* x, int64_t n, int64_t d, int64_t ld, int append_one, unsigned int* amax_bits,
+                          float* scale, float* unscale, cudaStream_t st);
 
 // mult_y[c] = g * sqrt(max(q_c,0)) / |y_c|
 int launch_ggn_col_mult(const float* q, const float* inv_norm_y, int64_t C, float g, float* mult_y, cudaStream_t st);

@@ -22,8 +22,13 @@ from ._lib import lib
 # ----------------------------------------------------------------------------------------------------------------------
 # K2 / K3: analytic GGN of the contrastive losses w.r.t. the source embeddings
 # ----------------------------------------------------------------------------------------------------------------------
+# Source batches below this size evaluate the logits with the hi/lo split (~fp32): a single fp16 pass perturbs every
+# logit by ~ s * 2^-11 / sqrt(D), which only averages out over thousands of sources (the KFAC class batches).
+GGN_SPLIT_LOGITS_BELOW = 8192
+
+
 def _ggn(source: torch.Tensor, target: torch.Tensor, logit_scale, logit_bias, siglip: bool,
-         out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+         out: Optional[torch.Tensor] = None, accumulate: bool = False, precision: Optional[str] = None) -> torch.Tensor:
     source = _lib.rowmajor(_lib.require_cuda(source, "source embeddings"))
     target = _lib.rowmajor(_lib.require_cuda(target, "target embeddings"))
     if source.dim() != 2 or target.dim() != 2:
@@ -38,16 +43,20 @@ def _ggn(source: torch.Tensor, target: torch.Tensor, logit_scale, logit_bias, si
         if not accumulate:
             out.zero_()
         return out
-    ws = _lib.workspace(dev, lib.bvlm_ggn_workspace_bytes(b, c, d), tag="ggn")
+    if precision is None:
+        prec = _lib.PREC_X3 if b < GGN_SPLIT_LOGITS_BELOW else _lib.PREC_X1
+    else:
+        prec = {"fp16": _lib.PREC_X1, "fp16x3": _lib.PREC_X3}[precision]
+    ws = _lib.workspace(dev, lib.bvlm_ggn_workspace_bytes(b, c, d, prec), tag="ggn")
     ls = float(logit_scale)
     if siglip:
         rc = lib.bvlm_ggn_siglip(_lib.ptr(source), b, source.stride(0), _lib.ptr(target), c, target.stride(0), d, ls,
-                                 float(logit_bias), _lib.ptr(out), out.stride(0), int(accumulate), _lib.ptr(ws), ws.numel(),
+                                 float(logit_bias), prec, _lib.ptr(out), out.stride(0), int(accumulate), _lib.ptr(ws), ws.numel(),
                                  _lib.stream_ptr(dev))
         _lib.check(rc, "bvlm_ggn_siglip")
     else:
         rc = lib.bvlm_ggn_infonce(_lib.ptr(source), b, source.stride(0), _lib.ptr(target), c, target.stride(0), d, ls,
-                                  _lib.ptr(out), out.stride(0), int(accumulate), _lib.ptr(ws), ws.numel(),
+                                  prec, _lib.ptr(out), out.stride(0), int(accumulate), _lib.ptr(ws), ws.numel(),
                                   _lib.stream_ptr(dev))
         _lib.check(rc, "bvlm_ggn_infonce")
     return out

@@ -31,7 +31,7 @@ extern "C" {
 #define BVLM_EWORKSPACE (-4)
 
 /* precision of the mean-logit / SYRK contractions: operands are rounded to 16 bit, accumulation is fp32.
- * BVLM_PREC_X1: single pass (fp16 for unit-norm embeddings, bf16 for raw activations).
+ * BVLM_PREC_X1: single fp16 pass (unit-norm embeddings as they are; raw activations with per-feature power-of-two scaling).
  * BVLM_PREC_X3: hi/lo split, three tensor-core passes (a_hi b_hi + a_lo b_hi + a_hi b_lo), ~2^-22 relative. */
 #define BVLM_PREC_X1 1
 #define BVLM_PREC_X3 3
@@ -54,13 +54,17 @@ int bvlm_syrk_f32acc(const float* X, int64_t n, int64_t d, int64_t ldx, int appe
  * K2 / K3 -- per-class-batch GGN of the contrastive loss w.r.t. the source embeddings (the KFAC B factor):
  *   H (+)= sum_b J_b^T Hess_b J_b     bayesvlm/hessians.py:10-48 (InfoNCE), :50-117 (SigLIP)
  * X [B, D] sources, Y [C, D] targets (un-normalised), logit_scale in log space (exp applied inside).
- * H [D, D] fp32 (pitch ldh); accumulate = 0 zeroes H first.
+ * H [D, D] fp32 (pitch ldh); accumulate = 0 overwrites H.  The increment is exactly symmetric.
+ * precision: BVLM_PREC_X1 evaluates the logits s*<xh,yh> from fp16 operands (logit error ~ s*2^-11/sqrt(D) per pair,
+ * which averages out over a class batch of thousands of sources); BVLM_PREC_X3 uses the hi/lo split (~fp32 logits)
+ * and is what small source batches need (e.g. the single-sample update of bayesvlm/epig.py:242-246).
  * --------------------------------------------------------------------------------------------------------- */
-size_t bvlm_ggn_workspace_bytes(int64_t B, int64_t C, int64_t D);
+size_t bvlm_ggn_workspace_bytes(int64_t B, int64_t C, int64_t D, int precision);
 int bvlm_ggn_infonce(const float* X, int64_t B, int64_t ldx, const float* Y, int64_t C, int64_t ldy, int64_t D,
-                     float logit_scale, float* H, int64_t ldh, int accumulate, void* ws, size_t ws_bytes, void* stream);
+                     float logit_scale, int precision, float* H, int64_t ldh, int accumulate, void* ws, size_t ws_bytes,
+                     void* stream);
 int bvlm_ggn_siglip(const float* X, int64_t B, int64_t ldx, const float* Y, int64_t C, int64_t ldy, int64_t D,
-                    float logit_scale, float logit_bias, float* H, int64_t ldh, int accumulate, void* ws,
+                    float logit_scale, float logit_bias, int precision, float* H, int64_t ldh, int accumulate, void* ws,
                     size_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
