@@ -286,7 +286,7 @@ struct EpiRowLse {
 
 // ---------------------------------------------------------------------------------------------
 // GGN pass 2. For every (source b, target c) the per-pair curvature weight
-//     InfoNCE : omega = softmax_c(s L_b.) with the pivot target of the row masked to 0     (hessians.py:27)
+//     InfoNCE : omega = softmax_c(s L_b.) / (1 - p*_b) with the pivot target of the row masked to 0   (hessians.py:27)
 //     SigLIP  : omega = sigma(z)(1 - sigma(z)), z = s L + bias   (hessians.py:88-94, without the s^2 factor)
 // is written as fp16 (scaled by WSCALE so that 1/C-sized probabilities stay normal numbers) together with
 //     InfoNCE : omega * d,  d = l_bc - m_b  (log2-unit logit distance to the pivot, <= 0)
@@ -295,6 +295,9 @@ struct EpiRowLse {
 // panel and written once (no atomics).
 // ---------------------------------------------------------------------------------------------
 constexpr float GGN_WSCALE = 4096.f;
+// InfoNCE: |d| reaches 2 s log2(e) (~290 at s = 100) while the conditional weight of the runner-up target is ~1, so
+// omega * d is stored with a smaller scale than omega itself to stay inside fp16 (max 65504).
+constexpr float GGN_WDSCALE = 64.f;
 
 template <int BN, bool SIGLIP>
 struct EpiGgnWeights {
@@ -327,7 +330,11 @@ struct EpiGgnWeights {
     st.w = ok ? p.w[row] : 0.f;
     if constexpr (!SIGLIP) {
       st.m2 = ok ? p.rowmax2[row] : 0.f;
-      st.lg1pr = ok ? log2f(1.f + p.rest[row]) : 0.f;
+      // omega is stored as the CONDITIONAL distribution over the non-pivot targets, p_c / (1 - p*) in [0,1]: a peaked
+      // row keeps full fp16 precision however small 1 - p* is; the factor rho = rest/(1+rest) is re-applied in fp32
+      const float rs = ok ? p.rest[row] : 0.f;
+      st.lg1pr = rs > 0.f ? log2f(rs) : INFINITY;
+      st.w *= rs / (1.f + rs);
       st.piv = ok ? p.pivot[row] : -1;
     }
   }
@@ -361,7 +368,7 @@ struct EpiGgnWeights {
       for (int j = 0; j < 32; ++j) t[j] = om[j] * GGN_WSCALE;
       if constexpr (!SIGLIP) store_row32_f16(p.W16 + off, t, n_valid, al);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) t[j] *= v[j];
+      for (int j = 0; j < 32; ++j) t[j] *= v[j] * (SIGLIP ? 1.f : GGN_WDSCALE / GGN_WSCALE);
       store_row32_f16(p.WL16 + off, t, n_valid, al);
     }
 #pragma unroll

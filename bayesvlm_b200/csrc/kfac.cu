@@ -91,10 +91,6 @@ GgnLayout ggn_layout(int64_t B, int64_t C, int64_t D, int siglip, int prec, void
   return g;
 }
 
-__global__ void k_mean_weight(const float* __restrict__ w_sum, float inv_count, float* __restrict__ wbar) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) *wbar = *w_sum * inv_count;
-}
-
 int ggn_impl(const float* X, int64_t B, int64_t ldx, const float* Y, int64_t C, int64_t ldy, int64_t D, float logit_scale,
              float logit_bias, int siglip, int prec, float* H, int64_t ldh, int accumulate, void* ws, size_t ws_bytes,
              cudaStream_t st) {
@@ -113,14 +109,11 @@ int ggn_impl(const float* X, int64_t B, int64_t ldx, const float* Y, int64_t C, 
   BVLM_CUDA_TRY(cudaMemsetAsync(g.scalars, 0, 64 * sizeof(float), st));
   BVLM_CUDA_TRY(cudaMemsetAsync(g.Hinc, 0, static_cast<size_t>(D) * D * sizeof(float), st));
   float* w_sum = g.scalars;
-  float* wbar = g.scalars + 1;
 
   // ---- operand preparation
   if ((rc = launch_ggn_row_prep(X, B, D, ldx, GGN_OPSCALE, prec, 0, g.Xh16, g.Dp, g.inv_nx, g.w_raw, w_sum, st))) return rc;
   if ((rc = launch_ggn_row_prep(Y, C, D, ldy, GGN_OPSCALE, prec, 1, g.Yh16, g.Dp, g.inv_ny, nullptr, nullptr, st))) return rc;
   if ((rc = launch_normalize_weights(g.w_raw, w_sum, B, g.w, st))) return rc;
-  k_mean_weight<<<1, 32, 0, st>>>(w_sum, 1.0f / static_cast<float>(B), wbar);
-  count_launch();
   if ((rc = launch_transpose_to_16(Y, C, D, ldy, g.inv_ny, 0, nullptr, GGN_OPSCALE, 0, FMT_F16, g.YhT16, g.Cp, 0, g.Cp, st)))
     return rc;
 
@@ -163,6 +156,10 @@ int ggn_impl(const float* X, int64_t B, int64_t ldx, const float* Y, int64_t C, 
                                     static_cast<size_t>(B), st));
   }
 
+  // ---- gamma = max_c q_c and the derived scalars
+  if ((rc = launch_ggn_scalars(g.q, C, g.scalars, 1.0f / static_cast<float>(B), st))) return rc;
+  const float* inv_gamma = g.scalars + 4;
+
   // ---- pass 3: InfoNCE [n ; r] = [omega ; omega*d] Yh (M = Bs + B stacked rows) | SigLIP r = (omega*L) Yh ; K = C
   float* Nn = g.MR;
   float* Rr = siglip ? g.MR : g.MR + static_cast<size_t>(g.Bs) * D;
@@ -180,11 +177,12 @@ int ggn_impl(const float* X, int64_t B, int64_t ldx, const float* Y, int64_t C, 
 
   // ---- per-source finalisation and stacked operands of pass 4
   const float unscale_n = 1.0f / (GGN_WSCALE * GGN_OPSCALE);
-  const float unscale_r = siglip ? unscale_n : unscale_n / (s * kLog2e);  // InfoNCE: d is in log2-logit units
-  if ((rc = launch_ggn_row_finalize(X, B, D, ldx, g.inv_nx, g.w, Y, ldy, g.inv_ny, g.pivot, g.rest, Nn, Rr, g.RA, D, unscale_n,
-                                    unscale_r, siglip, g.mult_x, st)))
+  const float unscale_r =  // InfoNCE: d is in log2-logit units and stored with GGN_WDSCALE
+      siglip ? unscale_n : 1.0f / (GGN_WDSCALE * GGN_OPSCALE * s * kLog2e);
+  if ((rc = launch_ggn_row_finalize(X, B, D, ldx, g.inv_nx, g.w, Y, ldy, g.inv_ny, g.pivot, g.rest, inv_gamma, Nn, Rr, g.RA, D,
+                                    unscale_n, unscale_r, siglip, g.mult_x, st)))
     return rc;
-  if ((rc = launch_ggn_col_mult(g.q, g.inv_ny, C, GGN_G, g.mult_y, st))) return rc;
+  if ((rc = launch_ggn_col_mult(g.q, g.inv_ny, inv_gamma, C, GGN_G, g.mult_y, st))) return rc;
 
   const int64_t K = g.Ktot;
   int64_t off = 0;
@@ -217,8 +215,8 @@ int ggn_impl(const float* X, int64_t B, int64_t ldx, const float* Y, int64_t C, 
     EpiStoreF32<GGN_BN>::Params e4{g.Hinc, D, 1.0f, 1, 0, nullptr, nullptr};
     if ((rc = launch_gemm<GGN_BN, GGN_STAGES, EpiStoreF32<GGN_BN>>(tmL, tmR, p4, e4, st))) return rc;
   }
-  // ---- H (+)= s^2 wbar / g^2 * (Hinc + Hinc^T)/2
-  return launch_sym_add(g.Hinc, D, D, H, ldh, s * s / (GGN_G * GGN_G), wbar, accumulate, st);
+  // ---- H (+)= s^2 wbar gamma / g^2 * (Hinc + Hinc^T)/2
+  return launch_sym_add(g.Hinc, D, D, H, ldh, s * s / (GGN_G * GGN_G), g.scalars + 3, accumulate, st);
 }
 
 }  // namespace

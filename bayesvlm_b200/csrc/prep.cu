@@ -212,58 +212,83 @@ __global__ void __launch_bounds__(ROW_BLOCK)
 k_ggn_row_finalize(const float* __restrict__ x, int64_t B, int64_t D, int64_t ldx, const float* __restrict__ inv_norm,
                    const float* __restrict__ w, const float* __restrict__ y, int64_t ldy,
                    const float* __restrict__ inv_norm_y, const int* __restrict__ pivot, const float* __restrict__ rest,
-                   float* __restrict__ Nraw, float* __restrict__ Rraw, float* __restrict__ RA, int64_t ldm,
-                   float unscale_n, float unscale_r, int siglip, float* __restrict__ mult_x) {
+                   const float* __restrict__ inv_gamma, float* __restrict__ Nraw, float* __restrict__ Rraw,
+                   float* __restrict__ RA, int64_t ldm, float unscale_n, float unscale_r, int siglip,
+                   float* __restrict__ mult_x) {
   const int64_t row = static_cast<int64_t>(blockIdx.x) * WARPS_PER_BLOCK + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= B) return;
   const float inv = inv_norm[row];
-  const float sw = sqrtf(fmaxf(w[row], 0.f));
   const float* xr = x + row * ldx;
   float* rr = Rraw + row * ldm;
+  float kappa;
   if (siglip) {
-    // u = r (cosine-weighted), a = u.xh ;  R_B = sqrt(w) (u - a/2 xh)
+    // u = r (cosine-weighted), a = u.xh ;  R_B = kappa (u - a/2 xh),  kappa = sqrt(w / gamma)
+    kappa = sqrtf(fmaxf(w[row] * (*inv_gamma), 0.f));
     float a = 0.f;
     for (int64_t j = lane; j < D; j += 32) a = fmaf(rr[j] * unscale_r, xr[j] * inv, a);
     a = warp_sum(a);
-    for (int64_t j = lane; j < D; j += 32) rr[j] = sw * fmaf(-0.5f * a, xr[j] * inv, rr[j] * unscale_r);
+    for (int64_t j = lane; j < D; j += 32) rr[j] = kappa * fmaf(-0.5f * a, xr[j] * inv, rr[j] * unscale_r);
   } else {
+    // conditional (rho-free) quantities: nbar = E[yh | c != pivot], ebar = nbar - g, rbar = E[d yh | c != pivot] ...
     const int pv = pivot[row];
     const float* gr = y + static_cast<int64_t>(pv) * ldy;
     const float ginv = inv_norm_y[pv];
     const float rs = rest[row];
     const float rho = rs / (1.f + rs);         // 1 - softmax(pivot), no cancellation
     const float sq = sqrtf(1.f / (1.f + rs));  // sqrt(softmax(pivot))
-    const float c1 = rho / (1.f + sq);         // 1 - sqrt(p*)
+    const float c1 = 1.f / (1.f + sq);         // (1 - sqrt p*) / rho
     const float c2 = 1.f + sq;
+    kappa = sqrtf(fmaxf(w[row] * rho * (*inv_gamma), 0.f));
     float* nr = Nraw + row * ldm;
     float* ra = RA + row * ldm;
-    // e = n - rho g ; tau = e.xh
-    float tau = 0.f;
+    float tau = 0.f;  // ebar . xh
     for (int64_t j = lane; j < D; j += 32) {
-      const float e = fmaf(-rho, gr[j] * ginv, nr[j] * unscale_n);
+      const float e = fmaf(nr[j], unscale_n, -gr[j] * ginv);
       tau = fmaf(e, xr[j] * inv, tau);
     }
     tau = warp_sum(tau);
-    // u = r'' - tau (g + e) ; a = u.xh
-    float a = 0.f;
+    float a = 0.f;  // ubar . xh,  ubar = rbar - tau (g + rho ebar)
     for (int64_t j = lane; j < D; j += 32) {
       const float g = gr[j] * ginv;
-      const float e = fmaf(-rho, g, nr[j] * unscale_n);
-      const float u = fmaf(-tau, g + e, rr[j] * unscale_r);
+      const float e = fmaf(nr[j], unscale_n, -g);
+      const float u = fmaf(-tau, fmaf(rho, e, g), rr[j] * unscale_r);
       a = fmaf(u, xr[j] * inv, a);
     }
     a = warp_sum(a);
     for (int64_t j = lane; j < D; j += 32) {
       const float g = gr[j] * ginv;
-      const float e = fmaf(-rho, g, nr[j] * unscale_n);
-      const float u = fmaf(-tau, g + e, rr[j] * unscale_r);
-      nr[j] = -sw * fmaf(c1, g, e);                       // L_A
-      ra[j] = sw * fmaf(c2, g, e);                        // R_A
-      rr[j] = sw * fmaf(-0.5f * a, xr[j] * inv, u);       // R_B
+      const float e = fmaf(nr[j], unscale_n, -g);
+      const float u = fmaf(-tau, fmaf(rho, e, g), rr[j] * unscale_r);
+      nr[j] = -kappa * fmaf(c1, g, e);                        // L_A
+      ra[j] = kappa * fmaf(rho, e, c2 * g);                   // R_A
+      rr[j] = kappa * fmaf(-0.5f * a, xr[j] * inv, u);        // R_B
     }
   }
-  if (lane == 0) mult_x[row] = -2.f * sw * inv;           // L_B = -2 sqrt(w) xh, written by the transposing writer
+  if (lane == 0) mult_x[row] = -2.f * kappa * inv;            // L_B = -2 kappa xh, written by the transposing writer
+}
+
+// gamma = max_c q_c (q >= 0): atomicMax on the float bit pattern
+__global__ void k_max_nonneg(const float* __restrict__ q, int64_t n, unsigned int* __restrict__ out_bits) {
+  float m = 0.f;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float v = q[i];
+    if (v > m && isfinite(v)) m = v;
+  }
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out_bits, __float_as_uint(m));
+}
+
+// scalars: [0] sum_b 1/|x_b|^2, [1] wbar, [2] gamma, [3] wbar * gamma, [4] 1/gamma (0 if gamma == 0)
+__global__ void k_ggn_scalars(float* __restrict__ sc, float inv_count) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const float wbar = sc[0] * inv_count;
+    const float gamma = sc[2];
+    sc[1] = wbar;
+    sc[3] = wbar * gamma;
+    sc[4] = gamma > 0.f ? 1.0f / gamma : 0.f;
+  }
 }
 
 // out (+)= alpha * alpha_dev * (S + S^T) / 2
@@ -306,10 +331,10 @@ __global__ void k_col_pow2_scale(const unsigned int* __restrict__ amax_bits, int
   unscale[j] = ldexpf(1.f, -e);
 }
 
-__global__ void k_ggn_col_mult(const float* __restrict__ q, const float* __restrict__ inv_norm_y, int64_t C, float g,
-                               float* __restrict__ mult_y) {
+__global__ void k_ggn_col_mult(const float* __restrict__ q, const float* __restrict__ inv_norm_y,
+                               const float* __restrict__ inv_gamma, int64_t C, float g, float* __restrict__ mult_y) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < C) mult_y[i] = g * sqrtf(fmaxf(q[i], 0.f)) * inv_norm_y[i];
+  if (i < C) mult_y[i] = g * sqrtf(fmaxf(q[i] * (*inv_gamma), 0.f)) * inv_norm_y[i];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -430,11 +455,22 @@ int launch_transpose_to_16(const float* src, int64_t R, int64_t d, int64_t ld, c
 
 int launch_ggn_row_finalize(const float* x, int64_t B, int64_t D, int64_t ldx, const float* inv_norm, const float* w,
                             const float* y, int64_t ldy, const float* inv_norm_y, const int* pivot, const float* rest,
-                            float* Nraw, float* Rraw, float* RA, int64_t ldm, float unscale_n, float unscale_r, int siglip,
-                            float* mult_x, cudaStream_t st) {
+                            const float* inv_gamma, float* Nraw, float* Rraw, float* RA, int64_t ldm, float unscale_n,
+                            float unscale_r, int siglip, float* mult_x, cudaStream_t st) {
   if (B <= 0) return BVLM_OK;
-  k_ggn_row_finalize<<<row_grid(B), ROW_BLOCK, 0, st>>>(x, B, D, ldx, inv_norm, w, y, ldy, inv_norm_y, pivot, rest, Nraw,
-                                                        Rraw, RA, ldm, unscale_n, unscale_r, siglip, mult_x);
+  k_ggn_row_finalize<<<row_grid(B), ROW_BLOCK, 0, st>>>(x, B, D, ldx, inv_norm, w, y, ldy, inv_norm_y, pivot, rest,
+                                                        inv_gamma, Nraw, Rraw, RA, ldm, unscale_n, unscale_r, siglip, mult_x);
+  count_launch();
+  BVLM_CUDA_TRY(cudaGetLastError());
+  return BVLM_OK;
+}
+
+int launch_ggn_scalars(const float* q, int64_t C, float* scalars, float inv_count, cudaStream_t st) {
+  unsigned grid = static_cast<unsigned>((C + 255) / 256);
+  if (grid > 1024) grid = 1024;
+  k_max_nonneg<<<grid, 256, 0, st>>>(q, C, reinterpret_cast<unsigned int*>(scalars + 2));
+  count_launch();
+  k_ggn_scalars<<<1, 32, 0, st>>>(scalars, inv_count);
   count_launch();
   BVLM_CUDA_TRY(cudaGetLastError());
   return BVLM_OK;
@@ -465,9 +501,10 @@ int launch_col_pow2_scale(const float* x, int64_t n, int64_t d, int64_t ld, int 
   return BVLM_OK;
 }
 
-int launch_ggn_col_mult(const float* q, const float* inv_norm_y, int64_t C, float g, float* mult_y, cudaStream_t st) {
+int launch_ggn_col_mult(const float* q, const float* inv_norm_y, const float* inv_gamma, int64_t C, float g, float* mult_y,
+                        cudaStream_t st) {
   if (C <= 0) return BVLM_OK;
-  k_ggn_col_mult<<<static_cast<unsigned>((C + 255) / 256), 256, 0, st>>>(q, inv_norm_y, C, g, mult_y);
+  k_ggn_col_mult<<<static_cast<unsigned>((C + 255) / 256), 256, 0, st>>>(q, inv_norm_y, inv_gamma, C, g, mult_y);
   count_launch();
   BVLM_CUDA_TRY(cudaGetLastError());
   return BVLM_OK;

@@ -38,15 +38,22 @@ int launch_transpose_to_16(const float* src, int64_t R, int64_t d, int64_t ld, c
                            int64_t col_off, int64_t R_pad, cudaStream_t st);
 
 // Per-source finalisation of the pivot-centred GGN (collapsed form of hessians.py:30-46 / 103-113; see kfac.cu).
-//   InfoNCE: n = Nraw*unscale_n, r'' = Rraw*unscale_r, g = yh[pivot], rho = rest/(1+rest), p* = 1/(1+rest)
-//            e = n - rho g, tau = e.xh, u = r'' - tau (g + e), a = u.xh
-//            Nraw <- L_A = -sqrt(w)(e + (1-sqrt p*) g),  RA <- R_A = sqrt(w)(e + (1+sqrt p*) g),  Rraw <- R_B = sqrt(w)(u - a/2 xh)
-//   SigLIP : u = Rraw*unscale_r, a = u.xh, Rraw <- R_B
-//   mult_x[b] = -2 sqrt(w_b)/|x_b|   (row multiplier that turns X into L_B)
+// gamma = max_c q_c normalises the stacked operands of pass 4 into fp16's range whatever the curvature scale is.
+//   InfoNCE (conditional, rho-free inputs from pass 3): nbar = Nraw*unscale_n, rbar = Rraw*unscale_r, g = yh[pivot],
+//            rho = rest/(1+rest), p* = 1/(1+rest), ebar = nbar - g, tau = ebar.xh, ubar = rbar - tau (g + rho ebar),
+//            abar = ubar.xh, kappa = sqrt(w rho / gamma)
+//            Nraw <- L_A = -kappa (ebar + g/(1+sqrt p*)),  RA <- R_A = kappa (rho ebar + (1+sqrt p*) g),
+//            Rraw <- R_B = kappa (ubar - abar/2 xh)
+//   SigLIP : u = Rraw*unscale_r, a = u.xh, kappa = sqrt(w / gamma), Rraw <- R_B = kappa (u - a/2 xh)
+//   mult_x[b] = -2 kappa_b/|x_b|   (row multiplier that turns X into L_B)
 int launch_ggn_row_finalize(const float* x, int64_t B, int64_t D, int64_t ldx, const float* inv_norm, const float* w,
                             const float* y, int64_t ldy, const float* inv_norm_y, const int* pivot, const float* rest,
-                            float* Nraw, float* Rraw, float* RA, int64_t ldm, float unscale_n, float unscale_r, int siglip,
-                            float* mult_x, cudaStream_t st);
+                            const float* inv_gamma, float* Nraw, float* Rraw, float* RA, int64_t ldm, float unscale_n,
+                            float unscale_r, int siglip, float* mult_x, cudaStream_t st);
+
+// scalars[2] = gamma = max_c q_c (scalars[2] must be zero on entry), then
+// scalars[1] = wbar = scalars[0] * inv_count, scalars[3] = wbar * gamma, scalars[4] = 1/gamma (0 when gamma == 0)
+int launch_ggn_scalars(const float* q, int64_t C, float* scalars, float inv_count, cudaStream_t st);
 
 // out (+)= alpha * (*alpha_dev) * (S + S^T) / 2
 int launch_sym_add(const float* S, int64_t d, int64_t lds, float* out, int64_t ldo, float alpha, const float* alpha_dev,
@@ -56,8 +63,9 @@ int launch_sym_add(const float* S, int64_t d, int64_t lds, float* out, int64_t l
 int launch_col_pow2_scale(const float* x, int64_t n, int64_t d, int64_t ld, int append_one, unsigned int* amax_bits,
                           float* scale, float* unscale, cudaStream_t st);
 
-// mult_y[c] = g * sqrt(max(q_c,0)) / |y_c|
-int launch_ggn_col_mult(const float* q, const float* inv_norm_y, int64_t C, float g, float* mult_y, cudaStream_t st);
+// mult_y[c] = g * sqrt(max(q_c / gamma, 0)) / |y_c|
+int launch_ggn_col_mult(const float* q, const float* inv_norm_y, const float* inv_gamma, int64_t C, float g, float* mult_y,
+                        cudaStream_t st);
 
 // Canonical probit softmax (scripts/zeroshot.py:119-120): probs = softmax_j(mean / sqrt(1 + pi/8 var)).
 int launch_probit_softmax(const float* mean, const float* var, int64_t N, int64_t C, int64_t ld, float* probs,
