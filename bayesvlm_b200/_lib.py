@@ -71,6 +71,10 @@ SIGNATURES = {
     "bvlm_gemm_tn_f32": (c_int, [_P, _I, _P, _I, _I, c_int, c_float, _P, _I, c_int, _P]),
     "bvlm_convert_rows_16": (c_int, [_P, _I, _I, _I, c_int, _P, _I, _P]),
     "bvlm_launch_count": (c_int64, []),
+    "bvlm_timing_enable": (c_int, [c_int]),
+    "bvlm_timing_tag_count": (c_int, []),
+    "bvlm_timing_tag_name": (c_char_p, [c_int]),
+    "bvlm_timing_collect": (c_int, [_P, _P, c_int]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():
@@ -94,6 +98,19 @@ def version() -> str:
 
 def launch_count() -> int:
     return int(lib.bvlm_launch_count())
+
+
+def timing_enable(on: bool) -> None:
+    check(lib.bvlm_timing_enable(int(on)), "bvlm_timing_enable")
+
+
+def timing_collect() -> dict:
+    """{kernel tag: (launches, total milliseconds)} of the tensor-core launches recorded since the last collect."""
+    n = int(lib.bvlm_timing_tag_count())
+    launches = (c_int64 * n)()
+    total = (ctypes.c_double * n)()
+    check(lib.bvlm_timing_collect(ctypes.cast(launches, c_void_p), ctypes.cast(total, c_void_p), n), "bvlm_timing_collect")
+    return {lib.bvlm_timing_tag_name(i).decode(): (int(launches[i]), float(total[i])) for i in range(n) if launches[i]}
 
 
 # ------------------------------------------------------------------------------------------------------------------

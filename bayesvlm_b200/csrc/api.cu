@@ -1,6 +1,8 @@
 // Library-level entry points: version / status strings, device check, launch counter and the diagnostic
 // plain-GEMM path the tests use to validate the tcgen05 engine in isolation.
 #include <atomic>
+#include <mutex>
+#include <vector>
 
 #include "epilogues.cuh"
 #include "prep.cuh"
@@ -10,6 +12,41 @@ namespace {
 std::atomic<int64_t> g_launches{0};
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+namespace {
+struct TimedLaunch {
+  int tag;
+  cudaEvent_t beg, end;
+};
+std::atomic<int> g_timing_on{0};
+std::mutex g_timing_mu;
+std::vector<TimedLaunch> g_timed;
+cudaEvent_t g_pending_beg = nullptr;
+}  // namespace
+
+void timing_begin(int tag, cudaStream_t st) {
+  (void)tag;
+  if (!g_timing_on.load(std::memory_order_relaxed)) return;
+  std::lock_guard<std::mutex> lk(g_timing_mu);
+  if (cudaEventCreate(&g_pending_beg) != cudaSuccess) {
+    g_pending_beg = nullptr;
+    return;
+  }
+  cudaEventRecord(g_pending_beg, st);
+}
+void timing_end(int tag, cudaStream_t st) {
+  if (!g_timing_on.load(std::memory_order_relaxed)) return;
+  std::lock_guard<std::mutex> lk(g_timing_mu);
+  if (g_pending_beg == nullptr) return;
+  TimedLaunch t{tag, g_pending_beg, nullptr};
+  g_pending_beg = nullptr;
+  if (cudaEventCreate(&t.end) != cudaSuccess) {
+    cudaEventDestroy(t.beg);
+    return;
+  }
+  cudaEventRecord(t.end, st);
+  g_timed.push_back(t);
+}
 }  // namespace bvlm
 
 using namespace bvlm;
@@ -50,6 +87,44 @@ int bvlm_device_check(void) {
 
 int64_t bvlm_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
+int bvlm_timing_enable(int on) {
+  g_timing_on.store(on ? 1 : 0, std::memory_order_relaxed);
+  return BVLM_OK;
+}
+
+int bvlm_timing_tag_count(void) { return TAG_COUNT; }
+
+const char* bvlm_timing_tag_name(int tag) {
+  static const char* names[TAG_COUNT] = {"gemm_diag",    "syrk",     "ggn_rowstats", "ggn_weights", "ggn_moments",
+                                         "ggn_stacked",  "quadform", "predictive",   "epig_joint"};
+  return (tag >= 0 && tag < TAG_COUNT) ? names[tag] : "?";
+}
+
+int bvlm_timing_collect(int64_t* launches, double* total_ms, int n_tags) {
+  if (launches == nullptr || total_ms == nullptr || n_tags < TAG_COUNT) return BVLM_EINVAL;
+  std::lock_guard<std::mutex> lk(g_timing_mu);
+  for (int i = 0; i < n_tags; ++i) {
+    launches[i] = 0;
+    total_ms[i] = 0.0;
+  }
+  int rc = BVLM_OK;
+  for (auto& t : g_timed) {
+    cudaError_t e = cudaEventSynchronize(t.end);
+    float ms = 0.f;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, t.beg, t.end);
+    if (e == cudaSuccess) {
+      launches[t.tag] += 1;
+      total_ms[t.tag] += ms;
+    } else {
+      rc = static_cast<int>(e);
+    }
+    cudaEventDestroy(t.beg);
+    cudaEventDestroy(t.end);
+  }
+  g_timed.clear();
+  return rc;
+}
+
 int bvlm_convert_rows_16(const float* in, int64_t R, int64_t d, int64_t ld, int fmt, void* out, int64_t k_pad,
                          void* stream) {
   if (in == nullptr || out == nullptr || (fmt != FMT_F16 && fmt != FMT_BF16)) return BVLM_EINVAL;
@@ -75,7 +150,7 @@ int bvlm_gemm_tn_f32(const void* A16, int64_t M, const void* B16, int64_t N, int
   if (plan.splits > 1) {
     BVLM_CUDA_TRY(cudaMemset2DAsync(D, static_cast<size_t>(ldd) * 4, 0, static_cast<size_t>(N) * 4, static_cast<size_t>(M), st));
   }
-  return launch_gemm<BN, 4, EpiStoreF32<BN>>(tmA, tmB, plan, ep, st);
+  return launch_gemm<BN, 4, EpiStoreF32<BN>>(tmA, tmB, plan, ep, st, TAG_GEMM_DIAG);
 }
 
 }  // extern "C"

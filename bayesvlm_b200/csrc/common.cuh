@@ -27,6 +27,23 @@ namespace bvlm {
 // kernel-launch counter (bench.py reports it as gpu_launches); defined in api.cu
 void count_launch(int n = 1);
 
+// Optional per-kernel CUDA-event timing of the tensor-core launches (bench.py's live roofline numerator).
+// Disabled by default: timing_begin/timing_end are no-ops unless bvlm_timing_enable(1) was called.
+enum KernelTag : int {
+  TAG_GEMM_DIAG = 0,
+  TAG_SYRK = 1,
+  TAG_GGN_ROWSTATS = 2,
+  TAG_GGN_WEIGHTS = 3,
+  TAG_GGN_MOMENTS = 4,
+  TAG_GGN_STACKED = 5,
+  TAG_QUADFORM = 6,
+  TAG_PREDICTIVE = 7,
+  TAG_EPIG_JOINT = 8,
+  TAG_COUNT = 9
+};
+void timing_begin(int tag, cudaStream_t st);
+void timing_end(int tag, cudaStream_t st);
+
 __host__ __device__ constexpr inline int64_t ceil_div_i64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 __host__ __device__ constexpr inline int64_t round_up_i64(int64_t a, int64_t b) { return ceil_div_i64(a, b) * b; }
 

@@ -243,7 +243,7 @@ int bvlm_epig_joint_entropy_f16(const void* pool16, int64_t Np, const void* targ
   plan.a_tx_bytes = static_cast<uint32_t>(ppt * Cl * GEMM_BK * 2);
   EpiEpigJoint<EPIG_BN>::Params ep{Hjoint, Np, static_cast<int>(Cl), ppt, static_cast<int>(col_chunk / EPIG_BN),
                                    static_cast<float>(K), static_cast<float>(Nt)};
-  return launch_gemm<EPIG_BN, EPIG_STAGES, EpiEpigJoint<EPIG_BN>>(tmA, tmB, plan, ep, st);
+  return launch_gemm<EPIG_BN, EPIG_STAGES, EpiEpigJoint<EPIG_BN>>(tmA, tmB, plan, ep, st, TAG_EPIG_JOINT);
 }
 
 }  // extern "C"

@@ -298,7 +298,7 @@ inline GemmPlan make_plan(int M, int N, int K_padded, int mode, int splits, int 
 
 template <int BN, int STAGES, class Epi>
 inline int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmPlan& plan,
-                       const typename Epi::Params& ep, cudaStream_t stream) {
+                       const typename Epi::Params& ep, cudaStream_t stream, int tag) {
   if (plan.kb_total <= 0 || plan.M <= 0 || plan.N <= 0) return BVLM_EINVAL;
   constexpr size_t smem = gemm_smem_bytes<BN, STAGES, Epi>();
   static_assert(smem <= 232448, "shared memory budget exceeded");
@@ -311,7 +311,9 @@ inline int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   const int items = plan_num_items<BN>(plan);
   int grid = device_sm_count();
   if (items < grid) grid = items;
+  timing_begin(tag, stream);
   kfn<<<grid, GEMM_THREADS, smem, stream>>>(tmA, tmB, plan, ep);
+  timing_end(tag, stream);
   count_launch();
   BVLM_CUDA_TRY(cudaGetLastError());
   return BVLM_OK;

@@ -129,7 +129,7 @@ int ggn_impl(const float* X, int64_t B, int64_t ldx, const float* Y, int64_t C, 
     GemmPlan p1 = make_plan<GGN_BN>(static_cast<int>(B), static_cast<int>(C), static_cast<int>(Kl), SCHED_ROW_PANEL, 1,
                                     FMT_F16, FMT_F16);
     EpiRowLse<GGN_BN>::Params e1{g.rowmax2, g.rest, g.pivot, s * kLog2e / op2};
-    if ((rc = launch_gemm<GGN_BN, GGN_STAGES, EpiRowLse<GGN_BN>>(tmX, tmY, p1, e1, st))) return rc;
+    if ((rc = launch_gemm<GGN_BN, GGN_STAGES, EpiRowLse<GGN_BN>>(tmX, tmY, p1, e1, st, TAG_GGN_ROWSTATS))) return rc;
   }
 
   // ---- pass 2: curvature weights omega (fp16), omega*(d|L) (fp16), q
@@ -141,11 +141,11 @@ int ggn_impl(const float* X, int64_t B, int64_t ldx, const float* Y, int64_t C, 
     if (siglip) {
       EpiGgnWeights<GGN_BN, true>::Params e2{nullptr, nullptr, nullptr, g.w, nullptr, WL16, g.Cp, g.q, s / op2, 1.0f / op2,
                                              logit_bias};
-      if ((rc = launch_gemm<GGN_BN, GGN_STAGES, EpiGgnWeights<GGN_BN, true>>(tmX, tmY, p2, e2, st))) return rc;
+      if ((rc = launch_gemm<GGN_BN, GGN_STAGES, EpiGgnWeights<GGN_BN, true>>(tmX, tmY, p2, e2, st, TAG_GGN_WEIGHTS))) return rc;
     } else {
       EpiGgnWeights<GGN_BN, false>::Params e2{g.rowmax2, g.rest, g.pivot, g.w, W16, WL16, g.Cp, g.q, s * kLog2e / op2,
                                               1.0f / op2, 0.f};
-      if ((rc = launch_gemm<GGN_BN, GGN_STAGES, EpiGgnWeights<GGN_BN, false>>(tmX, tmY, p2, e2, st))) return rc;
+      if ((rc = launch_gemm<GGN_BN, GGN_STAGES, EpiGgnWeights<GGN_BN, false>>(tmX, tmY, p2, e2, st, TAG_GGN_WEIGHTS))) return rc;
     }
   }
   if (g.Cp != C) {  // K padding of pass 3 must be exact zeros
@@ -172,7 +172,7 @@ int ggn_impl(const float* X, int64_t B, int64_t ldx, const float* Y, int64_t C, 
     GemmPlan p3 = make_plan<GGN_BN>(static_cast<int>(opW.rows), static_cast<int>(D), static_cast<int>(g.Cp), SCHED_TILES, 1,
                                     FMT_F16, FMT_F16);
     EpiStoreF32<GGN_BN>::Params e3{g.MR, D, 1.0f, 0, 0, nullptr, nullptr};
-    if ((rc = launch_gemm<GGN_BN, GGN_STAGES, EpiStoreF32<GGN_BN>>(tmW, tmYT, p3, e3, st))) return rc;
+    if ((rc = launch_gemm<GGN_BN, GGN_STAGES, EpiStoreF32<GGN_BN>>(tmW, tmYT, p3, e3, st, TAG_GGN_MOMENTS))) return rc;
   }
 
   // ---- per-source finalisation and stacked operands of pass 4
@@ -213,7 +213,7 @@ int ggn_impl(const float* X, int64_t B, int64_t ldx, const float* Y, int64_t C, 
     GemmPlan p4 = make_plan<GGN_BN>(static_cast<int>(D), static_cast<int>(D), static_cast<int>(K), SCHED_TILES, splits,
                                     FMT_F16, FMT_F16);
     EpiStoreF32<GGN_BN>::Params e4{g.Hinc, D, 1.0f, 1, 0, nullptr, nullptr};
-    if ((rc = launch_gemm<GGN_BN, GGN_STAGES, EpiStoreF32<GGN_BN>>(tmL, tmR, p4, e4, st))) return rc;
+    if ((rc = launch_gemm<GGN_BN, GGN_STAGES, EpiStoreF32<GGN_BN>>(tmL, tmR, p4, e4, st, TAG_GGN_STACKED))) return rc;
   }
   // ---- H (+)= s^2 wbar gamma / g^2 * (Hinc + Hinc^T)/2
   return launch_sym_add(g.Hinc, D, D, H, ldh, s * s / (GGN_G * GGN_G), g.scalars + 3, accumulate, st);
@@ -265,7 +265,7 @@ int bvlm_syrk_f32acc(const float* X, int64_t n, int64_t d, int64_t ldx, int appe
                                      splits, FMT_F16, FMT_F16);
   // lower triangle accumulated with red.global.add, then mirrored: C stays exactly symmetric
   EpiStoreF32<SYRK_BN>::Params ep{C, ldc, alpha, 1, 1, nullptr, unscale};
-  if ((rc = launch_gemm<SYRK_BN, SYRK_STAGES, EpiStoreF32<SYRK_BN>>(tmA, tmB, plan, ep, st))) return rc;
+  if ((rc = launch_gemm<SYRK_BN, SYRK_STAGES, EpiStoreF32<SYRK_BN>>(tmA, tmB, plan, ep, st, TAG_SYRK))) return rc;
   return launch_symmetrize_scale(C, dA, ldc, 1.0f, st);
 }
 

@@ -48,7 +48,7 @@ int quadform_impl(const float* act, int64_t n, int64_t d, int64_t ld, int append
                                      1, FMT_F16, FMT_F16);
   plan.tri_k = 1;
   EpiRowSumSq<PRED_BN>::Params ep{out, row_unscale, 1.0f / (w_scale * w_scale)};
-  return launch_gemm<PRED_BN, PRED_STAGES, EpiRowSumSq<PRED_BN>>(tmA, tmB, plan, ep, st);
+  return launch_gemm<PRED_BN, PRED_STAGES, EpiRowSumSq<PRED_BN>>(tmA, tmB, plan, ep, st, TAG_QUADFORM);
 }
 
 }  // namespace
@@ -147,7 +147,7 @@ int bvlm_predictive(const float* E, int64_t N, int64_t D, int64_t lde, const flo
   GemmPlan plan = make_plan<PRED_BN>(static_cast<int>(N), static_cast<int>(C), static_cast<int>(kp), SCHED_TILES, 1,
                                      FMT_F16, FMT_F16);
   EpiPredictive<PRED_BN>::Params ep{mean, var, ldo, rowU, rowV, colA, colB, s / (PRED_OPSCALE * PRED_OPSCALE)};
-  rc = launch_gemm<PRED_BN, PRED_STAGES, EpiPredictive<PRED_BN>>(tmA, tmB, plan, ep, st);
+  rc = launch_gemm<PRED_BN, PRED_STAGES, EpiPredictive<PRED_BN>>(tmA, tmB, plan, ep, st, TAG_PREDICTIVE);
   if (rc) return rc;
   if (probs != nullptr) rc = launch_probit_softmax(mean, var, N, C, ldo, probs, st);
   return rc;

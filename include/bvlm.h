@@ -136,6 +136,13 @@ int bvlm_convert_rows_16(const float* in, int64_t R, int64_t d, int64_t ld, int 
                          void* stream);
 /* number of kernel launches issued through this library since load (for bench.py's gpu_launches claim). */
 int64_t bvlm_launch_count(void);
+/* Optional CUDA-event timing of every tensor-core (tcgen05) kernel launch, on the stream it is launched on.
+ * bvlm_timing_enable(1) starts recording; bvlm_timing_collect synchronises the recorded events, sums launches and
+ * milliseconds per kernel tag (arrays of at least bvlm_timing_tag_count() entries) and clears the record. */
+int bvlm_timing_enable(int on);
+int bvlm_timing_tag_count(void);
+const char* bvlm_timing_tag_name(int tag);
+int bvlm_timing_collect(int64_t* launches, double* total_ms, int n_tags);
 
 #ifdef __cplusplus
 }

@@ -137,3 +137,37 @@ def test_log_marglik_objective_is_maximised_by_reference_lambda(golden):
     W = golden["prior_W"]
     f = lambda l: O.log_marglik(golden["prior_A"], golden["prior_B"], n, l, float((W ** 2).sum()), W.size)
     assert f(lam) > f(lam0)  # 60 Adam ascent steps improved the objective the oracle restates
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# oracle/torch_port.py: the torch-CPU restatement bench.py times as the reference arm, against the same goldens
+# ----------------------------------------------------------------------------------------------------------------------
+def test_torch_port_matches_reference_outputs(golden):
+    import torch
+
+    from oracle import torch_port as T
+
+    t = lambda k: torch.from_numpy(golden[k])
+    X, Y = t("ggn_X"), t("ggn_Y")
+    np.testing.assert_allclose(T.infonce_ggn(X, Y, LS).numpy(), golden["ggn_infonce_H"], rtol=2e-4, atol=2e-4)
+    s, b = golden["ggn_siglip_params"]
+    np.testing.assert_allclose(T.siglip_ggn(X, torch.arange(7), Y, s, b, chunk_size_j=16).numpy(), golden["ggn_siglip_H"],
+                               rtol=2e-4, atol=1e-5)
+    ncls, bs = (int(v) for v in golden["kfac_cfg"])
+    A, B = T.kfac_ggn(t("kfac_emb_s"), t("kfac_act_s"), t("kfac_emb_t"), ncls, bs, LS)
+    assert relerr(A.numpy(), golden["kfac_infonce_A"]) < 1e-6 and relerr(B.numpy(), golden["kfac_infonce_B"]) < 1e-4
+    A, B = T.kfac_ggn(t("kfac_emb_s"), t("kfac_act_s"), t("kfac_emb_t"), ncls, bs, s, b, "siglip", siglip_chunk_size_j=20)
+    assert relerr(A.numpy(), golden["kfac_siglip_A"]) < 1e-6 and relerr(B.numpy(), golden["kfac_siglip_B"]) < 1e-4
+    for tag, bias, ls in (("clip", False, LS), ("siglip", True, s)):
+        g = {k[len(f"pred_{tag}_"):]: torch.from_numpy(v) for k, v in golden.items() if k.startswith(f"pred_{tag}_")}
+        mean, var = T.predictive(g["img_emb"], g["img_act"], g["txt_emb"], g["txt_act"], g["A_img_inv"], g["B_img_inv"],
+                                 g["A_txt_inv"], g["B_txt_inv"], ls, bias, bias)
+        np.testing.assert_allclose(mean.numpy(), g["mean"].numpy(), rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(var.numpy(), g["var"].numpy(), rtol=1e-5)
+        np.testing.assert_allclose(T.probit_softmax(mean, var).numpy(), g["probit"].numpy(), rtol=1e-5, atol=1e-7)
+    p16, t16 = t("epig_probs_p").half(), t("epig_probs_t").half()
+    chunk = int(golden["epig_cfg"][0])
+    sc = T.epig_from_probs(p16, t16, chunk_size=chunk)
+    assert np.abs(sc.float().numpy() - golden["epig_scores_f16"]).max() <= 2.0 ** -9
+    np.testing.assert_allclose(T.epig_from_probs(t("epig_probs_p"), t("epig_probs_t"), chunk).numpy(),
+                               golden["epig_scores_f32"], atol=5e-6)
