@@ -226,12 +226,13 @@ def run_b200(args, rank, world, local_rank):
         _lib.timing_enable(True)
         l0 = _lib.launch_count()
         beg, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with ClockSampler(local_rank) as clocks:
-            beg.record()
-            for _ in range(K):
-                out = model(img, txt)
-            end.record()
-            barrier_sync()
+        clocks = ClockSampler(local_rank)  # samples nvidia-smi every ~100 ms from here to the end of the KFAC loop
+        clocks.__enter__()
+        beg.record()
+        for _ in range(K):
+            out = model(img, txt)
+        end.record()
+        barrier_sync()
         _lib.timing_enable(False)
         launches = _lib.launch_count() - l0
         kern = _lib.timing_collect()
@@ -310,6 +311,7 @@ def run_b200(args, rank, world, local_rank):
             "kernels": {k: {"launches": v[0], "avg_ms": v[1] / v[0]} for k, v in kk.items()},
             "gpu_launches": kfac_launches}
     assert torch.isfinite(A).all() and torch.isfinite(B).all()
+    clocks.__exit__()
 
     # ------------------------------------------------------------------ reference algorithm on the host cores (rank 0, N=1)
     cpu_baseline = None
@@ -343,7 +345,7 @@ def run_b200(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--e2e-batch", type=int, default=12500)
