@@ -49,6 +49,7 @@ SIGNATURES = {
     "bvlm_ggn_infonce": (c_int, [_P, _I, _I, _P, _I, _I, _I, c_float, c_int, _P, _I, c_int, _P, c_size_t, _P]),
     "bvlm_ggn_siglip": (c_int, [_P, _I, _I, _P, _I, _I, _I, c_float, c_float, c_int, _P, _I, c_int, _P, c_size_t, _P]),
     "bvlm_padded_k": (c_int64, [_I]),
+    "bvlm_padded_cols": (c_int64, [_I]),
     "bvlm_factor_prepare": (c_int, [_P, _I, _I, c_float, _P, _I, _P]),
     "bvlm_quadform_workspace_bytes": (c_size_t, [_I, _I, c_int]),
     "bvlm_quadform": (c_int, [_P, _I, _I, _I, c_int, _P, _I, _I, c_float, _P, _P, c_size_t, _P]),

@@ -136,6 +136,9 @@ struct EpiEpigJoint {
     st.chunk_acc = 0.f;
   }
 
+  static constexpr bool ALL_CHUNKS = false;
+  __device__ static void kernel_begin(State&, const Params&, const EpiCtx&) {}
+  __device__ static void kernel_end(State&, const Params&, const EpiCtx&) {}
   __device__ static void item_begin(State& st, const Params& p, const EpiCtx& ctx, const TileCoord& tc) {
     const int r = ctx.ew * 32 + ctx.lane;
     const int pl = r / p.Cl;

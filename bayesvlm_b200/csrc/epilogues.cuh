@@ -78,6 +78,9 @@ struct EpiStoreF32 {
   struct State {
     float alpha;
   };
+  static constexpr bool ALL_CHUNKS = false;
+  __device__ static void kernel_begin(State&, const Params&, const EpiCtx&) {}
+  __device__ static void kernel_end(State&, const Params&, const EpiCtx&) {}
   __device__ static void item_begin(State& st, const Params& p, const EpiCtx&, const TileCoord&) {
     st.alpha = p.alpha_dev != nullptr ? p.alpha * (*p.alpha_dev) : p.alpha;
   }
@@ -129,6 +132,9 @@ struct EpiRowSumSq {
   struct State {
     float acc;
   };
+  static constexpr bool ALL_CHUNKS = false;
+  __device__ static void kernel_begin(State&, const Params&, const EpiCtx&) {}
+  __device__ static void kernel_end(State&, const Params&, const EpiCtx&) {}
   __device__ static void item_begin(State& st, const Params&, const EpiCtx&, const TileCoord&) { st.acc = 0.f; }
   __device__ static void tile_begin(State&, const Params&, const EpiCtx&, const TileCoord&) {}
   __device__ static void chunk(State& st, const Params&, const EpiCtx&, const TileCoord&, float (&v)[32], int) {
@@ -159,54 +165,67 @@ struct EpiRowSumSq {
 // ---------------------------------------------------------------------------------------------
 template <int BN>
 struct EpiPredictive {
-  static constexpr size_t SCRATCH_BYTES = 4 * 2 * BN * sizeof(float);  // per-warp copy of a_j / b_j of the tile
+  static constexpr size_t SCRATCH_BYTES = 4 * 2 * SLAB_BYTES;  // per epilogue warp: one mean slab + one var slab
   struct Params {
+    CUtensorMap tm_mean, tm_var;  // [N, C] fp32, box {32 cols, 32 rows}, SWIZZLE_128B (used when use_tma)
     float* mean;
     float* var;
     int64_t ld;
     const float* u;
     const float* v;
-    const float* a;
+    const float* a;  // padded to a multiple of BN entries (zeros beyond C)
     const float* b;
     float mean_scale;
+    int use_tma;     // 0: row pitch not a multiple of 16 bytes -> direct stores
   };
   struct State {
     float u, v;
   };
+  static constexpr bool ALL_CHUNKS = false;
+  __device__ static void kernel_begin(State&, const Params&, const EpiCtx&) {}
+  __device__ static void kernel_end(State&, const Params& p, const EpiCtx& ctx) {
+    if (p.use_tma && ctx.lane == 0) tma_store_wait_all<0>();
+  }
   __device__ static void item_begin(State&, const Params&, const EpiCtx&, const TileCoord&) {}
   __device__ static void tile_begin(State& st, const Params& p, const EpiCtx& ctx, const TileCoord& tc) {
     const int row = epi_row(ctx, tc);
     st.u = row < ctx.M ? p.u[row] : 0.f;
     st.v = row < ctx.M ? p.v[row] : 0.f;
-    float* sa = ctx.scratch + ctx.ew * 2 * BN;
-    float* sb = sa + BN;
-    __syncwarp();
-    for (int i = ctx.lane; i < BN; i += 32) {
-      const int col = tc.n * BN + i;
-      sa[i] = col < ctx.N ? p.a[col] : 0.f;
-      sb[i] = col < ctx.N ? p.b[col] : 0.f;
-    }
-    __syncwarp();
   }
   __device__ static void chunk(State& st, const Params& p, const EpiCtx& ctx, const TileCoord& tc, float (&v)[32], int c) {
     const int row = epi_row(ctx, tc);
     const int col0 = tc.n * BN + c * 32;
-    const int n_valid = ctx.N - col0;
-    const float* sa = ctx.scratch + ctx.ew * 2 * BN + c * 32;
-    const float* sb = sa + BN;
+    const float4* a4p = reinterpret_cast<const float4*>(p.a + col0);  // same address in every lane: broadcast loads
+    const float4* b4p = reinterpret_cast<const float4*>(p.b + col0);
     float var[32];
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      const float4 a4 = *reinterpret_cast<const float4*>(sa + j);
-      const float4 b4 = *reinterpret_cast<const float4*>(sb + j);
-      var[j + 0] = fmaf(st.u, a4.x, st.v * b4.x);
-      var[j + 1] = fmaf(st.u, a4.y, st.v * b4.y);
-      var[j + 2] = fmaf(st.u, a4.z, st.v * b4.z);
-      var[j + 3] = fmaf(st.u, a4.w, st.v * b4.w);
+    for (int j = 0; j < 8; ++j) {
+      const float4 a4 = __ldg(a4p + j);
+      const float4 b4 = __ldg(b4p + j);
+      var[4 * j + 0] = fmaf(st.u, a4.x, st.v * b4.x);
+      var[4 * j + 1] = fmaf(st.u, a4.y, st.v * b4.y);
+      var[4 * j + 2] = fmaf(st.u, a4.z, st.v * b4.z);
+      var[4 * j + 3] = fmaf(st.u, a4.w, st.v * b4.w);
     }
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] *= p.mean_scale;
+    if (p.use_tma) {
+      // rows beyond N and columns beyond C are clipped by the tensor map
+      const uint32_t slab_m = ctx.scratch_u32 + static_cast<uint32_t>(ctx.ew) * (2 * SLAB_BYTES);
+      const uint32_t slab_v = slab_m + SLAB_BYTES;
+      const int row0 = tc.m * GEMM_BM + ctx.ew * 32;
+      slab_wait_free<1>(ctx.lane);  // pending: previous mean, previous var -> the mean slab is free again
+      slab_write_f32(slab_m, ctx.lane, v);
+      slab_issue(&p.tm_mean, slab_m, ctx.lane, col0, row0);
+      slab_commit(ctx.lane);
+      slab_wait_free<1>(ctx.lane);  // pending: previous var, this mean -> the var slab is free again
+      slab_write_f32(slab_v, ctx.lane, var);
+      slab_issue(&p.tm_var, slab_v, ctx.lane, col0, row0);
+      slab_commit(ctx.lane);
+      return;
+    }
     if (row >= ctx.M) return;
+    const int n_valid = ctx.N - col0;
     const bool al = (p.ld & 3) == 0 && (reinterpret_cast<uintptr_t>(p.mean) & 15) == 0 &&
                     (reinterpret_cast<uintptr_t>(p.var) & 15) == 0;
     const int64_t off = static_cast<int64_t>(row) * p.ld + col0;
@@ -237,6 +256,9 @@ struct EpiRowLse {
     float m, rest;
     int piv;
   };
+  static constexpr bool ALL_CHUNKS = false;
+  __device__ static void kernel_begin(State&, const Params&, const EpiCtx&) {}
+  __device__ static void kernel_end(State&, const Params&, const EpiCtx&) {}
   __device__ static void item_begin(State& st, const Params&, const EpiCtx&, const TileCoord&) {
     st.m = -INFINITY;
     st.rest = 0.f;
@@ -301,25 +323,32 @@ constexpr float GGN_WDSCALE = 64.f;
 
 template <int BN, bool SIGLIP>
 struct EpiGgnWeights {
-  static constexpr size_t SCRATCH_BYTES = 4 * BN * sizeof(float);
+  // per epilogue warp: double-buffered slabs for omega and omega*(d|L); the column-sum exchange reuses the block
+  static constexpr size_t SCRATCH_BYTES = 4 * 4 * SLAB_BYTES;
+  static_assert(SCRATCH_BYTES >= 4 * BN * sizeof(float), "column-sum exchange needs 4*BN floats");
   struct Params {
+    CUtensorMap tm_w, tm_wl;  // [B, Cp] fp16, box {64 cols, 32 rows}, SWIZZLE_128B
     const float* rowmax2;  // InfoNCE only
     const float* rest;     // InfoNCE only
     const int* pivot;      // InfoNCE only
     const float* w;        // per-source weight (1/|x|^2, normalised)
-    __half* W16;           // [M_pad, ld] omega * WSCALE           (InfoNCE only)
-    __half* WL16;          // [M_pad, ld] omega * (d | L) * WSCALE
-    int64_t ld;
     float* q;              // [N]
     float s_log2e;         // InfoNCE: s*log2e/opscale ; SigLIP: s/opscale
     float l_scale;         // 1/opscale: acc -> cosine
     float bias;            // SigLIP logit bias
+    int q_atomic;          // column panels are split along M: accumulate q with red.global.add
   };
   struct State {
     float q[BN / 32];
     float m2, lg1pr, w;
     int piv;
+    int buf;  // slab double-buffer index
   };
+  static constexpr bool ALL_CHUNKS = true;  // slabs are issued per pair of 32-column chunks
+  __device__ static void kernel_begin(State& st, const Params&, const EpiCtx&) { st.buf = 0; }
+  __device__ static void kernel_end(State&, const Params&, const EpiCtx& ctx) {
+    if (ctx.lane == 0) tma_store_wait_all<0>();
+  }
   __device__ static void item_begin(State& st, const Params&, const EpiCtx&, const TileCoord&) {
 #pragma unroll
     for (int i = 0; i < BN / 32; ++i) st.q[i] = 0.f;
@@ -356,36 +385,50 @@ struct EpiGgnWeights {
       } else {
         const float d = fmaf(v[j], p.s_log2e, -st.m2);  // <= 0, exactly 0 at the pivot
         o = (col0 + j == st.piv) ? 0.f : fast_exp2(d - st.lg1pr);
-        v[j] = d;
+        v[j] = d * (GGN_WDSCALE / GGN_WSCALE);
       }
-      om[j] = (row_ok && j < n_valid) ? o : 0.f;
+      om[j] = (row_ok && j < n_valid) ? o * GGN_WSCALE : 0.f;  // zeros beyond C: the K padding of pass 3 must be exact
     }
-    if (row_ok) {
-      const bool al = (p.ld & 7) == 0;
-      const int64_t off = static_cast<int64_t>(row) * p.ld + col0;
-      float t[32];
+    // ---- stage fp16 omega / omega*(d|L) in the warp's slabs (two 32-column chunks fill one 64-column slab)
+    const uint32_t base = ctx.scratch_u32 + static_cast<uint32_t>(ctx.ew) * (4 * SLAB_BYTES) +
+                          static_cast<uint32_t>(st.buf) * (2 * SLAB_BYTES);
+    const int h = c & 1;
+    if (h == 0) slab_wait_free<1>(ctx.lane);  // the bulk group issued two slab pairs ago has finished reading
+    if constexpr (!SIGLIP) slab_write_f16_half(base, ctx.lane, h, om);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) t[j] = om[j] * GGN_WSCALE;
-      if constexpr (!SIGLIP) store_row32_f16(p.W16 + off, t, n_valid, al);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) t[j] *= v[j] * (SIGLIP ? 1.f : GGN_WDSCALE / GGN_WSCALE);
-      store_row32_f16(p.WL16 + off, t, n_valid, al);
+    for (int j = 0; j < 32; ++j) v[j] *= om[j];
+    slab_write_f16_half(base + SLAB_BYTES, ctx.lane, h, v);
+    if (h == 1) {
+      const int row0 = tc.m * GEMM_BM + ctx.ew * 32;
+      if constexpr (!SIGLIP) slab_issue(&p.tm_w, base, ctx.lane, col0 - 32, row0);
+      slab_issue(&p.tm_wl, base + SLAB_BYTES, ctx.lane, col0 - 32, row0);
+      slab_commit(ctx.lane);
+      st.buf ^= 1;
     }
+    // ---- weighted column sums
 #pragma unroll
-    for (int j = 0; j < 32; ++j) om[j] *= st.w;
+    for (int j = 0; j < 32; ++j) om[j] *= st.w * (1.0f / GGN_WSCALE);
     st.q[c] += warp_transpose_reduce32(om, ctx.lane);
   }
   __device__ static void tile_end(State&, const Params&, const EpiCtx&, const TileCoord&) {}
   __device__ static void item_end(State& st, const Params& p, const EpiCtx& ctx, const TileCoord& tc) {
-    float* s = ctx.scratch;
+    // the slabs double as the exchange buffer: wait until no bulk store reads them any more
+    slab_wait_free<0>(ctx.lane);
+    const uint32_t s = ctx.scratch_u32;
     epi_bar_sync();
 #pragma unroll
-    for (int i = 0; i < BN / 32; ++i) s[ctx.ew * BN + i * 32 + ctx.lane] = st.q[i];
+    for (int i = 0; i < BN / 32; ++i) sts_f32(s + 4u * static_cast<uint32_t>(ctx.ew * BN + i * 32 + ctx.lane), st.q[i]);
     epi_bar_sync();
     for (int i = ctx.ew * 32 + ctx.lane; i < BN; i += 128) {
       const int col = tc.n * BN + i;
-      if (col < ctx.N) p.q[col] = s[i] + s[BN + i] + s[2 * BN + i] + s[3 * BN + i];
+      if (col < ctx.N) {
+        const float qs = lds_f32(s + 4u * i) + lds_f32(s + 4u * (BN + i)) + lds_f32(s + 4u * (2 * BN + i)) +
+                         lds_f32(s + 4u * (3 * BN + i));
+        if (p.q_atomic) red_add_f32(p.q + col, qs);
+        else p.q[col] = qs;
+      }
     }
+    epi_bar_sync();  // nobody starts writing slabs of the next item before the sums are read
   }
 };
 

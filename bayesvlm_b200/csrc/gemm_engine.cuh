@@ -32,7 +32,7 @@ struct GemmPlan {
   int m_tiles;
   int n_tiles;
   int mode;      // SchedMode
-  int splits;    // split-K factor (SCHED_TILES / SCHED_TRI_TILES)
+  int splits;    // split-K factor (SCHED_TILES / SCHED_TRI_TILES); number of M ranges a column panel is cut into (SCHED_COL_PANEL)
   int tri_k;     // 1: operand B is lower triangular in (n,k) -> K loop stops at the diagonal block
   uint32_t idesc;
   int a_is_3d;       // 1: operand A is fetched through a 3-D map at (k, 0, m * a_outer_step)
@@ -49,16 +49,22 @@ template <int BN>
 __host__ __device__ inline int plan_num_items(const GemmPlan& p) {
   switch (p.mode) {
     case SCHED_ROW_PANEL: return p.m_tiles;
-    case SCHED_COL_PANEL: return p.n_tiles;
+    case SCHED_COL_PANEL: return p.n_tiles * p.splits;
     case SCHED_TRI_TILES: return (p.m_tiles * (p.m_tiles + 1) / 2) * p.splits;
     default: return p.m_tiles * p.n_tiles * p.splits;
   }
 }
+__host__ __device__ inline int col_panel_m0(const GemmPlan& p, int split) {
+  return static_cast<int>(static_cast<long long>(split) * p.m_tiles / p.splits);
+}
 template <int BN>
-__host__ __device__ inline int plan_inner(const GemmPlan& p) {
+__host__ __device__ inline int plan_inner(const GemmPlan& p, int item) {
   switch (p.mode) {
     case SCHED_ROW_PANEL: return p.n_tiles;
-    case SCHED_COL_PANEL: return p.m_tiles;
+    case SCHED_COL_PANEL: {
+      const int split = item / p.n_tiles;
+      return col_panel_m0(p, split + 1) - col_panel_m0(p, split);
+    }
     default: return 1;
   }
 }
@@ -70,8 +76,11 @@ __device__ __forceinline__ TileCoord plan_tile(const GemmPlan& p, int item, int 
     t.m = item;
     t.n = inner;
   } else if (p.mode == SCHED_COL_PANEL) {
-    t.n = item;
-    t.m = inner;
+    t.n = item % p.n_tiles;
+    t.m = col_panel_m0(p, item / p.n_tiles) + inner;
+    t.kb0 = 0;
+    t.kb1 = p.kb_total;
+    return t;
   } else if (p.mode == SCHED_TRI_TILES) {
     const int tri = p.m_tiles * (p.m_tiles + 1) / 2;
     const int idx = item % tri;
@@ -103,21 +112,72 @@ struct EpiCtx {
   int ew;          // epilogue warp 0..3 (== TMEM lane quadrant)
   int lane;        // lane in warp
   int M, N;        // valid extents
-  float* scratch;  // Epi::SCRATCH_BYTES of shared memory, shared by the four epilogue warps
+  float* scratch;        // Epi::SCRATCH_BYTES of shared memory (1024-byte aligned), shared by the four epilogue warps
+  uint32_t scratch_u32;  // the same block as a shared-window address (for st.shared / ld.shared / TMA stores)
 };
+
+// ---------------------------------------------------------------------------------------------
+// Output staging for TMA stores: every epilogue warp owns 32 accumulator rows; a "slab" is 32 rows x 128 bytes of
+// shared memory in the 128-byte-swizzle pattern (16-byte chunk k of row r lives at chunk k ^ (r & 7)), which is what
+// a SWIZZLE_128B tensor map with a {128 bytes, 32 rows} box reads.  Threads write their own row with conflict-free
+// st.shared.v4 (each quarter-warp hits eight different 16-byte bank groups); one lane then issues the bulk store, so
+// global memory sees full 128-byte lines instead of 32 scattered 16-byte pieces per instruction.
+// ---------------------------------------------------------------------------------------------
+constexpr int SLAB_BYTES = 32 * 128;
+
+__device__ __forceinline__ void slab_write_f32(uint32_t slab, int lane, const float (&v)[32]) {
+  const uint32_t row = slab + static_cast<uint32_t>(lane) * 128u;
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    sts_v4(row + (static_cast<uint32_t>(k ^ (lane & 7)) << 4), v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+}
+// 32 fp16 columns (64 bytes) into half `h` (0/1) of the thread's 128-byte slab row
+__device__ __forceinline__ void slab_write_f16_half(uint32_t slab, int lane, int h, const float (&v)[32]) {
+  const uint32_t row = slab + static_cast<uint32_t>(lane) * 128u;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    uint32_t pk[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __half2 h2 = __floats2half2_rn(v[8 * k + 2 * i], v[8 * k + 2 * i + 1]);
+      pk[i] = *reinterpret_cast<uint32_t*>(&h2);
+    }
+    sts_v4_u32(row + (static_cast<uint32_t>((4 * h + k) ^ (lane & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
+  }
+}
+// make the warp's st.shared visible to the async proxy, then one lane issues the bulk tensor store
+__device__ __forceinline__ void slab_issue(const CUtensorMap* tm, uint32_t slab, int lane, int c0, int c1) {
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 :
+                 : "l"(reinterpret_cast<uint64_t>(tm)), "r"(slab), "r"(c0), "r"(c1)
+                 : "memory");
+  }
+}
+__device__ __forceinline__ void slab_commit(int lane) {
+  if (lane == 0) tma_store_commit();
+}
+// wait until at most N of this lane's committed bulk groups still read shared memory, then release the warp
+template <int N>
+__device__ __forceinline__ void slab_wait_free(int lane) {
+  if (lane == 0) tma_store_wait_read<N>();
+  __syncwarp();
+}
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 template <int BN, int STAGES, class Epi>
 constexpr size_t gemm_smem_bytes() {
   return 1024 + static_cast<size_t>(STAGES) * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) + GEMM_AUX_BYTES +
-         Epi::SCRATCH_BYTES;
+         ((Epi::SCRATCH_BYTES + 1023) / 1024) * 1024;
 }
 
 template <int BN, int STAGES, class Epi>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmPlan plan,
-               const typename Epi::Params ep) {
+               const __grid_constant__ typename Epi::Params ep) {
   static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN must be a multiple of 32 in [32,256]");
   constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   constexpr int B_BYTES = BN * GEMM_BK * 2;
@@ -127,13 +187,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_BYTES;
-  uint8_t* aux = sB + STAGES * B_BYTES;
+  float* scratch = reinterpret_cast<float*>(sB + STAGES * B_BYTES);  // 1024-byte aligned
+  uint8_t* aux = sB + STAGES * B_BYTES + ((Epi::SCRATCH_BYTES + 1023) / 1024) * 1024;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  float* scratch = reinterpret_cast<float*>(aux + GEMM_AUX_BYTES);
   static_assert((2 * STAGES + 4) * 8 + 4 <= GEMM_AUX_BYTES, "aux region too small");
 
   const int warp = threadIdx.x >> 5;
@@ -164,7 +224,6 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
 
   const int n_items = plan_num_items<BN>(plan);
-  const int n_inner = plan_inner<BN>(plan);
 
   if (warp == 0) {
     // ------------------------------------------------ TMA producer
@@ -172,6 +231,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int n_inner = plan_inner<BN>(plan, item);
         for (int inner = 0; inner < n_inner; ++inner) {
           const TileCoord tc = plan_tile<BN>(plan, item, inner);
           for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
@@ -199,6 +259,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int n_inner = plan_inner<BN>(plan, item);
         for (int inner = 0; inner < n_inner; ++inner) {
           const TileCoord tc = plan_tile<BN>(plan, item, inner);
           mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
@@ -235,10 +296,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     ctx.M = plan.M;
     ctx.N = plan.N;
     ctx.scratch = scratch;
+    ctx.scratch_u32 = smem_u32(scratch);
     typename Epi::State st;
+    Epi::kernel_begin(st, ep, ctx);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int n_inner = plan_inner<BN>(plan, item);
       Epi::item_begin(st, ep, ctx, plan_tile<BN>(plan, item, 0));
       for (int inner = 0; inner < n_inner; ++inner) {
         const TileCoord tc = plan_tile<BN>(plan, item, inner);
@@ -249,7 +313,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int n_valid = plan.N - tc.n * BN;
 #pragma unroll
         for (int c = 0; c < BN / 32; ++c) {
-          if (c * 32 >= n_valid) break;
+          if (!Epi::ALL_CHUNKS && c * 32 >= n_valid) break;
           float v[32];
           tmem_ld_32x32(taddr + static_cast<uint32_t>(c * 32), v);
           tmem_ld_wait();
@@ -263,6 +327,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       Epi::item_end(st, ep, ctx, plan_tile<BN>(plan, item, 0));
     }
+    Epi::kernel_end(st, ep, ctx);  // e.g. drain outstanding bulk stores before shared memory goes away
   }
 
   tc_fence_before();

@@ -29,6 +29,7 @@ namespace {
 
 constexpr int GGN_BN = 256;
 constexpr int GGN_STAGES = 4;
+constexpr int GGN_W_STAGES = 3;  // the weights pass trades one operand stage for double-buffered output slabs
 constexpr int SYRK_BN = 128;
 constexpr int SYRK_STAGES = 6;
 constexpr float GGN_OPSCALE = 256.f;  // unit vectors -> fp16
@@ -138,22 +139,32 @@ int ggn_impl(const float* X, int64_t B, int64_t ldx, const float* Y, int64_t C, 
   {
     GemmPlan p2 = make_plan<GGN_BN>(static_cast<int>(B), static_cast<int>(C), static_cast<int>(Kl), SCHED_COL_PANEL, 1,
                                     FMT_F16, FMT_F16);
-    if (siglip) {
-      EpiGgnWeights<GGN_BN, true>::Params e2{nullptr, nullptr, nullptr, g.w, nullptr, WL16, g.Cp, g.q, s / op2, 1.0f / op2,
-                                             logit_bias};
-      if ((rc = launch_gemm<GGN_BN, GGN_STAGES, EpiGgnWeights<GGN_BN, true>>(tmX, tmY, p2, e2, st, TAG_GGN_WEIGHTS))) return rc;
-    } else {
-      EpiGgnWeights<GGN_BN, false>::Params e2{g.rowmax2, g.rest, g.pivot, g.w, W16, WL16, g.Cp, g.q, s * kLog2e / op2,
-                                              1.0f / op2, 0.f};
-      if ((rc = launch_gemm<GGN_BN, GGN_STAGES, EpiGgnWeights<GGN_BN, false>>(tmX, tmY, p2, e2, st, TAG_GGN_WEIGHTS))) return rc;
+    // cut every column panel into M ranges so that all SMs get an even share; q is then accumulated atomically
+    const int sms = device_sm_count();
+    int ps = 1;
+    if (p2.n_tiles < 4 * sms) {
+      ps = (8 * sms + p2.n_tiles - 1) / p2.n_tiles;
+      if (ps > p2.m_tiles) ps = p2.m_tiles;
+      if (ps < 1) ps = 1;
     }
-  }
-  if (g.Cp != C) {  // K padding of pass 3 must be exact zeros
-    if (!siglip)
-      BVLM_CUDA_TRY(cudaMemset2DAsync(W16 + C, static_cast<size_t>(g.Cp) * 2, 0, static_cast<size_t>(g.Cp - C) * 2,
-                                      static_cast<size_t>(B), st));
-    BVLM_CUDA_TRY(cudaMemset2DAsync(WL16 + C, static_cast<size_t>(g.Cp) * 2, 0, static_cast<size_t>(g.Cp - C) * 2,
-                                    static_cast<size_t>(B), st));
+    p2.splits = ps;
+    if (ps > 1) BVLM_CUDA_TRY(cudaMemsetAsync(g.q, 0, static_cast<size_t>(C) * sizeof(float), st));
+    CUtensorMap tmW, tmWL;
+    if ((rc = make_tmap_2d(&tmW, W16, TM_F16, static_cast<uint64_t>(g.Cp), static_cast<uint64_t>(B),
+                           static_cast<uint64_t>(g.Cp) * 2, 64, 32, 1)))
+      return rc;
+    if ((rc = make_tmap_2d(&tmWL, WL16, TM_F16, static_cast<uint64_t>(g.Cp), static_cast<uint64_t>(B),
+                           static_cast<uint64_t>(g.Cp) * 2, 64, 32, 1)))
+      return rc;
+    if (siglip) {
+      EpiGgnWeights<GGN_BN, true>::Params e2{tmW, tmWL, nullptr, nullptr, nullptr, g.w, g.q, s / op2, 1.0f / op2, logit_bias,
+                                             ps > 1 ? 1 : 0};
+      if ((rc = launch_gemm<GGN_BN, GGN_W_STAGES, EpiGgnWeights<GGN_BN, true>>(tmX, tmY, p2, e2, st, TAG_GGN_WEIGHTS))) return rc;
+    } else {
+      EpiGgnWeights<GGN_BN, false>::Params e2{tmW, tmWL, g.rowmax2, g.rest, g.pivot, g.w, g.q, s * kLog2e / op2, 1.0f / op2,
+                                              0.f, ps > 1 ? 1 : 0};
+      if ((rc = launch_gemm<GGN_BN, GGN_W_STAGES, EpiGgnWeights<GGN_BN, false>>(tmX, tmY, p2, e2, st, TAG_GGN_WEIGHTS))) return rc;
+    }
   }
 
   // ---- gamma = max_c q_c and the derived scalars

@@ -57,6 +57,8 @@ extern "C" {
 
 int64_t bvlm_padded_k(int64_t k) { return pad64(k); }
 
+int64_t bvlm_padded_cols(int64_t c) { return round_up_i64(c, PRED_BN); }
+
 int bvlm_factor_prepare(const float* W, int64_t dA, int64_t ldw, float w_scale, void* W16, int64_t k_pad, void* stream) {
   if (W == nullptr || W16 == nullptr || dA <= 0 || k_pad != pad64(dA)) return BVLM_EINVAL;
   return launch_rows_to_16(W, dA, dA, ldw, 0, FMT_F16, 0, w_scale, W16, k_pad, nullptr, static_cast<cudaStream_t>(stream));
@@ -98,6 +100,12 @@ int bvlm_predictive_target_prepare(const float* T, int64_t C, int64_t D, int64_t
   int rc = quadform_impl(Tact, C, d_act, ldact, append_one, Wt16, dA, k_pad, w_scale, gamma,
                          static_cast<uint8_t*>(ws) + used, ws_bytes - used, st);
   if (rc) return rc;
+  // the epilogue reads colA / colB in whole column tiles: zero the padded tail
+  const int64_t cpad = bvlm_padded_cols(C);
+  if (cpad > C) {
+    BVLM_CUDA_TRY(cudaMemsetAsync(colA + C, 0, static_cast<size_t>(cpad - C) * sizeof(float), st));
+    BVLM_CUDA_TRY(cudaMemsetAsync(colB + C, 0, static_cast<size_t>(cpad - C) * sizeof(float), st));
+  }
   // side 1: out0 = gamma/E, out1 = (gamma*kappa + sum_d beta_d t_d^2)/E ; E = |t|^2 + gamma * sum(delta)
   return launch_predictive_row_prep(T, C, D, ldt, gamma, beta, sum_delta, kappa, 0.f, /*side=*/1, precision,
                                     PRED_OPSCALE, static_cast<__half*>(T16), pad64(D), colA, colB, st);
@@ -146,7 +154,26 @@ int bvlm_predictive(const float* E, int64_t N, int64_t D, int64_t lde, const flo
   if ((rc = operand_tmap<PRED_BN>(&tmB, opB))) return rc;
   GemmPlan plan = make_plan<PRED_BN>(static_cast<int>(N), static_cast<int>(C), static_cast<int>(kp), SCHED_TILES, 1,
                                      FMT_F16, FMT_F16);
-  EpiPredictive<PRED_BN>::Params ep{mean, var, ldo, rowU, rowV, colA, colB, s / (PRED_OPSCALE * PRED_OPSCALE)};
+  EpiPredictive<PRED_BN>::Params ep{};
+  ep.mean = mean;
+  ep.var = var;
+  ep.ld = ldo;
+  ep.u = rowU;
+  ep.v = rowV;
+  ep.a = colA;
+  ep.b = colB;
+  ep.mean_scale = s / (PRED_OPSCALE * PRED_OPSCALE);
+  // TMA stores need 16-byte aligned rows; tiny class counts (e.g. C = 10) fall back to direct stores
+  ep.use_tma = ((ldo * 4) % 16 == 0 && (reinterpret_cast<uintptr_t>(mean) & 15) == 0 &&
+                (reinterpret_cast<uintptr_t>(var) & 15) == 0) ? 1 : 0;
+  if (ep.use_tma) {
+    if ((rc = make_tmap_2d(&ep.tm_mean, mean, TM_F32, static_cast<uint64_t>(C), static_cast<uint64_t>(N),
+                           static_cast<uint64_t>(ldo) * 4, 32, 32, 1)))
+      return rc;
+    if ((rc = make_tmap_2d(&ep.tm_var, var, TM_F32, static_cast<uint64_t>(C), static_cast<uint64_t>(N),
+                           static_cast<uint64_t>(ldo) * 4, 32, 32, 1)))
+      return rc;
+  }
   rc = launch_gemm<PRED_BN, PRED_STAGES, EpiPredictive<PRED_BN>>(tmA, tmB, plan, ep, st, TAG_PREDICTIVE);
   if (rc) return rc;
   if (probs != nullptr) rc = launch_probit_softmax(mean, var, N, C, ldo, probs, st);

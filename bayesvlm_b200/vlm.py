@@ -315,8 +315,9 @@ class CLIP(torch.nn.Module):
             raise ValueError(f"target activations have {d_act}(+{bias}) features but A_inv is {tgt.factor.dA}^2")
         seg = int(lib.bvlm_padded_k(d))
         t16 = torch.empty((c, seg * prec), dtype=torch.float16, device=emb.device)
-        col_a = torch.empty(c, dtype=torch.float32, device=emb.device)
-        col_b = torch.empty(c, dtype=torch.float32, device=emb.device)
+        c_pad = int(lib.bvlm_padded_cols(c))  # the epilogue reads whole 256-column tiles
+        col_a = torch.empty(c_pad, dtype=torch.float32, device=emb.device)
+        col_b = torch.empty(c_pad, dtype=torch.float32, device=emb.device)
         ws_bytes = lib.bvlm_predictive_target_workspace_bytes(c, d, d_act, bias)
         ws = _lib.workspace(emb.device, ws_bytes)
         rc = lib.bvlm_predictive_target_prepare(

@@ -74,6 +74,8 @@ int bvlm_ggn_siglip(const float* X, int64_t B, int64_t ldx, const float* Y, int6
  * multiplied by w_scale (a power of two chosen by the caller so that max|W| * w_scale ~ 2^9).
  * --------------------------------------------------------------------------------------------------------- */
 int64_t bvlm_padded_k(int64_t k);
+/* colA / colB of the predictive hold bvlm_padded_cols(C) floats (C rounded up to the 256-wide column tile). */
+int64_t bvlm_padded_cols(int64_t c);
 int bvlm_factor_prepare(const float* W, int64_t dA, int64_t ldw, float w_scale, void* W16, int64_t k_pad, void* stream);
 size_t bvlm_quadform_workspace_bytes(int64_t n, int64_t d, int append_one);
 int bvlm_quadform(const float* act, int64_t n, int64_t d, int64_t ld, int append_one, const void* W16, int64_t dA,
@@ -85,6 +87,7 @@ int bvlm_quadform(const float* act, int64_t n, int64_t d, int64_t ld, int append
  * Target (text/class) side, once per (target set, covariance):
  *   gamma_j = t_act_j^T A_txt_inv t_act_j ; E_j = |t_j|^2 + gamma_j * sum(delta)
  *   T16 [C, prec * d_pad] packed unit-energy embeddings, colA_j = gamma_j / E_j, colB_j = (gamma_j kappa + q_j) / E_j
+ *   (colA / colB: bvlm_padded_cols(C) floats each, zero beyond C)
  * with beta = diag(B_img_inv), delta = diag(B_txt_inv), kappa = beta.delta, q_j = sum_d beta_d t_jd^2.
  *
  * Source (image) side, per call:
