@@ -103,7 +103,7 @@ k_epig_permute(const __half* __restrict__ in, int64_t N, int64_t K, int64_t Cl, 
 // ---------------------------------------------------------------------------------------------------------------
 template <int BN>
 struct EpiEpigJoint {
-  static constexpr size_t SCRATCH_BYTES = 128 * sizeof(float);
+  static constexpr size_t scratch_bytes(int) { return 128 * sizeof(float); }
   struct Params {
     float* Hjoint;      // [Np]
     int64_t Np;
@@ -124,9 +124,9 @@ struct EpiEpigJoint {
 
   __device__ static void flush(State& st, const Params& p, const EpiCtx& ctx) {
     const int r = ctx.ew * 32 + ctx.lane;
-    epi_bar_sync();
+    epi_bar_sync(ctx);
     ctx.scratch[r] = st.valid ? st.chunk_acc : 0.f;
-    epi_bar_sync();
+    epi_bar_sync(ctx);
     if (st.leader) {
       float s = 0.f;
       for (int c = 0; c < p.Cl; ++c) s += ctx.scratch[r + c];

@@ -6,7 +6,7 @@
 namespace bvlm {
 
 __device__ __forceinline__ int epi_row(const EpiCtx& ctx, const TileCoord& tc) {
-  return tc.m * GEMM_BM + ctx.ew * 32 + ctx.lane;
+  return tc.row0 + ctx.ew * 32 + ctx.lane;
 }
 
 // Store 32 consecutive fp32 of one row; vectorised when the slice is complete and 16-byte aligned.
@@ -65,7 +65,7 @@ __device__ __forceinline__ float warp_transpose_reduce32(float (&v)[32], int lan
 // ---------------------------------------------------------------------------------------------
 template <int BN>
 struct EpiStoreF32 {
-  static constexpr size_t SCRATCH_BYTES = 16;
+  static constexpr size_t scratch_bytes(int) { return 16; }
   struct Params {
     float* C;
     int64_t ldc;
@@ -123,7 +123,7 @@ struct EpiStoreF32 {
 // ---------------------------------------------------------------------------------------------
 template <int BN>
 struct EpiRowSumSq {
-  static constexpr size_t SCRATCH_BYTES = 16;
+  static constexpr size_t scratch_bytes(int) { return 16; }
   struct Params {
     float* out;
     const float* row_scale;  // optional per-row multiplier (undoes the per-row power-of-two operand scaling)
@@ -165,7 +165,7 @@ struct EpiRowSumSq {
 // ---------------------------------------------------------------------------------------------
 template <int BN>
 struct EpiPredictive {
-  static constexpr size_t SCRATCH_BYTES = 4 * 2 * SLAB_BYTES;  // per epilogue warp: one mean slab + one var slab
+  static constexpr size_t scratch_bytes(int warps) { return warps * 2 * SLAB_BYTES; }  // per warp: mean slab + var slab
   struct Params {
     CUtensorMap tm_mean, tm_var;  // [N, C] fp32, box {32 cols, 32 rows}, SWIZZLE_128B (used when use_tma)
     float* mean;
@@ -211,9 +211,9 @@ struct EpiPredictive {
     for (int j = 0; j < 32; ++j) v[j] *= p.mean_scale;
     if (p.use_tma) {
       // rows beyond N and columns beyond C are clipped by the tensor map
-      const uint32_t slab_m = ctx.scratch_u32 + static_cast<uint32_t>(ctx.ew) * (2 * SLAB_BYTES);
+      const uint32_t slab_m = ctx.scratch_u32 + static_cast<uint32_t>(ctx.wid) * (2 * SLAB_BYTES);
       const uint32_t slab_v = slab_m + SLAB_BYTES;
-      const int row0 = tc.m * GEMM_BM + ctx.ew * 32;
+      const int row0 = tc.row0 + ctx.ew * 32;
       slab_wait_free<1>(ctx.lane);  // pending: previous mean, previous var -> the mean slab is free again
       slab_write_f32(slab_m, ctx.lane, v);
       slab_issue(&p.tm_mean, slab_m, ctx.lane, col0, row0);
@@ -245,7 +245,7 @@ struct EpiPredictive {
 // ---------------------------------------------------------------------------------------------
 template <int BN>
 struct EpiRowLse {
-  static constexpr size_t SCRATCH_BYTES = 16;
+  static constexpr size_t scratch_bytes(int) { return 16; }
   struct Params {
     float* rowmax2;  // [B] m   (log2 units)
     float* rest;     // [B]
@@ -324,8 +324,8 @@ constexpr float GGN_WDSCALE = 64.f;
 template <int BN, bool SIGLIP>
 struct EpiGgnWeights {
   // per epilogue warp: double-buffered slabs for omega and omega*(d|L); the column-sum exchange reuses the block
-  static constexpr size_t SCRATCH_BYTES = 4 * 4 * SLAB_BYTES;
-  static_assert(SCRATCH_BYTES >= 4 * BN * sizeof(float), "column-sum exchange needs 4*BN floats");
+  static constexpr size_t scratch_bytes(int warps) { return warps * 4 * SLAB_BYTES; }
+  static_assert(4 * 4 * SLAB_BYTES >= 4 * BN * sizeof(float), "column-sum exchange needs 4*BN floats");
   struct Params {
     CUtensorMap tm_w, tm_wl;  // [B, Cp] fp16, box {64 cols, 32 rows}, SWIZZLE_128B
     const float* rowmax2;  // InfoNCE only
@@ -390,7 +390,7 @@ struct EpiGgnWeights {
       om[j] = (row_ok && j < n_valid) ? o * GGN_WSCALE : 0.f;  // zeros beyond C: the K padding of pass 3 must be exact
     }
     // ---- stage fp16 omega / omega*(d|L) in the warp's slabs (two 32-column chunks fill one 64-column slab)
-    const uint32_t base = ctx.scratch_u32 + static_cast<uint32_t>(ctx.ew) * (4 * SLAB_BYTES) +
+    const uint32_t base = ctx.scratch_u32 + static_cast<uint32_t>(ctx.wid) * (4 * SLAB_BYTES) +
                           static_cast<uint32_t>(st.buf) * (2 * SLAB_BYTES);
     const int h = c & 1;
     if (h == 0) slab_wait_free<1>(ctx.lane);  // the bulk group issued two slab pairs ago has finished reading
@@ -399,7 +399,7 @@ struct EpiGgnWeights {
     for (int j = 0; j < 32; ++j) v[j] *= om[j];
     slab_write_f16_half(base + SLAB_BYTES, ctx.lane, h, v);
     if (h == 1) {
-      const int row0 = tc.m * GEMM_BM + ctx.ew * 32;
+      const int row0 = tc.row0 + ctx.ew * 32;
       if constexpr (!SIGLIP) slab_issue(&p.tm_w, base, ctx.lane, col0 - 32, row0);
       slab_issue(&p.tm_wl, base + SLAB_BYTES, ctx.lane, col0 - 32, row0);
       slab_commit(ctx.lane);
@@ -415,11 +415,16 @@ struct EpiGgnWeights {
     // the slabs double as the exchange buffer: wait until no bulk store reads them any more
     slab_wait_free<0>(ctx.lane);
     const uint32_t s = ctx.scratch_u32;
-    epi_bar_sync();
+    epi_bar_sync(ctx);
+    {
+      const int per = (BN / 32) / (ctx.n_warps / 4);  // chunks per warp
+      const int c0 = (ctx.wid / 4) * per;
 #pragma unroll
-    for (int i = 0; i < BN / 32; ++i) sts_f32(s + 4u * static_cast<uint32_t>(ctx.ew * BN + i * 32 + ctx.lane), st.q[i]);
-    epi_bar_sync();
-    for (int i = ctx.ew * 32 + ctx.lane; i < BN; i += 128) {
+      for (int i = 0; i < BN / 32; ++i)
+        if (i >= c0 && i < c0 + per) sts_f32(s + 4u * static_cast<uint32_t>(ctx.ew * BN + i * 32 + ctx.lane), st.q[i]);
+    }
+    epi_bar_sync(ctx);
+    for (int i = ctx.wid * 32 + ctx.lane; i < BN; i += ctx.n_warps * 32) {
       const int col = tc.n * BN + i;
       if (col < ctx.N) {
         const float qs = lds_f32(s + 4u * i) + lds_f32(s + 4u * (BN + i)) + lds_f32(s + 4u * (2 * BN + i)) +
@@ -428,7 +433,7 @@ struct EpiGgnWeights {
         else p.q[col] = qs;
       }
     }
-    epi_bar_sync();  // nobody starts writing slabs of the next item before the sums are read
+    epi_bar_sync(ctx);  // nobody starts writing slabs of the next item before the sums are read
   }
 };
 

@@ -1,0 +1,335 @@
+// Two-CTA (cta_group::2) variant of the tcgen05 GEMM engine:  D[M,N] = A[M,K] * B[N,K]^T on CTA PAIRS.
+//
+// A cluster of two CTAs (two SMs of one TPC) computes a 256 x BN output tile with tcgen05.mma.cta_group::2 (M = 256):
+//   * CTA r of the pair owns accumulator rows [256 m + 128 r, +128) in ITS tensor memory and loads ITS 128 x 64 slice of
+//     A plus HALF of the B tile (BN/2 x 64) per K block -- 32 KB per stage instead of 48 KB, so six stages fit where the
+//     one-CTA engine has four (the one-CTA main loop was TMA-latency bound: ncu, profiles/r1a_*), and every B byte is
+//     fetched from L2 once per pair instead of once per CTA;
+//   * both producers signal ONE full barrier in the leader CTA (cp.async.bulk.tensor ... .cta_group::2 with the peer bit
+//     of the barrier address cleared); the leader's elected thread issues the MMAs, and tcgen05.commit multicasts the
+//     "stage free" / "accumulator ready" arrivals to the barriers at the same offset in both CTAs;
+//   * 4 or 8 epilogue warps per CTA drain the CTA's own 128 TMEM lanes (8 warps: two per lane quadrant, each taking half
+//     of the BN columns) and run the same pluggable epilogue functors as the one-CTA engine.
+// Schedules: SCHED_TILES (optionally split-K), SCHED_ROW_PANEL, SCHED_COL_PANEL, with M tiles of 256 rows.
+#pragma once
+#include "gemm_engine.cuh"
+
+namespace bvlm {
+
+constexpr int GEMM2_BM = 256;         // rows per cluster tile
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;  // shared::cluster address of the same offset in the even (leader) CTA
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive (+ expect_tx) on the barrier at the same offset in the leader CTA, from either CTA of the pair
+__device__ __forceinline__ void mbar_arrive_expect_tx_leader(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(smem_u32(bar) & PEER_BIT_MASK), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_BIT_MASK) : "memory");
+}
+// TMA load into THIS CTA's shared memory, transaction bytes credited to the LEADER CTA's barrier
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int32_t c0,
+                                                 int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_ss_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at this offset in BOTH CTAs once all previously issued MMAs of the pair have completed
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+      "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
+
+template <int BN, int STAGES, int EPI_WARPS, class Epi>
+constexpr size_t gemm2_smem_bytes() {
+  return 1024 + static_cast<size_t>(STAGES) * (GEMM_BM * GEMM_BK * 2 + (BN / 2) * GEMM_BK * 2) + GEMM_AUX_BYTES +
+         ((Epi::scratch_bytes(EPI_WARPS) + 1023) / 1024) * 1024;
+}
+
+template <int BN, int STAGES, int EPI_WARPS, class Epi>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * EPI_WARPS, 1)
+gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmPlan plan,
+                const __grid_constant__ typename Epi::Params ep) {
+  static_assert(BN % 64 == 0 && BN >= 64 && BN <= 256, "BN must be a multiple of 64 in [64,256]");
+  static_assert(EPI_WARPS == 4 || EPI_WARPS == 8, "4 or 8 epilogue warps");
+  constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;    // this CTA's 128 rows of A
+  constexpr int B_BYTES = (BN / 2) * GEMM_BK * 2;   // this CTA's half of the B tile
+  constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  constexpr int CHUNKS = BN / 32;
+  constexpr int CH_PER_WARP = CHUNKS / (EPI_WARPS / 4);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_BYTES;
+  float* scratch = reinterpret_cast<float*>(sB + STAGES * B_BYTES);
+  uint8_t* aux = sB + STAGES * B_BYTES + ((Epi::scratch_bytes(EPI_WARPS) + 1023) / 1024) * 1024;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);   // used in the leader CTA: 2 producer arrivals + tx bytes
+  uint64_t* empty_bar = full_bar + STAGES;                  // per CTA: 1 arrival (multicast commit)
+  uint64_t* tfull_bar = empty_bar + STAGES;                 // per CTA: 1 arrival (multicast commit)
+  uint64_t* tempty_bar = tfull_bar + 2;                     // used in the leader CTA: 2 * EPI_WARPS arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  static_assert((2 * STAGES + 4) * 8 + 4 <= GEMM_AUX_BYTES, "aux region too small");
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 2);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 2 * EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_pair(tmem_slot, TMEM_COLS);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  cluster_sync_all();  // barriers of BOTH CTAs are initialised before anyone arrives remotely
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_items = plan_num_items<BN>(plan);
+  const int cluster_id = blockIdx.x >> 1;
+  const int n_clusters = gridDim.x >> 1;
+
+  if (warp == 0) {
+    // ------------------------------------------------ TMA producer (one per CTA)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = cluster_id; item < n_items; item += n_clusters) {
+        const int n_inner = plan_inner<BN>(plan, item);
+        for (int inner = 0; inner < n_inner; ++inner) {
+          const TileCoord tc = plan_tile<BN>(plan, item, inner);
+          const int row_a = tc.m * GEMM2_BM + static_cast<int>(rank) * GEMM_BM;
+          const int row_b = tc.n * BN + static_cast<int>(rank) * (BN / 2);
+          int seg_v = 0, seg_off = tc.kb0;
+          for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
+            int col_a = kb * GEMM_BK, col_b = col_a;
+            if (plan.seg_kb != 0) {
+              col_a = (static_cast<int>((plan.a_seg_mask >> seg_v) & 1u) * plan.seg_kb + seg_off) * GEMM_BK;
+              col_b = (static_cast<int>((plan.b_seg_mask >> seg_v) & 1u) * plan.seg_kb + seg_off) * GEMM_BK;
+              if (++seg_off == plan.seg_kb) {
+                seg_off = 0;
+                ++seg_v;
+              }
+            }
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            mbar_arrive_expect_tx_leader(&full_bar[stage], A_BYTES + B_BYTES);
+            tma_load_2d_pair(sA + stage * A_BYTES, &tmA, &full_bar[stage], col_a, row_a);
+            tma_load_2d_pair(sB + stage * B_BYTES, &tmB, &full_bar[stage], col_b, row_b);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer (one thread of the leader CTA)
+    if (leader && lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int item = cluster_id; item < n_items; item += n_clusters) {
+        const int n_inner = plan_inner<BN>(plan, item);
+        for (int inner = 0; inner < n_inner; ++inner) {
+          const TileCoord tc = plan_tile<BN>(plan, item, inner);
+          mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BN);
+          for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint64_t da = make_smem_desc_kmajor_sw128(smem_u32(sA + stage * A_BYTES));
+            const uint64_t db = make_smem_desc_kmajor_sw128(smem_u32(sB + stage * B_BYTES));
+#pragma unroll
+            for (int k = 0; k < GEMM_BK / GEMM_UMMA_K; ++k) {
+              umma_f16_ss_pair(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), plan.idesc,
+                               (kb > tc.kb0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit_pair(&empty_bar[stage]);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+          umma_commit_pair(&tfull_bar[acc]);
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp >= GEMM_EPI_WARP0) {
+    // ------------------------------------------------ epilogue warps (both CTAs, own TMEM lanes)
+    EpiCtx ctx;
+    ctx.wid = warp - GEMM_EPI_WARP0;
+    ctx.ew = ctx.wid & 3;
+    ctx.n_warps = EPI_WARPS;
+    ctx.lane = lane;
+    ctx.M = plan.M;
+    ctx.N = plan.N;
+    ctx.scratch = scratch;
+    ctx.scratch_u32 = smem_u32(scratch);
+    const int chalf = ctx.wid >> 2;
+    typename Epi::State st;
+    Epi::kernel_begin(st, ep, ctx);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int item = cluster_id; item < n_items; item += n_clusters) {
+      const int n_inner = plan_inner<BN>(plan, item);
+      TileCoord t0 = plan_tile<BN>(plan, item, 0);
+      t0.row0 = t0.m * GEMM2_BM + static_cast<int>(rank) * GEMM_BM;
+      Epi::item_begin(st, ep, ctx, t0);
+      for (int inner = 0; inner < n_inner; ++inner) {
+        TileCoord tc = plan_tile<BN>(plan, item, inner);
+        tc.row0 = tc.m * GEMM2_BM + static_cast<int>(rank) * GEMM_BM;
+        Epi::tile_begin(st, ep, ctx, tc);
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ctx.ew * 32) << 16) + static_cast<uint32_t>(acc * BN);
+        const int n_valid = plan.N - tc.n * BN;
+#pragma unroll
+        for (int c = 0; c < CHUNKS; ++c) {
+          if (c / CH_PER_WARP != chalf) continue;
+          if (!Epi::ALL_CHUNKS && c * 32 >= n_valid) continue;
+          float v[32];
+          tmem_ld_32x32(taddr + static_cast<uint32_t>(c * 32), v);
+          tmem_ld_wait();
+          Epi::chunk(st, ep, ctx, tc, v, c);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
+        Epi::tile_end(st, ep, ctx, tc);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+      Epi::item_end(st, ep, ctx, t0);
+    }
+    Epi::kernel_end(st, ep, ctx);
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // nobody leaves while the peer may still read its shared memory or signal its barriers
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+template <int BN>
+inline GemmPlan make_plan2(int M, int N, int K_padded, int mode, int splits, int fmt) {
+  GemmPlan p = make_plan<BN>(M, N, K_padded, mode, splits, fmt, fmt);
+  p.m_tiles = (M + GEMM2_BM - 1) / GEMM2_BM;
+  p.idesc = make_idesc_f16(GEMM2_BM, BN, fmt, fmt);
+  return p;
+}
+template <int BN>
+inline GemmPlan make_split_plan2(int M, int N, int seg, int mode, int fmt) {
+  GemmPlan p = make_split_plan<BN>(M, N, seg, mode, fmt);
+  p.m_tiles = (M + GEMM2_BM - 1) / GEMM2_BM;
+  p.idesc = make_idesc_f16(GEMM2_BM, BN, fmt, fmt);
+  return p;
+}
+
+// number of CTA pairs that can be co-resident for this instantiation (queried once)
+template <int BN, int STAGES, int EPI_WARPS, class Epi>
+inline int gemm2_max_clusters(size_t smem) {
+  static int cached = -1;
+  if (cached >= 0) return cached;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(device_sm_count() & ~1), 1, 1);
+  cfg.blockDim = dim3(128 + 32 * EPI_WARPS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, gemm2_tn_kernel<BN, STAGES, EPI_WARPS, Epi>, &cfg) != cudaSuccess || n <= 0) {
+    (void)cudaGetLastError();
+    n = device_sm_count() / 2;
+  }
+  cached = n;
+  return n;
+}
+
+// B operand tensor map box rows = BN / 2 (each CTA of the pair loads half of the B tile)
+template <int BN, int STAGES, int EPI_WARPS, class Epi>
+inline int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmPlan& plan,
+                        const typename Epi::Params& ep, cudaStream_t stream, int tag) {
+  if (plan.kb_total <= 0 || plan.M <= 0 || plan.N <= 0) return BVLM_EINVAL;
+  constexpr size_t smem = gemm2_smem_bytes<BN, STAGES, EPI_WARPS, Epi>();
+  static_assert(smem <= 232448, "shared memory budget exceeded");
+  auto kfn = gemm2_tn_kernel<BN, STAGES, EPI_WARPS, Epi>;
+  static bool configured = false;  // per instantiation
+  if (!configured) {
+    BVLM_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    configured = true;
+  }
+  const int items = plan_num_items<BN>(plan);
+  int clusters = gemm2_max_clusters<BN, STAGES, EPI_WARPS, Epi>(smem);
+  if (items < clusters) clusters = items;
+  timing_begin(tag, stream);
+  kfn<<<2 * clusters, 128 + 32 * EPI_WARPS, smem, stream>>>(tmA, tmB, plan, ep);
+  timing_end(tag, stream);
+  count_launch();
+  BVLM_CUDA_TRY(cudaGetLastError());
+  return BVLM_OK;
+}
+
+}  // namespace bvlm

@@ -39,10 +39,17 @@ struct GemmPlan {
   int a_outer_step;  // rows (2-D) or outer-dimension items (3-D) consumed per M tile
   uint32_t a_tx_bytes;
   uint32_t b_tx_bytes;
+  // hi/lo split operands are stored once as [hi | lo] (2 segments of seg_kb K blocks); the three products
+  // hi.hi + lo.hi + hi.lo walk 3 virtual segments whose source segment is a_seg[i] / b_seg[i].  seg_kb == 0: plain.
+  // Bit v of a_seg_mask / b_seg_mask is the stored segment (0 = hi, 1 = lo) virtual segment v reads.
+  int seg_kb;
+  uint32_t a_seg_mask;
+  uint32_t b_seg_mask;
 };
 
 struct TileCoord {
   int m, n, kb0, kb1;
+  int row0;  // first accumulator row of this CTA's 128-row slab of the tile (set by the kernel, engine specific)
 };
 
 template <int BN>
@@ -80,6 +87,7 @@ __device__ __forceinline__ TileCoord plan_tile(const GemmPlan& p, int item, int 
     t.m = col_panel_m0(p, item / p.n_tiles) + inner;
     t.kb0 = 0;
     t.kb1 = p.kb_total;
+    t.row0 = t.m * GEMM_BM;
     return t;
   } else if (p.mode == SCHED_TRI_TILES) {
     const int tri = p.m_tiles * (p.m_tiles + 1) / 2;
@@ -104,12 +112,15 @@ __device__ __forceinline__ TileCoord plan_tile(const GemmPlan& p, int item, int 
   }
   t.kb0 = static_cast<int>(static_cast<long long>(split) * kb_end / p.splits);
   t.kb1 = static_cast<int>(static_cast<long long>(split + 1) * kb_end / p.splits);
+  t.row0 = t.m * GEMM_BM;
   return t;
 }
 
 // Per-thread view the epilogue functors get.
 struct EpiCtx {
-  int ew;          // epilogue warp 0..3 (== TMEM lane quadrant)
+  int ew;          // TMEM lane quadrant 0..3 of this warp (rows 32*ew .. 32*ew+31 of the CTA's slab)
+  int wid;         // epilogue warp index 0..n_warps-1 (wid / 4 selects the column half when there are 8 warps)
+  int n_warps;     // 4 or 8 epilogue warps
   int lane;        // lane in warp
   int M, N;        // valid extents
   float* scratch;        // Epi::SCRATCH_BYTES of shared memory (1024-byte aligned), shared by the four epilogue warps
@@ -166,12 +177,14 @@ __device__ __forceinline__ void slab_wait_free(int lane) {
   __syncwarp();
 }
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync(const EpiCtx& ctx) {
+  asm volatile("bar.sync 1, %0;" ::"r"(ctx.n_warps * 32) : "memory");
+}
 
 template <int BN, int STAGES, class Epi>
 constexpr size_t gemm_smem_bytes() {
   return 1024 + static_cast<size_t>(STAGES) * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) + GEMM_AUX_BYTES +
-         ((Epi::SCRATCH_BYTES + 1023) / 1024) * 1024;
+         ((Epi::scratch_bytes(4) + 1023) / 1024) * 1024;
 }
 
 template <int BN, int STAGES, class Epi>
@@ -188,7 +201,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_BYTES;
   float* scratch = reinterpret_cast<float*>(sB + STAGES * B_BYTES);  // 1024-byte aligned
-  uint8_t* aux = sB + STAGES * B_BYTES + ((Epi::SCRATCH_BYTES + 1023) / 1024) * 1024;
+  uint8_t* aux = sB + STAGES * B_BYTES + ((Epi::scratch_bytes(4) + 1023) / 1024) * 1024;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
@@ -234,15 +247,25 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int n_inner = plan_inner<BN>(plan, item);
         for (int inner = 0; inner < n_inner; ++inner) {
           const TileCoord tc = plan_tile<BN>(plan, item, inner);
+          int seg_v = 0, seg_off = tc.kb0;  // virtual segment / K block inside it (split plans always start at kb0 = 0)
           for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
+            int col_a = kb * GEMM_BK, col_b = col_a;
+            if (plan.seg_kb != 0) {
+              col_a = (static_cast<int>((plan.a_seg_mask >> seg_v) & 1u) * plan.seg_kb + seg_off) * GEMM_BK;
+              col_b = (static_cast<int>((plan.b_seg_mask >> seg_v) & 1u) * plan.seg_kb + seg_off) * GEMM_BK;
+              if (++seg_off == plan.seg_kb) {
+                seg_off = 0;
+                ++seg_v;
+              }
+            }
             mbar_wait(&empty_bar[stage], phase ^ 1u);
             mbar_arrive_expect_tx(&full_bar[stage], plan.a_tx_bytes + plan.b_tx_bytes);
             if (plan.a_is_3d) {
               tma_load_3d(sA + stage * A_BYTES, &tmA, &full_bar[stage], kb * GEMM_BK, 0, tc.m * plan.a_outer_step);
             } else {
-              tma_load_2d(sA + stage * A_BYTES, &tmA, &full_bar[stage], kb * GEMM_BK, tc.m * plan.a_outer_step);
+              tma_load_2d(sA + stage * A_BYTES, &tmA, &full_bar[stage], col_a, tc.m * plan.a_outer_step);
             }
-            tma_load_2d(sB + stage * B_BYTES, &tmB, &full_bar[stage], kb * GEMM_BK, tc.n * BN);
+            tma_load_2d(sB + stage * B_BYTES, &tmB, &full_bar[stage], col_b, tc.n * BN);
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1u;
@@ -292,6 +315,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ------------------------------------------------ epilogue warps
     EpiCtx ctx;
     ctx.ew = warp - GEMM_EPI_WARP0;
+    ctx.wid = ctx.ew;
+    ctx.n_warps = 4;
     ctx.lane = lane;
     ctx.M = plan.M;
     ctx.N = plan.N;
@@ -358,6 +383,17 @@ inline GemmPlan make_plan(int M, int N, int K_padded, int mode, int splits, int 
   p.a_outer_step = GEMM_BM;
   p.a_tx_bytes = GEMM_BM * GEMM_BK * 2;
   p.b_tx_bytes = BN * GEMM_BK * 2;
+  p.seg_kb = 0;
+  return p;
+}
+
+// Three-product plan over operands stored as [hi | lo] with `seg` (multiple of 64) elements per segment.
+template <int BN>
+inline GemmPlan make_split_plan(int M, int N, int seg, int mode, int fmt) {
+  GemmPlan p = make_plan<BN>(M, N, 3 * seg, mode, 1, fmt, fmt);
+  p.seg_kb = seg / GEMM_BK;
+  p.a_seg_mask = 0b010u;  // hi lo hi
+  p.b_seg_mask = 0b100u;  // hi hi lo
   return p;
 }
 
@@ -388,14 +424,20 @@ inline int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
 struct Operand16 {
   const void* ptr;
   int64_t rows;    // valid rows
-  int64_t k_pad;   // padded K (multiple of 64); also the row pitch in elements
+  int64_t k_pad;   // padded K (multiple of 64)
   int fmt;         // OperandFormat
+  int64_t pitch = 0;  // row pitch in elements (0: k_pad)
 };
+
+// Row pitch for library-owned K-major operands: pitches that are a multiple of 1 KiB alias in the L2 slice hash when a
+// tile's rows are fetched 128 bytes at a time, so such pitches get one extra 128-byte line (BVLM_PITCH_PAD overrides).
+int64_t operand_pitch(int64_t k_elems);
 
 template <int BOX_ROWS>
 inline int operand_tmap(CUtensorMap* out, const Operand16& op) {
+  const int64_t pitch = op.pitch > 0 ? op.pitch : op.k_pad;
   return make_tmap_2d(out, op.ptr, op.fmt == FMT_BF16 ? TM_BF16 : TM_F16, static_cast<uint64_t>(op.k_pad),
-                      static_cast<uint64_t>(op.rows), static_cast<uint64_t>(op.k_pad) * 2, GEMM_BK, BOX_ROWS, 1);
+                      static_cast<uint64_t>(op.rows), static_cast<uint64_t>(pitch) * 2, GEMM_BK, BOX_ROWS, 1);
 }
 
 }  // namespace bvlm

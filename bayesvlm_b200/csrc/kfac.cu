@@ -68,8 +68,8 @@ GgnLayout ggn_layout(int64_t B, int64_t C, int64_t D, int siglip, int prec, void
   g.Bs = pad128(B);
   g.Ktot = g.Cp + (siglip ? 1 : 2) * g.Bp;
   Carver cv(ws);
-  g.Xh16 = cv.take<__half>(static_cast<size_t>(B) * g.Dp * prec);
-  g.Yh16 = cv.take<__half>(static_cast<size_t>(C) * g.Dp * prec);
+  g.Xh16 = cv.take<__half>(static_cast<size_t>(B) * g.Dp * (prec == 3 ? 2 : 1));
+  g.Yh16 = cv.take<__half>(static_cast<size_t>(C) * g.Dp * (prec == 3 ? 2 : 1));
   g.YhT16 = cv.take<__half>(static_cast<size_t>(D) * g.Cp);
   g.W16 = cv.take<__half>(static_cast<size_t>(2 * g.Bs) * g.Cp);  // [omega ; omega*d] stacked (SigLIP uses the 2nd half)
   g.L16 = cv.take<__half>(static_cast<size_t>(D) * g.Ktot);
@@ -119,16 +119,21 @@ int ggn_impl(const float* X, int64_t B, int64_t ldx, const float* Y, int64_t C, 
     return rc;
 
   CUtensorMap tmX, tmY;
-  const int64_t Kl = g.Dp * prec;  // logit GEMM: X1 = one fp16 pass, X3 = hi.hi + lo.hi + hi.lo along K
-  Operand16 opX{g.Xh16, B, Kl, FMT_F16};
-  Operand16 opY{g.Yh16, C, Kl, FMT_F16};
+  // logit GEMM: X1 = one fp16 pass; X3 = hi.hi + lo.hi + hi.lo over operands stored as [hi | lo]
+  const int64_t Kst = g.Dp * (prec == 3 ? 2 : 1);
+  Operand16 opX{g.Xh16, B, Kst, FMT_F16};
+  Operand16 opY{g.Yh16, C, Kst, FMT_F16};
+  auto logit_plan = [&](int mode) {
+    return prec == 3 ? make_split_plan<GGN_BN>(static_cast<int>(B), static_cast<int>(C), static_cast<int>(g.Dp), mode, FMT_F16)
+                     : make_plan<GGN_BN>(static_cast<int>(B), static_cast<int>(C), static_cast<int>(g.Dp), mode, 1, FMT_F16,
+                                         FMT_F16);
+  };
   if ((rc = operand_tmap<GEMM_BM>(&tmX, opX))) return rc;
   if ((rc = operand_tmap<GGN_BN>(&tmY, opY))) return rc;
 
   // ---- pass 1 (InfoNCE only): row max, pivot, rest
   if (!siglip) {
-    GemmPlan p1 = make_plan<GGN_BN>(static_cast<int>(B), static_cast<int>(C), static_cast<int>(Kl), SCHED_ROW_PANEL, 1,
-                                    FMT_F16, FMT_F16);
+    GemmPlan p1 = logit_plan(SCHED_ROW_PANEL);
     EpiRowLse<GGN_BN>::Params e1{g.rowmax2, g.rest, g.pivot, s * kLog2e / op2};
     if ((rc = launch_gemm<GGN_BN, GGN_STAGES, EpiRowLse<GGN_BN>>(tmX, tmY, p1, e1, st, TAG_GGN_ROWSTATS))) return rc;
   }
@@ -137,8 +142,7 @@ int ggn_impl(const float* X, int64_t B, int64_t ldx, const float* Y, int64_t C, 
   __half* W16 = g.W16;
   __half* WL16 = g.W16 + static_cast<size_t>(g.Bs) * g.Cp;
   {
-    GemmPlan p2 = make_plan<GGN_BN>(static_cast<int>(B), static_cast<int>(C), static_cast<int>(Kl), SCHED_COL_PANEL, 1,
-                                    FMT_F16, FMT_F16);
+    GemmPlan p2 = logit_plan(SCHED_COL_PANEL);
     // cut every column panel into M ranges so that all SMs get an even share; q is then accumulated atomically
     const int sms = device_sm_count();
     int ps = 1;

@@ -1,7 +1,10 @@
 // P1 / P2 / P3: quadratic forms, fused Kronecker-Laplace predictive GEMM, probit softmax.
 // Reference: bayesvlm/vlm.py:630-684 (CLIP._compute_probabilistic_logits_smith), scripts/zeroshot.py:119-120.
 #include "../../include/bvlm.h"
+#include <cstdlib>
+
 #include "epilogues.cuh"
+#include "gemm2_engine.cuh"
 #include "prep.cuh"
 
 using namespace bvlm;
@@ -108,13 +111,13 @@ int bvlm_predictive_target_prepare(const float* T, int64_t C, int64_t D, int64_t
   }
   // side 1: out0 = gamma/E, out1 = (gamma*kappa + sum_d beta_d t_d^2)/E ; E = |t|^2 + gamma * sum(delta)
   return launch_predictive_row_prep(T, C, D, ldt, gamma, beta, sum_delta, kappa, 0.f, /*side=*/1, precision,
-                                    PRED_OPSCALE, static_cast<__half*>(T16), pad64(D), colA, colB, st);
+                                    PRED_OPSCALE, static_cast<__half*>(T16), pad64(D), 0, colA, colB, st);
 }
 
 size_t bvlm_predictive_workspace_bytes(int64_t N, int64_t D, int64_t d_act, int append_one, int precision) {
   size_t b = bvlm_quadform_workspace_bytes(N, d_act, append_one);
   b += 3 * (round_up_i64(N * 4, 256) + 256);
-  b += round_up_i64(N * pad64(D) * precision * 2, 256) + 256;
+  b += round_up_i64(N * operand_pitch(pad64(D) * (precision == 3 ? 2 : 1)) * 2, 256) + 256;
   return b;
 }
 
@@ -132,12 +135,13 @@ int bvlm_predictive(const float* E, int64_t N, int64_t D, int64_t lde, const flo
   if (ws_bytes < bvlm_predictive_workspace_bytes(N, D, d_act, append_one, precision)) return BVLM_EWORKSPACE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t seg = pad64(D);
-  const int64_t kp = seg * precision;
+  const int64_t kp = seg * (precision == 3 ? 2 : 1);  // stored operand width: [hi | lo] for the split mode
   Carver cv(ws);
   float* alpha = cv.take<float>(static_cast<size_t>(N));
   float* rowU = cv.take<float>(static_cast<size_t>(N));
   float* rowV = cv.take<float>(static_cast<size_t>(N));
-  __half* E16 = cv.take<__half>(static_cast<size_t>(N) * kp);
+  const int64_t e_pitch = operand_pitch(kp);
+  __half* E16 = cv.take<__half>(static_cast<size_t>(N) * e_pitch);
   const size_t used = cv.used();
   int rc = quadform_impl(Eact, N, d_act, ldact, append_one, Wi16, dA, k_pad, w_scale, alpha,
                          static_cast<uint8_t*>(ws) + used, ws_bytes - used, st);
@@ -145,15 +149,28 @@ int bvlm_predictive(const float* E, int64_t N, int64_t D, int64_t lde, const flo
   const float s = expf(logit_scale);
   // side 0: out0 = s^2 (sum_d e_d^2 delta_d)/E, out1 = s^2 alpha/E ; E = |e|^2 + alpha * sum(beta)
   rc = launch_predictive_row_prep(E, N, D, lde, alpha, delta, sum_beta, 0.f, s * s, /*side=*/0, precision, PRED_OPSCALE,
-                                  E16, seg, rowU, rowV, st);
+                                  E16, seg, e_pitch, rowU, rowV, st);
   if (rc) return rc;
   CUtensorMap tmA, tmB;
-  Operand16 opA{E16, N, kp, FMT_F16};
+  Operand16 opA{E16, N, kp, FMT_F16, e_pitch};
   Operand16 opB{T16, C, kp, FMT_F16};
   if ((rc = operand_tmap<GEMM_BM>(&tmA, opA))) return rc;
   if ((rc = operand_tmap<PRED_BN>(&tmB, opB))) return rc;
-  GemmPlan plan = make_plan<PRED_BN>(static_cast<int>(N), static_cast<int>(C), static_cast<int>(kp), SCHED_TILES, 1,
-                                     FMT_F16, FMT_F16);
+  static const int variant = [] {
+    const char* e = getenv("BVLM_PRED_VARIANT");  // 0: one-CTA engine, 1: CTA pairs + 4 epilogue warps, 2: pairs + 8 warps
+    return e != nullptr ? atoi(e) : 2;
+  }();
+  GemmPlan plan;
+  if (variant == 0) {
+    plan = precision == 3
+               ? make_split_plan<PRED_BN>(static_cast<int>(N), static_cast<int>(C), static_cast<int>(seg), SCHED_TILES, FMT_F16)
+               : make_plan<PRED_BN>(static_cast<int>(N), static_cast<int>(C), static_cast<int>(kp), SCHED_TILES, 1, FMT_F16, FMT_F16);
+  } else {
+    plan = precision == 3
+               ? make_split_plan2<PRED_BN>(static_cast<int>(N), static_cast<int>(C), static_cast<int>(seg), SCHED_TILES, FMT_F16)
+               : make_plan2<PRED_BN>(static_cast<int>(N), static_cast<int>(C), static_cast<int>(kp), SCHED_TILES, 1, FMT_F16);
+    if ((rc = operand_tmap<PRED_BN / 2>(&tmB, opB))) return rc;  // each CTA of a pair loads half of the B tile
+  }
   EpiPredictive<PRED_BN>::Params ep{};
   ep.mean = mean;
   ep.var = var;
@@ -174,7 +191,9 @@ int bvlm_predictive(const float* E, int64_t N, int64_t D, int64_t lde, const flo
                            static_cast<uint64_t>(ldo) * 4, 32, 32, 1)))
       return rc;
   }
-  rc = launch_gemm<PRED_BN, PRED_STAGES, EpiPredictive<PRED_BN>>(tmA, tmB, plan, ep, st, TAG_PREDICTIVE);
+  if (variant == 0) rc = launch_gemm<PRED_BN, PRED_STAGES, EpiPredictive<PRED_BN>>(tmA, tmB, plan, ep, st, TAG_PREDICTIVE);
+  else if (variant == 1) rc = launch_gemm2<PRED_BN, 6, 4, EpiPredictive<PRED_BN>>(tmA, tmB, plan, ep, st, TAG_PREDICTIVE);
+  else rc = launch_gemm2<PRED_BN, 5, 8, EpiPredictive<PRED_BN>>(tmA, tmB, plan, ep, st, TAG_PREDICTIVE);
   if (rc) return rc;
   if (probs != nullptr) rc = launch_probit_softmax(mean, var, N, C, ldo, probs, st);
   return rc;

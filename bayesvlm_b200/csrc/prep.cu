@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(ROW_BLOCK) k_rows_to_16(const float* __restric
 __global__ void __launch_bounds__(ROW_BLOCK)
 k_predictive_row_prep(const float* __restrict__ x, int64_t R, int64_t D, int64_t ld, const float* __restrict__ quad,
                       const float* __restrict__ diag_other, float sum_diag_self, float kappa, float s2, int side,
-                      int nsplit, float opscale, __half* __restrict__ packed, int64_t seg_pad,
+                      int nsplit, float opscale, __half* __restrict__ packed, int64_t seg_pad, int64_t out_pitch,
                       float* __restrict__ out0, float* __restrict__ out1) {
   const int64_t row = static_cast<int64_t>(blockIdx.x) * WARPS_PER_BLOCK + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -79,7 +79,8 @@ k_predictive_row_prep(const float* __restrict__ x, int64_t R, int64_t D, int64_t
   const float E = n2 + qd * sum_diag_self;
   const float rinv = 1.0f / sqrtf(E);
   const float mul = rinv * opscale;
-  const int64_t pitch = seg_pad * nsplit;
+  // split operands are stored once as [hi | lo]; out_pitch >= that width (0: tight)
+  const int64_t pitch = out_pitch > 0 ? out_pitch : seg_pad * (nsplit == 3 ? 2 : 1);
   __half* o = packed + row * pitch;
   for (int64_t j = 2 * lane; j < seg_pad; j += 64) {
     const float v0 = j < D ? xr[j] * mul : 0.f;
@@ -89,13 +90,7 @@ k_predictive_row_prep(const float* __restrict__ x, int64_t R, int64_t D, int64_t
     if (nsplit == 3) {
       const float2 hf = __half22float2(hi);
       const __half2 lo = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
-      if (side == 0) {  // A operand: [hi | lo | hi]
-        *reinterpret_cast<__half2*>(o + seg_pad + j) = lo;
-        *reinterpret_cast<__half2*>(o + 2 * seg_pad + j) = hi;
-      } else {  // B operand: [hi | hi | lo]
-        *reinterpret_cast<__half2*>(o + seg_pad + j) = hi;
-        *reinterpret_cast<__half2*>(o + 2 * seg_pad + j) = lo;
-      }
+      *reinterpret_cast<__half2*>(o + seg_pad + j) = lo;
     }
   }
   if (lane == 0) {
@@ -126,17 +121,15 @@ k_ggn_row_prep(const float* __restrict__ x, int64_t R, int64_t D, int64_t ld, fl
     n2 = warp_sum(n2);
     const float inv = 1.0f / sqrtf(n2);
     const float mul = inv * opscale;
-    __half* o = xhat + row * d_pad * nsplit;
+    __half* o = xhat + row * d_pad * (nsplit == 3 ? 2 : 1);  // split operands are stored once as [hi | lo]
     for (int64_t j = 2 * lane; j < d_pad; j += 64) {
       const float v0 = j < D ? xr[j] * mul : 0.f;
       const float v1 = j + 1 < D ? xr[j + 1] * mul : 0.f;
       const __half2 hi = __floats2half2_rn(v0, v1);
       *reinterpret_cast<__half2*>(o + j) = hi;
-      if (nsplit == 3) {  // hi/lo split: A side packs [hi|lo|hi], B side [hi|hi|lo] -> hi.hi + lo.hi + hi.lo
+      if (nsplit == 3) {  // hi/lo split; the GEMM plan forms hi.hi + lo.hi + hi.lo from the two stored segments
         const float2 hf = __half22float2(hi);
-        const __half2 lo = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
-        *reinterpret_cast<__half2*>(o + d_pad + j) = side == 0 ? lo : hi;
-        *reinterpret_cast<__half2*>(o + 2 * d_pad + j) = side == 0 ? hi : lo;
+        *reinterpret_cast<__half2*>(o + d_pad + j) = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
       }
     }
     wr = inv * inv;
@@ -409,12 +402,12 @@ int launch_rows_to_16(const float* in, int64_t R, int64_t d, int64_t ld, int app
 
 int launch_predictive_row_prep(const float* x, int64_t R, int64_t D, int64_t ld, const float* quad,
                                const float* diag_other, float sum_diag_self, float kappa, float s2, int side,
-                               int nsplit, float opscale, __half* packed, int64_t seg_pad, float* out0, float* out1,
-                               cudaStream_t st) {
+                               int nsplit, float opscale, __half* packed, int64_t seg_pad, int64_t out_pitch, float* out0,
+                               float* out1, cudaStream_t st) {
   if (R <= 0) return BVLM_OK;
   if ((nsplit != 1 && nsplit != 3) || seg_pad < D || (seg_pad & 1)) return BVLM_EINVAL;
   k_predictive_row_prep<<<row_grid(R), ROW_BLOCK, 0, st>>>(x, R, D, ld, quad, diag_other, sum_diag_self, kappa, s2, side,
-                                                           nsplit, opscale, packed, seg_pad, out0, out1);
+                                                           nsplit, opscale, packed, seg_pad, out_pitch, out0, out1);
   count_launch();
   BVLM_CUDA_TRY(cudaGetLastError());
   return BVLM_OK;

@@ -13,16 +13,16 @@ int launch_rows_to_16(const float* in, int64_t R, int64_t d, int64_t ld, int app
 
 // Predictive row statistics + operand packing (vlm.py:659-668).
 //   E_r   = |x_r|^2 + quad_r * sum_diag_self
-//   xhat  = x_r / sqrt(E_r) * opscale  -> 16-bit, nsplit in {1,3}: A side packs [hi|lo|hi], B side [hi|hi|lo]
+//   xhat  = x_r / sqrt(E_r) * opscale  -> fp16 [R, seg_pad] (nsplit 1) or [R, 2*seg_pad] = [hi | lo] (nsplit 3)
 //   side 0 (source/image):  out0 = s2 * (sum_d x_d^2 * diag_other_d) / E_r ,  out1 = s2 * quad_r / E_r
 //   side 1 (target/text) :  out0 = quad_r / E_r ,  out1 = (quad_r * kappa + sum_d diag_other_d * x_d^2) / E_r
 int launch_predictive_row_prep(const float* x, int64_t R, int64_t D, int64_t ld, const float* quad,
                                const float* diag_other, float sum_diag_self, float kappa, float s2, int side,
-                               int nsplit, float opscale, __half* packed, int64_t seg_pad, float* out0, float* out1,
-                               cudaStream_t st);
+                               int nsplit, float opscale, __half* packed, int64_t seg_pad, int64_t out_pitch, float* out0,
+                               float* out1, cudaStream_t st);
 
-// GGN row prep (hessians.py:15-21): xhat = x/|x| * opscale -> fp16 [R, nsplit * d_pad] (nsplit 3: hi/lo packing as in
-// launch_predictive_row_prep, side 0 = A operand, 1 = B operand); inv_norm[r] = 1/|x_r|;
+// GGN row prep (hessians.py:15-21): xhat = x/|x| * opscale -> fp16 [R, d_pad] (nsplit 1) or [R, 2*d_pad] = [hi | lo]
+// (nsplit 3; `side` is ignored); inv_norm[r] = 1/|x_r|;
 // w_raw[r] = 1/|x_r|^2 ; *w_sum += sum_r w_raw[r] (atomic).
 int launch_ggn_row_prep(const float* x, int64_t R, int64_t D, int64_t ld, float opscale, int nsplit, int side, __half* xhat,
                         int64_t d_pad, float* inv_norm, float* w_raw, float* w_sum, cudaStream_t st);

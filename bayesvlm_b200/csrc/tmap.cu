@@ -1,5 +1,6 @@
 #include "tmap.cuh"
 
+#include <cstdlib>
 #include <mutex>
 
 namespace bvlm {
@@ -63,6 +64,16 @@ int make_tmap_3d(CUtensorMap* out, const void* base, int dtype, uint64_t d0, uin
                         swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? BVLM_OK : BVLM_EDRIVER;
+}
+
+int64_t operand_pitch(int64_t k_elems) {
+  static int pad = -1;
+  if (pad < 0) {
+    const char* e = getenv("BVLM_PITCH_PAD");
+    pad = e != nullptr ? atoi(e) : 64;
+    if (pad < 0 || (pad % 8) != 0) pad = 64;
+  }
+  return ((k_elems * 2) % 1024 == 0) ? k_elems + pad : k_elems;
 }
 
 int device_sm_count() {

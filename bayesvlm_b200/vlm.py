@@ -314,7 +314,7 @@ class CLIP(torch.nn.Module):
         if d_act + bias != tgt.factor.dA:
             raise ValueError(f"target activations have {d_act}(+{bias}) features but A_inv is {tgt.factor.dA}^2")
         seg = int(lib.bvlm_padded_k(d))
-        t16 = torch.empty((c, seg * prec), dtype=torch.float16, device=emb.device)
+        t16 = torch.empty((c, seg * (2 if prec == _lib.PREC_X3 else 1)), dtype=torch.float16, device=emb.device)
         c_pad = int(lib.bvlm_padded_cols(c))  # the epilogue reads whole 256-column tiles
         col_a = torch.empty(c_pad, dtype=torch.float32, device=emb.device)
         col_b = torch.empty(c_pad, dtype=torch.float32, device=emb.device)

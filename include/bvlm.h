@@ -86,7 +86,7 @@ int bvlm_quadform(const float* act, int64_t n, int64_t d, int64_t ld, int append
  *
  * Target (text/class) side, once per (target set, covariance):
  *   gamma_j = t_act_j^T A_txt_inv t_act_j ; E_j = |t_j|^2 + gamma_j * sum(delta)
- *   T16 [C, prec * d_pad] packed unit-energy embeddings, colA_j = gamma_j / E_j, colB_j = (gamma_j kappa + q_j) / E_j
+ *   T16 [C, (prec == 3 ? 2 : 1) * d_pad] packed unit-energy embeddings ([hi | lo] in the split mode), colA_j = gamma_j / E_j, colB_j = (gamma_j kappa + q_j) / E_j
  *   (colA / colB: bvlm_padded_cols(C) floats each, zero beyond C)
  * with beta = diag(B_img_inv), delta = diag(B_txt_inv), kappa = beta.delta, q_j = sum_d beta_d t_jd^2.
  *
