@@ -4,7 +4,10 @@
 #include <mutex>
 #include <vector>
 
+#include <cstdlib>
+
 #include "epilogues.cuh"
+#include "gemm2_engine.cuh"
 #include "prep.cuh"
 
 namespace bvlm {
@@ -144,6 +147,21 @@ int bvlm_gemm_tn_f32(const void* A16, int64_t M, const void* B16, int64_t N, int
   int rc;
   if ((rc = operand_tmap<GEMM_BM>(&tmA, opA))) return rc;
   if ((rc = operand_tmap<BN>(&tmB, opB))) return rc;
+  static const int engine = [] {
+    const char* e = getenv("BVLM_DIAG_ENGINE");  // 1: one-CTA engine, 2: CTA-pair engine (4 epilogue warps), 3: pairs + 8 warps
+    return e != nullptr ? atoi(e) : 1;
+  }();
+  if (engine >= 2) {
+    if ((rc = operand_tmap<BN / 2>(&tmB, opB))) return rc;
+    GemmPlan plan2 = make_plan2<BN>(static_cast<int>(M), static_cast<int>(N), static_cast<int>(k_pad), SCHED_TILES,
+                                    split_k < 1 ? 1 : split_k, fmt);
+    EpiStoreF32<BN>::Params ep2{D, ldd, alpha, plan2.splits > 1 ? 1 : 0, 0, nullptr, nullptr};
+    if (plan2.splits > 1) {
+      BVLM_CUDA_TRY(cudaMemset2DAsync(D, static_cast<size_t>(ldd) * 4, 0, static_cast<size_t>(N) * 4, static_cast<size_t>(M), st));
+    }
+    if (engine == 2) return launch_gemm2<BN, 6, 4, EpiStoreF32<BN>>(tmA, tmB, plan2, ep2, st, TAG_GEMM_DIAG);
+    return launch_gemm2<BN, 6, 8, EpiStoreF32<BN>>(tmA, tmB, plan2, ep2, st, TAG_GEMM_DIAG);
+  }
   GemmPlan plan = make_plan<BN>(static_cast<int>(M), static_cast<int>(N), static_cast<int>(k_pad), SCHED_TILES,
                                 split_k < 1 ? 1 : split_k, fmt, fmt);
   EpiStoreF32<BN>::Params ep{D, ldd, alpha, plan.splits > 1 ? 1 : 0, 0, nullptr, nullptr};

@@ -123,7 +123,7 @@ struct EpiStoreF32 {
 // ---------------------------------------------------------------------------------------------
 template <int BN>
 struct EpiRowSumSq {
-  static constexpr size_t scratch_bytes(int) { return 16; }
+  static constexpr size_t scratch_bytes(int warps) { return warps == 8 ? 128 * sizeof(float) : 16; }
   struct Params {
     float* out;
     const float* row_scale;  // optional per-row multiplier (undoes the per-row power-of-two operand scaling)
@@ -149,6 +149,14 @@ struct EpiRowSumSq {
   __device__ static void tile_end(State&, const Params&, const EpiCtx&, const TileCoord&) {}
   __device__ static void item_end(State& st, const Params& p, const EpiCtx& ctx, const TileCoord& tc) {
     const int row = epi_row(ctx, tc);
+    if (ctx.n_warps == 8) {  // two warps share a row (one per column half): merge through shared memory
+      const uint32_t slot = ctx.scratch_u32 + 4u * static_cast<uint32_t>(ctx.ew * 32 + ctx.lane);
+      if (ctx.wid >= 4) sts_f32(slot, st.acc);
+      epi_bar_sync(ctx);
+      if (ctx.wid < 4) st.acc += lds_f32(slot);
+      epi_bar_sync(ctx);
+      if (ctx.wid >= 4) return;
+    }
     if (row < ctx.M) {
       float r = st.acc * p.scale;
       if (p.row_scale != nullptr) r *= p.row_scale[row];
@@ -243,14 +251,26 @@ struct EpiPredictive {
 // (Peaked softmaxes make Yh^T diag(p) Yh - (Yh^T p)(Yh^T p)^T cancel catastrophically; the GGN pipeline therefore
 //  centres every row on its pivot target -- see kfac.cu.)
 // ---------------------------------------------------------------------------------------------
+// merge two online-softmax partials (pivot excluded from `rest`); on ties the first (a) stays the pivot
+__device__ __forceinline__ void merge_rowstats(float& m, float& rest, int& piv, float m2, float rest2, int piv2) {
+  if (m2 > m) {
+    rest = rest2 + (rest + 1.f) * fast_exp2(m - m2);
+    m = m2;
+    piv = piv2;
+  } else if (m2 > -INFINITY) {
+    rest = rest + (rest2 + 1.f) * fast_exp2(m2 - m);
+  }
+}
+
 template <int BN>
 struct EpiRowLse {
-  static constexpr size_t scratch_bytes(int) { return 16; }
+  static constexpr size_t scratch_bytes(int warps) { return warps == 8 ? 3 * 128 * sizeof(float) : 16; }
   struct Params {
-    float* rowmax2;  // [B] m   (log2 units)
-    float* rest;     // [B]
-    int* pivot;      // [B]
+    float* rowmax2;  // [B, n_split] m   (log2 units)
+    float* rest;     // [B, n_split]
+    int* pivot;      // [B, n_split]
     float s_log2e;   // exp(logit_scale) * log2(e) / (operand scaling)
+    int n_split;     // row panels are cut into n_split column ranges; k_merge_rowstats combines the partials
   };
   struct State {
     float m, rest;
@@ -298,10 +318,23 @@ struct EpiRowLse {
   __device__ static void tile_end(State&, const Params&, const EpiCtx&, const TileCoord&) {}
   __device__ static void item_end(State& st, const Params& p, const EpiCtx& ctx, const TileCoord& tc) {
     const int row = epi_row(ctx, tc);
+    if (ctx.n_warps == 8) {  // the warp of the upper column half hands its partial to the lower one
+      const uint32_t slot = ctx.scratch_u32 + 12u * static_cast<uint32_t>(ctx.ew * 32 + ctx.lane);
+      if (ctx.wid >= 4) {
+        sts_f32(slot, st.m);
+        sts_f32(slot + 4, st.rest);
+        sts_f32(slot + 8, __int_as_float(st.piv));
+      }
+      epi_bar_sync(ctx);
+      if (ctx.wid < 4) merge_rowstats(st.m, st.rest, st.piv, lds_f32(slot), lds_f32(slot + 4), __float_as_int(lds_f32(slot + 8)));
+      epi_bar_sync(ctx);
+      if (ctx.wid >= 4) return;
+    }
     if (row < ctx.M) {
-      p.rowmax2[row] = st.m;
-      p.rest[row] = st.rest;
-      p.pivot[row] = st.piv;
+      const int64_t o = static_cast<int64_t>(row) * p.n_split + tc.split;
+      p.rowmax2[o] = st.m;
+      p.rest[o] = st.rest;
+      p.pivot[o] = st.piv;
     }
   }
 };
@@ -324,8 +357,9 @@ constexpr float GGN_WDSCALE = 64.f;
 template <int BN, bool SIGLIP>
 struct EpiGgnWeights {
   // per epilogue warp: double-buffered slabs for omega and omega*(d|L); the column-sum exchange reuses the block
-  static constexpr size_t scratch_bytes(int warps) { return warps * 4 * SLAB_BYTES; }
-  static_assert(4 * 4 * SLAB_BYTES >= 4 * BN * sizeof(float), "column-sum exchange needs 4*BN floats");
+  // (4 warps: double-buffered, 16 KB per warp; 8 warps: single-buffered, 8 KB per warp -- 64 KB either way)
+  static constexpr size_t scratch_bytes(int) { return 16 * SLAB_BYTES; }
+  static_assert(16 * SLAB_BYTES >= 4 * BN * sizeof(float), "column-sum exchange needs 4*BN floats");
   struct Params {
     CUtensorMap tm_w, tm_wl;  // [B, Cp] fp16, box {64 cols, 32 rows}, SWIZZLE_128B
     const float* rowmax2;  // InfoNCE only
@@ -390,10 +424,14 @@ struct EpiGgnWeights {
       om[j] = (row_ok && j < n_valid) ? o * GGN_WSCALE : 0.f;  // zeros beyond C: the K padding of pass 3 must be exact
     }
     // ---- stage fp16 omega / omega*(d|L) in the warp's slabs (two 32-column chunks fill one 64-column slab)
-    const uint32_t base = ctx.scratch_u32 + static_cast<uint32_t>(ctx.wid) * (4 * SLAB_BYTES) +
-                          static_cast<uint32_t>(st.buf) * (2 * SLAB_BYTES);
+    const bool dbl = ctx.n_warps == 4;
+    const uint32_t base = ctx.scratch_u32 + static_cast<uint32_t>(ctx.wid) * ((dbl ? 4 : 2) * SLAB_BYTES) +
+                          static_cast<uint32_t>(dbl ? st.buf : 0) * (2 * SLAB_BYTES);
     const int h = c & 1;
-    if (h == 0) slab_wait_free<1>(ctx.lane);  // the bulk group issued two slab pairs ago has finished reading
+    if (h == 0) {  // the bulk group that last read this slab pair has finished (two pairs ago when double-buffered)
+      if (dbl) slab_wait_free<1>(ctx.lane);
+      else slab_wait_free<0>(ctx.lane);
+    }
     if constexpr (!SIGLIP) slab_write_f16_half(base, ctx.lane, h, om);
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] *= om[j];

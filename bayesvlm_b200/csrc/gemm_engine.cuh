@@ -32,7 +32,7 @@ struct GemmPlan {
   int m_tiles;
   int n_tiles;
   int mode;      // SchedMode
-  int splits;    // split-K factor (SCHED_TILES / SCHED_TRI_TILES); number of M ranges a column panel is cut into (SCHED_COL_PANEL)
+  int splits;    // split-K factor (SCHED_TILES / SCHED_TRI_TILES); number of M (N) ranges a column (row) panel is cut into
   int tri_k;     // 1: operand B is lower triangular in (n,k) -> K loop stops at the diagonal block
   uint32_t idesc;
   int a_is_3d;       // 1: operand A is fetched through a 3-D map at (k, 0, m * a_outer_step)
@@ -49,13 +49,14 @@ struct GemmPlan {
 
 struct TileCoord {
   int m, n, kb0, kb1;
+  int split;  // panel split index (row / column panels)
   int row0;  // first accumulator row of this CTA's 128-row slab of the tile (set by the kernel, engine specific)
 };
 
 template <int BN>
 __host__ __device__ inline int plan_num_items(const GemmPlan& p) {
   switch (p.mode) {
-    case SCHED_ROW_PANEL: return p.m_tiles;
+    case SCHED_ROW_PANEL: return p.m_tiles * p.splits;
     case SCHED_COL_PANEL: return p.n_tiles * p.splits;
     case SCHED_TRI_TILES: return (p.m_tiles * (p.m_tiles + 1) / 2) * p.splits;
     default: return p.m_tiles * p.n_tiles * p.splits;
@@ -64,10 +65,16 @@ __host__ __device__ inline int plan_num_items(const GemmPlan& p) {
 __host__ __device__ inline int col_panel_m0(const GemmPlan& p, int split) {
   return static_cast<int>(static_cast<long long>(split) * p.m_tiles / p.splits);
 }
+__host__ __device__ inline int row_panel_n0(const GemmPlan& p, int split) {
+  return static_cast<int>(static_cast<long long>(split) * p.n_tiles / p.splits);
+}
 template <int BN>
 __host__ __device__ inline int plan_inner(const GemmPlan& p, int item) {
   switch (p.mode) {
-    case SCHED_ROW_PANEL: return p.n_tiles;
+    case SCHED_ROW_PANEL: {
+      const int split = item % p.splits;
+      return row_panel_n0(p, split + 1) - row_panel_n0(p, split);
+    }
     case SCHED_COL_PANEL: {
       const int split = item / p.n_tiles;
       return col_panel_m0(p, split + 1) - col_panel_m0(p, split);
@@ -78,21 +85,22 @@ __host__ __device__ inline int plan_inner(const GemmPlan& p, int item) {
 template <int BN>
 __device__ __forceinline__ TileCoord plan_tile(const GemmPlan& p, int item, int inner) {
   TileCoord t;
-  int split = 0;
+  int ksplit = 0, ksplits = 1;  // split-K index / count (tile schedules only)
+  t.split = 0;
   if (p.mode == SCHED_ROW_PANEL) {
-    t.m = item;
-    t.n = inner;
+    // consecutive items share the M tile (its A panel stays hot in L2) and walk different N ranges
+    t.m = item / p.splits;
+    t.split = item % p.splits;
+    t.n = row_panel_n0(p, t.split) + inner;
   } else if (p.mode == SCHED_COL_PANEL) {
     t.n = item % p.n_tiles;
-    t.m = col_panel_m0(p, item / p.n_tiles) + inner;
-    t.kb0 = 0;
-    t.kb1 = p.kb_total;
-    t.row0 = t.m * GEMM_BM;
-    return t;
+    t.split = item / p.n_tiles;
+    t.m = col_panel_m0(p, t.split) + inner;
   } else if (p.mode == SCHED_TRI_TILES) {
     const int tri = p.m_tiles * (p.m_tiles + 1) / 2;
     const int idx = item % tri;
-    split = item / tri;
+    ksplit = item / tri;
+    ksplits = p.splits;
     int m = static_cast<int>((sqrtf(8.0f * static_cast<float>(idx) + 1.0f) - 1.0f) * 0.5f);
     while ((m + 1) * (m + 2) / 2 <= idx) ++m;
     while (m * (m + 1) / 2 > idx) --m;
@@ -101,7 +109,8 @@ __device__ __forceinline__ TileCoord plan_tile(const GemmPlan& p, int item, int 
   } else {
     const int tiles = p.m_tiles * p.n_tiles;
     const int idx = item % tiles;
-    split = item / tiles;
+    ksplit = item / tiles;
+    ksplits = p.splits;
     t.m = idx / p.n_tiles;
     t.n = idx % p.n_tiles;
   }
@@ -110,8 +119,8 @@ __device__ __forceinline__ TileCoord plan_tile(const GemmPlan& p, int item, int 
     const int lim = ((t.n + 1) * BN + GEMM_BK - 1) / GEMM_BK;
     kb_end = lim < kb_end ? lim : kb_end;
   }
-  t.kb0 = static_cast<int>(static_cast<long long>(split) * kb_end / p.splits);
-  t.kb1 = static_cast<int>(static_cast<long long>(split + 1) * kb_end / p.splits);
+  t.kb0 = static_cast<int>(static_cast<long long>(ksplit) * kb_end / ksplits);
+  t.kb1 = static_cast<int>(static_cast<long long>(ksplit + 1) * kb_end / ksplits);
   t.row0 = t.m * GEMM_BM;
   return t;
 }

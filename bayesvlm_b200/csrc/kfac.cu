@@ -21,6 +21,7 @@
 //   pass 4            Hinc = [Yh sqrt(q) | L_A | L_B]^T [Yh sqrt(q) | R_A | R_B]   (K = C + 2B, split-K)
 //   H (+)= s^2 (Hinc + Hinc^T)/2
 #include "epilogues.cuh"
+#include "gemm2_engine.cuh"
 #include "prep.cuh"
 
 using namespace bvlm;
@@ -28,8 +29,9 @@ using namespace bvlm;
 namespace {
 
 constexpr int GGN_BN = 256;
-constexpr int GGN_STAGES = 4;
-constexpr int GGN_W_STAGES = 3;  // the weights pass trades one operand stage for double-buffered output slabs
+constexpr int GGN_STAGES = 6;    // CTA-pair engine: 32 KB per stage
+constexpr int GGN_W_STAGES = 5;  // the weights pass trades one operand stage for 64 KB of output slabs
+constexpr int GGN_ROWSTAT_SPLITS_MAX = 16;
 constexpr int SYRK_BN = 128;
 constexpr int SYRK_STAGES = 6;
 constexpr float GGN_OPSCALE = 256.f;  // unit vectors -> fp16
@@ -79,9 +81,9 @@ GgnLayout ggn_layout(int64_t B, int64_t C, int64_t D, int siglip, int prec, void
   g.w_raw = cv.take<float>(static_cast<size_t>(B));
   g.w = cv.take<float>(static_cast<size_t>(B));
   g.scalars = cv.take<float>(64);
-  g.rowmax2 = cv.take<float>(static_cast<size_t>(B));
-  g.rest = cv.take<float>(static_cast<size_t>(B));
-  g.pivot = cv.take<int>(static_cast<size_t>(B));
+  g.rowmax2 = cv.take<float>(static_cast<size_t>(B) * (GGN_ROWSTAT_SPLITS_MAX + 1));  // per-column-range partials + merged
+  g.rest = cv.take<float>(static_cast<size_t>(B) * (GGN_ROWSTAT_SPLITS_MAX + 1));
+  g.pivot = cv.take<int>(static_cast<size_t>(B) * (GGN_ROWSTAT_SPLITS_MAX + 1));
   g.q = cv.take<float>(static_cast<size_t>(C));
   g.mult_y = cv.take<float>(static_cast<size_t>(C));
   g.mult_x = cv.take<float>(static_cast<size_t>(B));
@@ -124,18 +126,36 @@ int ggn_impl(const float* X, int64_t B, int64_t ldx, const float* Y, int64_t C, 
   Operand16 opX{g.Xh16, B, Kst, FMT_F16};
   Operand16 opY{g.Yh16, C, Kst, FMT_F16};
   auto logit_plan = [&](int mode) {
-    return prec == 3 ? make_split_plan<GGN_BN>(static_cast<int>(B), static_cast<int>(C), static_cast<int>(g.Dp), mode, FMT_F16)
-                     : make_plan<GGN_BN>(static_cast<int>(B), static_cast<int>(C), static_cast<int>(g.Dp), mode, 1, FMT_F16,
-                                         FMT_F16);
+    return prec == 3 ? make_split_plan2<GGN_BN>(static_cast<int>(B), static_cast<int>(C), static_cast<int>(g.Dp), mode, FMT_F16)
+                     : make_plan2<GGN_BN>(static_cast<int>(B), static_cast<int>(C), static_cast<int>(g.Dp), mode, 1, FMT_F16);
   };
   if ((rc = operand_tmap<GEMM_BM>(&tmX, opX))) return rc;
-  if ((rc = operand_tmap<GGN_BN>(&tmY, opY))) return rc;
+  if ((rc = operand_tmap<GGN_BN / 2>(&tmY, opY))) return rc;  // CTA pairs: each CTA loads half of the B tile
 
-  // ---- pass 1 (InfoNCE only): row max, pivot, rest
+  // ---- pass 1 (InfoNCE only): row max, pivot, rest.  Row panels are cut into column ranges so that every CTA pair
+  //      gets an even share; the partial online-softmax states are merged by a tiny kernel.
+  const int pairs = device_sm_count() / 2;
+  float* rowmax2 = g.rowmax2;
+  float* rest = g.rest;
+  int* pivot = g.pivot;
   if (!siglip) {
     GemmPlan p1 = logit_plan(SCHED_ROW_PANEL);
-    EpiRowLse<GGN_BN>::Params e1{g.rowmax2, g.rest, g.pivot, s * kLog2e / op2};
-    if ((rc = launch_gemm<GGN_BN, GGN_STAGES, EpiRowLse<GGN_BN>>(tmX, tmY, p1, e1, st, TAG_GGN_ROWSTATS))) return rc;
+    int S = 1;
+    if (p1.m_tiles < 4 * pairs) {
+      S = (8 * pairs + p1.m_tiles - 1) / p1.m_tiles;
+      if (S > p1.n_tiles) S = p1.n_tiles;
+      if (S > GGN_ROWSTAT_SPLITS_MAX) S = GGN_ROWSTAT_SPLITS_MAX;
+      if (S < 1) S = 1;
+    }
+    p1.splits = S;
+    EpiRowLse<GGN_BN>::Params e1{g.rowmax2, g.rest, g.pivot, s * kLog2e / op2, S};
+    if ((rc = launch_gemm2<GGN_BN, GGN_STAGES, 8, EpiRowLse<GGN_BN>>(tmX, tmY, p1, e1, st, TAG_GGN_ROWSTATS))) return rc;
+    if (S > 1) {
+      if ((rc = launch_merge_rowstats(g.rowmax2, g.rest, g.pivot, B, S, st))) return rc;
+      rowmax2 += static_cast<size_t>(B) * S;
+      rest += static_cast<size_t>(B) * S;
+      pivot += static_cast<size_t>(B) * S;
+    }
   }
 
   // ---- pass 2: curvature weights omega (fp16), omega*(d|L) (fp16), q
@@ -144,15 +164,15 @@ int ggn_impl(const float* X, int64_t B, int64_t ldx, const float* Y, int64_t C, 
   {
     GemmPlan p2 = logit_plan(SCHED_COL_PANEL);
     // cut every column panel into M ranges so that all SMs get an even share; q is then accumulated atomically
-    const int sms = device_sm_count();
     int ps = 1;
-    if (p2.n_tiles < 4 * sms) {
-      ps = (8 * sms + p2.n_tiles - 1) / p2.n_tiles;
+    if (p2.n_tiles < 4 * pairs) {
+      ps = (8 * pairs + p2.n_tiles - 1) / p2.n_tiles;
       if (ps > p2.m_tiles) ps = p2.m_tiles;
       if (ps < 1) ps = 1;
     }
     p2.splits = ps;
-    if (ps > 1) BVLM_CUDA_TRY(cudaMemsetAsync(g.q, 0, static_cast<size_t>(C) * sizeof(float), st));
+    // both CTAs of a pair (and every M range) contribute to the same q columns: always accumulate atomically
+    BVLM_CUDA_TRY(cudaMemsetAsync(g.q, 0, static_cast<size_t>(C) * sizeof(float), st));
     CUtensorMap tmW, tmWL;
     if ((rc = make_tmap_2d(&tmW, W16, TM_F16, static_cast<uint64_t>(g.Cp), static_cast<uint64_t>(B),
                            static_cast<uint64_t>(g.Cp) * 2, 64, 32, 1)))
@@ -162,12 +182,14 @@ int ggn_impl(const float* X, int64_t B, int64_t ldx, const float* Y, int64_t C, 
       return rc;
     if (siglip) {
       EpiGgnWeights<GGN_BN, true>::Params e2{tmW, tmWL, nullptr, nullptr, nullptr, g.w, g.q, s / op2, 1.0f / op2, logit_bias,
-                                             ps > 1 ? 1 : 0};
-      if ((rc = launch_gemm<GGN_BN, GGN_W_STAGES, EpiGgnWeights<GGN_BN, true>>(tmX, tmY, p2, e2, st, TAG_GGN_WEIGHTS))) return rc;
+                                             1};
+      if ((rc = launch_gemm2<GGN_BN, GGN_W_STAGES, 8, EpiGgnWeights<GGN_BN, true>>(tmX, tmY, p2, e2, st, TAG_GGN_WEIGHTS)))
+        return rc;
     } else {
-      EpiGgnWeights<GGN_BN, false>::Params e2{tmW, tmWL, g.rowmax2, g.rest, g.pivot, g.w, g.q, s * kLog2e / op2, 1.0f / op2,
-                                              0.f, ps > 1 ? 1 : 0};
-      if ((rc = launch_gemm<GGN_BN, GGN_W_STAGES, EpiGgnWeights<GGN_BN, false>>(tmX, tmY, p2, e2, st, TAG_GGN_WEIGHTS))) return rc;
+      EpiGgnWeights<GGN_BN, false>::Params e2{tmW, tmWL, rowmax2, rest, pivot, g.w, g.q, s * kLog2e / op2, 1.0f / op2,
+                                              0.f, 1};
+      if ((rc = launch_gemm2<GGN_BN, GGN_W_STAGES, 8, EpiGgnWeights<GGN_BN, false>>(tmX, tmY, p2, e2, st, TAG_GGN_WEIGHTS)))
+        return rc;
     }
   }
 
@@ -183,18 +205,18 @@ int ggn_impl(const float* X, int64_t B, int64_t ldx, const float* Y, int64_t C, 
     Operand16 opW{siglip ? WL16 : W16, siglip ? B : g.Bs + B, g.Cp, FMT_F16};
     Operand16 opYT{g.YhT16, D, g.Cp, FMT_F16};
     if ((rc = operand_tmap<GEMM_BM>(&tmW, opW))) return rc;
-    if ((rc = operand_tmap<GGN_BN>(&tmYT, opYT))) return rc;
-    GemmPlan p3 = make_plan<GGN_BN>(static_cast<int>(opW.rows), static_cast<int>(D), static_cast<int>(g.Cp), SCHED_TILES, 1,
-                                    FMT_F16, FMT_F16);
+    if ((rc = operand_tmap<GGN_BN / 2>(&tmYT, opYT))) return rc;
+    GemmPlan p3 = make_plan2<GGN_BN>(static_cast<int>(opW.rows), static_cast<int>(D), static_cast<int>(g.Cp), SCHED_TILES, 1,
+                                     FMT_F16);
     EpiStoreF32<GGN_BN>::Params e3{g.MR, D, 1.0f, 0, 0, nullptr, nullptr};
-    if ((rc = launch_gemm<GGN_BN, GGN_STAGES, EpiStoreF32<GGN_BN>>(tmW, tmYT, p3, e3, st, TAG_GGN_MOMENTS))) return rc;
+    if ((rc = launch_gemm2<GGN_BN, GGN_STAGES, 4, EpiStoreF32<GGN_BN>>(tmW, tmYT, p3, e3, st, TAG_GGN_MOMENTS))) return rc;
   }
 
   // ---- per-source finalisation and stacked operands of pass 4
   const float unscale_n = 1.0f / (GGN_WSCALE * GGN_OPSCALE);
   const float unscale_r =  // InfoNCE: d is in log2-logit units and stored with GGN_WDSCALE
       siglip ? unscale_n : 1.0f / (GGN_WDSCALE * GGN_OPSCALE * s * kLog2e);
-  if ((rc = launch_ggn_row_finalize(X, B, D, ldx, g.inv_nx, g.w, Y, ldy, g.inv_ny, g.pivot, g.rest, inv_gamma, Nn, Rr, g.RA, D,
+  if ((rc = launch_ggn_row_finalize(X, B, D, ldx, g.inv_nx, g.w, Y, ldy, g.inv_ny, pivot, rest, inv_gamma, Nn, Rr, g.RA, D,
                                     unscale_n, unscale_r, siglip, g.mult_x, st)))
     return rc;
   if ((rc = launch_ggn_col_mult(g.q, g.inv_ny, inv_gamma, C, GGN_G, g.mult_y, st))) return rc;
@@ -221,14 +243,14 @@ int ggn_impl(const float* X, int64_t B, int64_t ldx, const float* Y, int64_t C, 
     Operand16 opL{g.L16, D, K, FMT_F16};
     Operand16 opR{g.R16, D, K, FMT_F16};
     if ((rc = operand_tmap<GEMM_BM>(&tmL, opL))) return rc;
-    if ((rc = operand_tmap<GGN_BN>(&tmR, opR))) return rc;
-    const int tiles = static_cast<int>(ceil_div_i64(D, GEMM_BM) * ceil_div_i64(D, GGN_BN));
-    int splits = device_sm_count() / tiles;
+    if ((rc = operand_tmap<GGN_BN / 2>(&tmR, opR))) return rc;
+    const int tiles = static_cast<int>(ceil_div_i64(D, GEMM2_BM) * ceil_div_i64(D, GGN_BN));
+    int splits = pairs / tiles;
     if (splits < 1) splits = 1;
-    GemmPlan p4 = make_plan<GGN_BN>(static_cast<int>(D), static_cast<int>(D), static_cast<int>(K), SCHED_TILES, splits,
-                                    FMT_F16, FMT_F16);
+    GemmPlan p4 = make_plan2<GGN_BN>(static_cast<int>(D), static_cast<int>(D), static_cast<int>(K), SCHED_TILES, splits,
+                                     FMT_F16);
     EpiStoreF32<GGN_BN>::Params e4{g.Hinc, D, 1.0f, 1, 0, nullptr, nullptr};
-    if ((rc = launch_gemm<GGN_BN, GGN_STAGES, EpiStoreF32<GGN_BN>>(tmL, tmR, p4, e4, st, TAG_GGN_STACKED))) return rc;
+    if ((rc = launch_gemm2<GGN_BN, GGN_STAGES, 4, EpiStoreF32<GGN_BN>>(tmL, tmR, p4, e4, st, TAG_GGN_STACKED))) return rc;
   }
   // ---- H (+)= s^2 wbar gamma / g^2 * (Hinc + Hinc^T)/2
   return launch_sym_add(g.Hinc, D, D, H, ldh, s * s / (GGN_G * GGN_G), g.scalars + 3, accumulate, st);

@@ -261,6 +261,28 @@ k_ggn_row_finalize(const float* __restrict__ x, int64_t B, int64_t D, int64_t ld
   if (lane == 0) mult_x[row] = -2.f * kappa * inv;            // L_B = -2 kappa xh, written by the transposing writer
 }
 
+// combine the per-column-range online-softmax partials of pass 1: [B, S] -> [B] (written to the first B entries)
+__global__ void k_merge_rowstats(float* __restrict__ m, float* __restrict__ rest, int* __restrict__ piv, int64_t B, int S) {
+  const int64_t b = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float mm = m[b * S], rr = rest[b * S];
+  int pp = piv[b * S];
+  for (int s = 1; s < S; ++s) {
+    const float m2 = m[b * S + s], r2 = rest[b * S + s];
+    const int p2 = piv[b * S + s];
+    if (m2 > mm) {
+      rr = r2 + (rr + 1.f) * exp2f(mm - m2);
+      mm = m2;
+      pp = p2;
+    } else if (m2 > -INFINITY) {
+      rr = rr + (r2 + 1.f) * exp2f(m2 - mm);
+    }
+  }
+  m[B * S + b] = mm;  // merged stats live behind the partials (no aliasing with rows other blocks still read)
+  rest[B * S + b] = rr;
+  piv[B * S + b] = pp;
+}
+
 // gamma = max_c q_c (q >= 0): atomicMax on the float bit pattern
 __global__ void k_max_nonneg(const float* __restrict__ q, int64_t n, unsigned int* __restrict__ out_bits) {
   float m = 0.f;
@@ -453,6 +475,14 @@ int launch_ggn_row_finalize(const float* x, int64_t B, int64_t D, int64_t ldx, c
   if (B <= 0) return BVLM_OK;
   k_ggn_row_finalize<<<row_grid(B), ROW_BLOCK, 0, st>>>(x, B, D, ldx, inv_norm, w, y, ldy, inv_norm_y, pivot, rest,
                                                         inv_gamma, Nraw, Rraw, RA, ldm, unscale_n, unscale_r, siglip, mult_x);
+  count_launch();
+  BVLM_CUDA_TRY(cudaGetLastError());
+  return BVLM_OK;
+}
+
+int launch_merge_rowstats(float* m, float* rest, int* piv, int64_t B, int S, cudaStream_t st) {
+  if (B <= 0) return BVLM_OK;
+  k_merge_rowstats<<<static_cast<unsigned>((B + 255) / 256), 256, 0, st>>>(m, rest, piv, B, S);
   count_launch();
   BVLM_CUDA_TRY(cudaGetLastError());
   return BVLM_OK;

@@ -51,6 +51,10 @@ int launch_ggn_row_finalize(const float* x, int64_t B, int64_t D, int64_t ldx, c
                             const float* inv_gamma, float* Nraw, float* Rraw, float* RA, int64_t ldm, float unscale_n,
                             float unscale_r, int siglip, float* mult_x, cudaStream_t st);
 
+// Pass-1 partials [B, S] (row max, rest, pivot per column range) -> merged stats written at offset B*S of each array
+// (the arrays hold B*(S+1) entries).
+int launch_merge_rowstats(float* m, float* rest, int* piv, int64_t B, int S, cudaStream_t st);
+
 // scalars[2] = gamma = max_c q_c (scalars[2] must be zero on entry), then
 // scalars[1] = wbar = scalars[0] * inv_count, scalars[3] = wbar * gamma, scalars[4] = 1/gamma (0 when gamma == 0)
 int launch_ggn_scalars(const float* q, int64_t C, float* scalars, float inv_count, cudaStream_t st);
