@@ -137,6 +137,7 @@ struct EpiEpigJoint {
   }
 
   static constexpr bool ALL_CHUNKS = false;
+  static constexpr bool UNROLL_CHUNKS = true;
   __device__ static void kernel_begin(State&, const Params&, const EpiCtx&) {}
   __device__ static void kernel_end(State&, const Params&, const EpiCtx&) {}
   __device__ static void item_begin(State& st, const Params& p, const EpiCtx& ctx, const TileCoord& tc) {

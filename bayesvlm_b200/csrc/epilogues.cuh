@@ -79,6 +79,7 @@ struct EpiStoreF32 {
     float alpha;
   };
   static constexpr bool ALL_CHUNKS = false;
+  static constexpr bool UNROLL_CHUNKS = true;
   __device__ static void kernel_begin(State&, const Params&, const EpiCtx&) {}
   __device__ static void kernel_end(State&, const Params&, const EpiCtx&) {}
   __device__ static void item_begin(State& st, const Params& p, const EpiCtx&, const TileCoord&) {
@@ -133,6 +134,7 @@ struct EpiRowSumSq {
     float acc;
   };
   static constexpr bool ALL_CHUNKS = false;
+  static constexpr bool UNROLL_CHUNKS = true;
   __device__ static void kernel_begin(State&, const Params&, const EpiCtx&) {}
   __device__ static void kernel_end(State&, const Params&, const EpiCtx&) {}
   __device__ static void item_begin(State& st, const Params&, const EpiCtx&, const TileCoord&) { st.acc = 0.f; }
@@ -190,6 +192,7 @@ struct EpiPredictive {
     float u, v;
   };
   static constexpr bool ALL_CHUNKS = false;
+  static constexpr bool UNROLL_CHUNKS = true;
   __device__ static void kernel_begin(State&, const Params&, const EpiCtx&) {}
   __device__ static void kernel_end(State&, const Params& p, const EpiCtx& ctx) {
     if (p.use_tma && ctx.lane == 0) tma_store_wait_all<0>();
@@ -277,6 +280,7 @@ struct EpiRowLse {
     int piv;
   };
   static constexpr bool ALL_CHUNKS = false;
+  static constexpr bool UNROLL_CHUNKS = true;
   __device__ static void kernel_begin(State&, const Params&, const EpiCtx&) {}
   __device__ static void kernel_end(State&, const Params&, const EpiCtx&) {}
   __device__ static void item_begin(State& st, const Params&, const EpiCtx&, const TileCoord&) {
@@ -356,36 +360,38 @@ constexpr float GGN_WDSCALE = 64.f;
 
 template <int BN, bool SIGLIP>
 struct EpiGgnWeights {
-  // per epilogue warp: double-buffered slabs for omega and omega*(d|L); the column-sum exchange reuses the block
-  // (4 warps: double-buffered, 16 KB per warp; 8 warps: single-buffered, 8 KB per warp -- 64 KB either way)
-  static constexpr size_t scratch_bytes(int) { return 16 * SLAB_BYTES; }
-  static_assert(16 * SLAB_BYTES >= 4 * BN * sizeof(float), "column-sum exchange needs 4*BN floats");
+  // per epilogue warp three rotating output slabs (12 KB), then 4 x BN floats of per-quadrant column sums
+  static constexpr size_t scratch_bytes(int warps) { return warps * 3 * SLAB_BYTES + 4 * BN * sizeof(float); }
   struct Params {
     CUtensorMap tm_w, tm_wl;  // [B, Cp] fp16, box {64 cols, 32 rows}, SWIZZLE_128B
     const float* rowmax2;  // InfoNCE only
     const float* rest;     // InfoNCE only
     const int* pivot;      // InfoNCE only
     const float* w;        // per-source weight (1/|x|^2, normalised)
-    float* q;              // [N]
+    float* q;              // [N], accumulated with red.global.add (zeroed by the host)
     float s_log2e;         // InfoNCE: s*log2e/opscale ; SigLIP: s/opscale
     float l_scale;         // 1/opscale: acc -> cosine
     float bias;            // SigLIP logit bias
-    int q_atomic;          // column panels are split along M: accumulate q with red.global.add
   };
   struct State {
-    float q[BN / 32];
-    float m2, lg1pr, w;
+    float m2, lgw, w;  // lgw = log2(rest) - log2(WSCALE): omega * WSCALE = 2^(d - lgw)
     int piv;
-    int buf;  // slab double-buffer index
+    int sidx;          // running bulk-store index (slab = sidx % 3)
   };
-  static constexpr bool ALL_CHUNKS = true;  // slabs are issued per pair of 32-column chunks
-  __device__ static void kernel_begin(State& st, const Params&, const EpiCtx&) { st.buf = 0; }
+  static constexpr bool ALL_CHUNKS = true;      // slabs are issued per pair of 32-column chunks
+  static constexpr bool UNROLL_CHUNKS = false;  // the body is large: keep one copy
+  __device__ static uint32_t qsum_addr(const EpiCtx& ctx) {
+    return ctx.scratch_u32 + static_cast<uint32_t>(ctx.n_warps) * (3 * SLAB_BYTES);
+  }
+  __device__ static void kernel_begin(State& st, const Params&, const EpiCtx&) { st.sidx = 0; }
   __device__ static void kernel_end(State&, const Params&, const EpiCtx& ctx) {
     if (ctx.lane == 0) tma_store_wait_all<0>();
   }
-  __device__ static void item_begin(State& st, const Params&, const EpiCtx&, const TileCoord&) {
-#pragma unroll
-    for (int i = 0; i < BN / 32; ++i) st.q[i] = 0.f;
+  __device__ static void item_begin(State&, const Params&, const EpiCtx& ctx, const TileCoord&) {
+    // zero this warp's share of the column sums: quadrant ew, the columns of the chunks this warp owns
+    const int per = (BN / 32) / (ctx.n_warps / 4);
+    const uint32_t qs = qsum_addr(ctx) + 4u * static_cast<uint32_t>(ctx.ew * BN + (ctx.wid / 4) * per * 32 + ctx.lane);
+    for (int i = 0; i < per; ++i) sts_f32(qs + 128u * i, 0.f);
   }
   __device__ static void tile_begin(State& st, const Params& p, const EpiCtx& ctx, const TileCoord& tc) {
     const int row = epi_row(ctx, tc);
@@ -394,84 +400,83 @@ struct EpiGgnWeights {
     if constexpr (!SIGLIP) {
       st.m2 = ok ? p.rowmax2[row] : 0.f;
       // omega is stored as the CONDITIONAL distribution over the non-pivot targets, p_c / (1 - p*) in [0,1]: a peaked
-      // row keeps full fp16 precision however small 1 - p* is; the factor rho = rest/(1+rest) is re-applied in fp32
+      // row keeps full fp16 precision however small 1 - p* is; the factor rho = rest/(1+rest) is re-applied in fp32.
+      // Rows beyond B get lgw = +inf, i.e. omega = 0 without any per-element masking.
       const float rs = ok ? p.rest[row] : 0.f;
-      st.lg1pr = rs > 0.f ? log2f(rs) : INFINITY;
-      st.w *= rs / (1.f + rs);
+      st.lgw = rs > 0.f ? log2f(rs) - 12.f : INFINITY;  // GGN_WSCALE = 2^12 folded into the exponent
+      st.w *= rs / (1.f + rs) * (1.0f / GGN_WSCALE);
       st.piv = ok ? p.pivot[row] : -1;
+    } else {
+      st.w *= 1.0f / GGN_WSCALE;
     }
   }
   __device__ static void chunk(State& st, const Params& p, const EpiCtx& ctx, const TileCoord& tc, float (&v)[32], int c) {
-    const int row = epi_row(ctx, tc);
+    static_assert(GGN_WSCALE == 4096.f, "the exponent fold assumes WSCALE = 2^12");
     const int col0 = tc.n * BN + c * 32;
-    const int n_valid = ctx.N - col0;
-    const bool row_ok = row < ctx.M;
     float om[32];
+    // Columns in [C, Cp) receive finite garbage here; the host zeroes that K padding after the pass. Columns >= Cp and
+    // rows >= B are clipped by the tensor maps; q is only written for columns < C.
+    if constexpr (SIGLIP) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      float o;
-      if constexpr (SIGLIP) {
+      for (int j = 0; j < 32; ++j) {
         const float z = fmaf(v[j], p.s_log2e, p.bias);
         const float t = fast_exp2(-fabsf(z) * 1.4426950408889634f);
         const float d = 1.f + t;
-        o = __fdividef(t, d * d);
+        om[j] = __fdividef(t * GGN_WSCALE, d * d);
         v[j] *= p.l_scale;  // cosine
-      } else {
-        const float d = fmaf(v[j], p.s_log2e, -st.m2);  // <= 0, exactly 0 at the pivot
-        o = (col0 + j == st.piv) ? 0.f : fast_exp2(d - st.lg1pr);
-        v[j] = d * (GGN_WDSCALE / GGN_WSCALE);
       }
-      om[j] = (row_ok && j < n_valid) ? o * GGN_WSCALE : 0.f;  // zeros beyond C: the K padding of pass 3 must be exact
+    } else {
+      const int pj = st.piv - col0;  // pivot position inside this chunk (outside [0,32) if elsewhere)
+      const float dsc = GGN_WDSCALE / GGN_WSCALE;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float d = fmaf(v[j], p.s_log2e, -st.m2);  // <= 0, exactly 0 at the pivot
+        const float o = fast_exp2(d - st.lgw);
+        om[j] = (j == pj) ? 0.f : o;
+        v[j] = d * dsc;
+      }
     }
-    // ---- stage fp16 omega / omega*(d|L) in the warp's slabs (two 32-column chunks fill one 64-column slab)
-    const bool dbl = ctx.n_warps == 4;
-    const uint32_t base = ctx.scratch_u32 + static_cast<uint32_t>(ctx.wid) * ((dbl ? 4 : 2) * SLAB_BYTES) +
-                          static_cast<uint32_t>(dbl ? st.buf : 0) * (2 * SLAB_BYTES);
+    // ---- stage fp16 omega / omega*(d|L) in the warp's rotating slabs (two 32-column chunks fill one 64-column slab)
+    const uint32_t wbase = ctx.scratch_u32 + static_cast<uint32_t>(ctx.wid) * (3 * SLAB_BYTES);
     const int h = c & 1;
-    if (h == 0) {  // the bulk group that last read this slab pair has finished (two pairs ago when double-buffered)
-      if (dbl) slab_wait_free<1>(ctx.lane);
-      else slab_wait_free<0>(ctx.lane);
-    }
-    if constexpr (!SIGLIP) slab_write_f16_half(base, ctx.lane, h, om);
+    const int b0 = st.sidx % 3;
+    const int b1 = SIGLIP ? b0 : (st.sidx + 1) % 3;
+    if (h == 0) slab_wait_free<1>(ctx.lane);  // every bulk store but the most recent one has finished reading
+    if constexpr (!SIGLIP) slab_write_f16_half(wbase + static_cast<uint32_t>(b0) * SLAB_BYTES, ctx.lane, h, om);
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] *= om[j];
-    slab_write_f16_half(base + SLAB_BYTES, ctx.lane, h, v);
+    slab_write_f16_half(wbase + static_cast<uint32_t>(b1) * SLAB_BYTES, ctx.lane, h, v);
     if (h == 1) {
       const int row0 = tc.row0 + ctx.ew * 32;
-      if constexpr (!SIGLIP) slab_issue(&p.tm_w, base, ctx.lane, col0 - 32, row0);
-      slab_issue(&p.tm_wl, base + SLAB_BYTES, ctx.lane, col0 - 32, row0);
+      if constexpr (!SIGLIP) {
+        slab_issue(&p.tm_w, wbase + static_cast<uint32_t>(b0) * SLAB_BYTES, ctx.lane, col0 - 32, row0);
+        slab_commit(ctx.lane);
+      }
+      slab_issue(&p.tm_wl, wbase + static_cast<uint32_t>(b1) * SLAB_BYTES, ctx.lane, col0 - 32, row0);
       slab_commit(ctx.lane);
-      st.buf ^= 1;
+      st.sidx += SIGLIP ? 1 : 2;
+      if (st.sidx >= 3) st.sidx -= 3;
     }
-    // ---- weighted column sums
+    // ---- weighted column sums of this 32 x 32 block: butterfly over the rows, accumulated in shared memory
 #pragma unroll
-    for (int j = 0; j < 32; ++j) om[j] *= st.w * (1.0f / GGN_WSCALE);
-    st.q[c] += warp_transpose_reduce32(om, ctx.lane);
+    for (int j = 0; j < 32; ++j) om[j] *= st.w;
+    const float qv = warp_transpose_reduce32(om, ctx.lane);
+    const uint32_t qa = qsum_addr(ctx) + 4u * static_cast<uint32_t>(ctx.ew * BN + c * 32 + ctx.lane);
+    sts_f32(qa, lds_f32(qa) + qv);
   }
   __device__ static void tile_end(State&, const Params&, const EpiCtx&, const TileCoord&) {}
-  __device__ static void item_end(State& st, const Params& p, const EpiCtx& ctx, const TileCoord& tc) {
-    // the slabs double as the exchange buffer: wait until no bulk store reads them any more
-    slab_wait_free<0>(ctx.lane);
-    const uint32_t s = ctx.scratch_u32;
-    epi_bar_sync(ctx);
-    {
-      const int per = (BN / 32) / (ctx.n_warps / 4);  // chunks per warp
-      const int c0 = (ctx.wid / 4) * per;
-#pragma unroll
-      for (int i = 0; i < BN / 32; ++i)
-        if (i >= c0 && i < c0 + per) sts_f32(s + 4u * static_cast<uint32_t>(ctx.ew * BN + i * 32 + ctx.lane), st.q[i]);
-    }
+  __device__ static void item_end(State&, const Params& p, const EpiCtx& ctx, const TileCoord& tc) {
+    const uint32_t s = qsum_addr(ctx);
     epi_bar_sync(ctx);
     for (int i = ctx.wid * 32 + ctx.lane; i < BN; i += ctx.n_warps * 32) {
       const int col = tc.n * BN + i;
       if (col < ctx.N) {
         const float qs = lds_f32(s + 4u * i) + lds_f32(s + 4u * (BN + i)) + lds_f32(s + 4u * (2 * BN + i)) +
                          lds_f32(s + 4u * (3 * BN + i));
-        if (p.q_atomic) red_add_f32(p.q + col, qs);
-        else p.q[col] = qs;
+        red_add_f32(p.q + col, qs);
       }
     }
-    epi_bar_sync(ctx);  // nobody starts writing slabs of the next item before the sums are read
+    epi_bar_sync(ctx);  // nobody zeroes the sums of the next item before they are read
   }
 };
 

@@ -345,13 +345,24 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ctx.ew * 32) << 16) + static_cast<uint32_t>(acc * BN);
         const int n_valid = plan.N - tc.n * BN;
+        if constexpr (Epi::UNROLL_CHUNKS) {
 #pragma unroll
-        for (int c = 0; c < BN / 32; ++c) {
-          if (!Epi::ALL_CHUNKS && c * 32 >= n_valid) break;
-          float v[32];
-          tmem_ld_32x32(taddr + static_cast<uint32_t>(c * 32), v);
-          tmem_ld_wait();
-          Epi::chunk(st, ep, ctx, tc, v, c);
+          for (int c = 0; c < BN / 32; ++c) {
+            if (!Epi::ALL_CHUNKS && c * 32 >= n_valid) break;
+            float v[32];
+            tmem_ld_32x32(taddr + static_cast<uint32_t>(c * 32), v);
+            tmem_ld_wait();
+            Epi::chunk(st, ep, ctx, tc, v, c);
+          }
+        } else {  // one copy of the epilogue body: large functors otherwise thrash the instruction cache
+#pragma unroll 1
+          for (int c = 0; c < BN / 32; ++c) {
+            if (!Epi::ALL_CHUNKS && c * 32 >= n_valid) break;
+            float v[32];
+            tmem_ld_32x32(taddr + static_cast<uint32_t>(c * 32), v);
+            tmem_ld_wait();
+            Epi::chunk(st, ep, ctx, tc, v, c);
+          }
         }
         tc_fence_before();
         mbar_arrive(&tempty_bar[acc]);

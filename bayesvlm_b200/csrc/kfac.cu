@@ -30,7 +30,7 @@ namespace {
 
 constexpr int GGN_BN = 256;
 constexpr int GGN_STAGES = 6;    // CTA-pair engine: 32 KB per stage
-constexpr int GGN_W_STAGES = 5;  // the weights pass trades one operand stage for 64 KB of output slabs
+constexpr int GGN_W_STAGES = 3;  // the weights pass is epilogue bound: 3 operand stages + 96 KB of rotating output slabs
 constexpr int GGN_ROWSTAT_SPLITS_MAX = 16;
 constexpr int SYRK_BN = 128;
 constexpr int SYRK_STAGES = 6;
@@ -181,16 +181,23 @@ int ggn_impl(const float* X, int64_t B, int64_t ldx, const float* Y, int64_t C, 
                            static_cast<uint64_t>(g.Cp) * 2, 64, 32, 1)))
       return rc;
     if (siglip) {
-      EpiGgnWeights<GGN_BN, true>::Params e2{tmW, tmWL, nullptr, nullptr, nullptr, g.w, g.q, s / op2, 1.0f / op2, logit_bias,
-                                             1};
+      EpiGgnWeights<GGN_BN, true>::Params e2{tmW, tmWL, nullptr, nullptr, nullptr, g.w, g.q, s / op2, 1.0f / op2, logit_bias};
       if ((rc = launch_gemm2<GGN_BN, GGN_W_STAGES, 8, EpiGgnWeights<GGN_BN, true>>(tmX, tmY, p2, e2, st, TAG_GGN_WEIGHTS)))
         return rc;
     } else {
       EpiGgnWeights<GGN_BN, false>::Params e2{tmW, tmWL, rowmax2, rest, pivot, g.w, g.q, s * kLog2e / op2, 1.0f / op2,
-                                              0.f, 1};
+                                              0.f};
       if ((rc = launch_gemm2<GGN_BN, GGN_W_STAGES, 8, EpiGgnWeights<GGN_BN, false>>(tmX, tmY, p2, e2, st, TAG_GGN_WEIGHTS)))
         return rc;
     }
+  }
+
+  if (g.Cp != C) {  // the K padding of pass 3 must be exact zeros (pass 2 leaves finite garbage there)
+    if (!siglip)
+      BVLM_CUDA_TRY(cudaMemset2DAsync(W16 + C, static_cast<size_t>(g.Cp) * 2, 0, static_cast<size_t>(g.Cp - C) * 2,
+                                      static_cast<size_t>(B), st));
+    BVLM_CUDA_TRY(cudaMemset2DAsync(WL16 + C, static_cast<size_t>(g.Cp) * 2, 0, static_cast<size_t>(g.Cp - C) * 2,
+                                    static_cast<size_t>(B), st));
   }
 
   // ---- gamma = max_c q_c and the derived scalars
