@@ -280,7 +280,7 @@ struct EpiRowLse {
     int piv;
   };
   static constexpr bool ALL_CHUNKS = false;
-  static constexpr bool UNROLL_CHUNKS = true;
+  static constexpr bool UNROLL_CHUNKS = false;
   __device__ static void kernel_begin(State&, const Params&, const EpiCtx&) {}
   __device__ static void kernel_end(State&, const Params&, const EpiCtx&) {}
   __device__ static void item_begin(State& st, const Params&, const EpiCtx&, const TileCoord&) {
@@ -290,40 +290,43 @@ struct EpiRowLse {
   }
   __device__ static void tile_begin(State&, const Params&, const EpiCtx&, const TileCoord&) {}
   __device__ static void chunk(State& st, const Params& p, const EpiCtx& ctx, const TileCoord& tc, float (&v)[32], int c) {
+    // st.m is kept in RAW accumulator units (the scale s_log2e > 0 is folded into the exp2 argument)
     const int col0 = tc.n * BN + c * 32;
     const int n_valid = ctx.N - col0;
-    float cm = -INFINITY;
-    int ci = 0;
+    if (n_valid < 32) {  // ragged last chunk only
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      v[j] = j < n_valid ? v[j] * p.s_log2e : -INFINITY;
-      if (v[j] > cm) {
-        cm = v[j];
-        ci = j;
-      }
+      for (int j = 0; j < 32; ++j) v[j] = j < n_valid ? v[j] : -INFINITY;
     }
-    const bool is_new = cm > st.m;  // strict: the first maximum stays the pivot on ties
-    const float m_new = is_new ? cm : st.m;
-    if (is_new) {
-      st.rest = (st.rest + 1.f) * fast_exp2(st.m - m_new);  // the old pivot joins the rest (0 on the first chunk)
+    float cm = v[0];
+#pragma unroll
+    for (int j = 1; j < 32; ++j) cm = fmaxf(cm, v[j]);
+    if (cm > st.m) {  // a new row maximum (rare after the first chunks): the old pivot joins the rest, the new one leaves
+      st.rest = (st.rest + 1.f) * fast_exp2((st.m - cm) * p.s_log2e);  // 0 on the first chunk (st.m = -inf)
+      st.m = cm;
+      int ci = 31;
+#pragma unroll
+      for (int j = 30; j >= 0; --j) ci = (v[j] == cm) ? j : ci;  // first maximum stays the pivot on ties
       st.piv = col0 + ci;
-    }
-    float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-    for (int j = 0; j < 32; j += 2) {
-      const float e0 = fast_exp2(v[j] - m_new);
-      const float e1 = fast_exp2(v[j + 1] - m_new);
-      s0 += (is_new && j == ci) ? 0.f : e0;
-      s1 += (is_new && j + 1 == ci) ? 0.f : e1;
+      for (int j = 0; j < 32; ++j) v[j] = (j == ci) ? -INFINITY : v[j];
     }
-    st.rest += s0 + s1;
-    st.m = m_new;
+    const float off = -st.m * p.s_log2e;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      s0 += fast_exp2(fmaf(v[j], p.s_log2e, off));
+      s1 += fast_exp2(fmaf(v[j + 1], p.s_log2e, off));
+      s2 += fast_exp2(fmaf(v[j + 2], p.s_log2e, off));
+      s3 += fast_exp2(fmaf(v[j + 3], p.s_log2e, off));
+    }
+    st.rest += (s0 + s1) + (s2 + s3);
   }
   __device__ static void tile_end(State&, const Params&, const EpiCtx&, const TileCoord&) {}
   __device__ static void item_end(State& st, const Params& p, const EpiCtx& ctx, const TileCoord& tc) {
     const int row = epi_row(ctx, tc);
     if (ctx.n_warps == 8) {  // the warp of the upper column half hands its partial to the lower one
       const uint32_t slot = ctx.scratch_u32 + 12u * static_cast<uint32_t>(ctx.ew * 32 + ctx.lane);
+      st.m *= p.s_log2e;  // raw accumulator units -> log2 units
       if (ctx.wid >= 4) {
         sts_f32(slot, st.m);
         sts_f32(slot + 4, st.rest);
@@ -333,6 +336,8 @@ struct EpiRowLse {
       if (ctx.wid < 4) merge_rowstats(st.m, st.rest, st.piv, lds_f32(slot), lds_f32(slot + 4), __float_as_int(lds_f32(slot + 8)));
       epi_bar_sync(ctx);
       if (ctx.wid >= 4) return;
+    } else {
+      st.m *= p.s_log2e;
     }
     if (row < ctx.M) {
       const int64_t o = static_cast<int64_t>(row) * p.n_split + tc.split;
@@ -364,11 +369,8 @@ struct EpiGgnWeights {
   static constexpr size_t scratch_bytes(int warps) { return warps * 3 * SLAB_BYTES + 4 * BN * sizeof(float); }
   struct Params {
     CUtensorMap tm_w, tm_wl;  // [B, Cp] fp16, box {64 cols, 32 rows}, SWIZZLE_128B
-    const float* rowmax2;  // InfoNCE only
-    const float* rest;     // InfoNCE only
-    const int* pivot;      // InfoNCE only
-    const float* w;        // per-source weight (1/|x|^2, normalised)
-    float* q;              // [N], accumulated with red.global.add (zeroed by the host)
+    const float4* rowinfo;  // [B] per source: {m2, lgw, wq, pivot bits} (InfoNCE) / {0, 0, wq, 0} (SigLIP); see k_ggn_rowinfo
+    float* q;               // [N], accumulated with red.global.add (zeroed by the host)
     float s_log2e;         // InfoNCE: s*log2e/opscale ; SigLIP: s/opscale
     float l_scale;         // 1/opscale: acc -> cosine
     float bias;            // SigLIP logit bias
@@ -377,13 +379,18 @@ struct EpiGgnWeights {
     float m2, lgw, w;  // lgw = log2(rest) - log2(WSCALE): omega * WSCALE = 2^(d - lgw)
     int piv;
     int sidx;          // running bulk-store index (slab = sidx % 3)
+    float4 nxt;        // row info of the NEXT tile, fetched one tile ahead (hides the global-load latency)
+    int nxt_row;
   };
   static constexpr bool ALL_CHUNKS = true;      // slabs are issued per pair of 32-column chunks
   static constexpr bool UNROLL_CHUNKS = false;  // the body is large: keep one copy
   __device__ static uint32_t qsum_addr(const EpiCtx& ctx) {
     return ctx.scratch_u32 + static_cast<uint32_t>(ctx.n_warps) * (3 * SLAB_BYTES);
   }
-  __device__ static void kernel_begin(State& st, const Params&, const EpiCtx&) { st.sidx = 0; }
+  __device__ static void kernel_begin(State& st, const Params&, const EpiCtx&) {
+    st.sidx = 0;
+    st.nxt_row = -1;
+  }
   __device__ static void kernel_end(State&, const Params&, const EpiCtx& ctx) {
     if (ctx.lane == 0) tma_store_wait_all<0>();
   }
@@ -393,21 +400,22 @@ struct EpiGgnWeights {
     const uint32_t qs = qsum_addr(ctx) + 4u * static_cast<uint32_t>(ctx.ew * BN + (ctx.wid / 4) * per * 32 + ctx.lane);
     for (int i = 0; i < per; ++i) sts_f32(qs + 128u * i, 0.f);
   }
+  __device__ static float4 load_info(const Params& p, const EpiCtx& ctx, int row) {
+    // rows beyond B: lgw = +inf (omega = 0 without per-element masking), wq = 0
+    return row < ctx.M ? __ldg(p.rowinfo + row) : make_float4(0.f, INFINITY, 0.f, __int_as_float(-1));
+  }
   __device__ static void tile_begin(State& st, const Params& p, const EpiCtx& ctx, const TileCoord& tc) {
     const int row = epi_row(ctx, tc);
-    const bool ok = row < ctx.M;
-    st.w = ok ? p.w[row] : 0.f;
-    if constexpr (!SIGLIP) {
-      st.m2 = ok ? p.rowmax2[row] : 0.f;
-      // omega is stored as the CONDITIONAL distribution over the non-pivot targets, p_c / (1 - p*) in [0,1]: a peaked
-      // row keeps full fp16 precision however small 1 - p* is; the factor rho = rest/(1+rest) is re-applied in fp32.
-      // Rows beyond B get lgw = +inf, i.e. omega = 0 without any per-element masking.
-      const float rs = ok ? p.rest[row] : 0.f;
-      st.lgw = rs > 0.f ? log2f(rs) - 12.f : INFINITY;  // GGN_WSCALE = 2^12 folded into the exponent
-      st.w *= rs / (1.f + rs) * (1.0f / GGN_WSCALE);
-      st.piv = ok ? p.pivot[row] : -1;
+    const float4 ri = (st.nxt_row == row) ? st.nxt : load_info(p, ctx, row);
+    st.m2 = ri.x;
+    st.lgw = ri.y;
+    st.w = ri.z;
+    st.piv = __float_as_int(ri.w);
+    if (tc.row0_next >= 0) {
+      st.nxt_row = tc.row0_next + ctx.ew * 32 + ctx.lane;
+      st.nxt = load_info(p, ctx, st.nxt_row);
     } else {
-      st.w *= 1.0f / GGN_WSCALE;
+      st.nxt_row = -1;
     }
   }
   __device__ static void chunk(State& st, const Params& p, const EpiCtx& ctx, const TileCoord& tc, float (&v)[32], int c) {
@@ -428,12 +436,15 @@ struct EpiGgnWeights {
     } else {
       const int pj = st.piv - col0;  // pivot position inside this chunk (outside [0,32) if elsewhere)
       const float dsc = GGN_WDSCALE / GGN_WSCALE;
+      const float o_off = -(st.m2 + st.lgw), s_d = p.s_log2e * dsc, d_off = -st.m2 * dsc;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const float d = fmaf(v[j], p.s_log2e, -st.m2);  // <= 0, exactly 0 at the pivot
-        const float o = fast_exp2(d - st.lgw);
-        om[j] = (j == pj) ? 0.f : o;
-        v[j] = d * dsc;
+        om[j] = fast_exp2(fmaf(v[j], p.s_log2e, o_off));  // 2^(d - lgw), d = l - m <= 0 (exactly 0 at the pivot)
+        v[j] = fmaf(v[j], s_d, d_off);                    // d * WDSCALE / WSCALE
+      }
+      if (pj >= 0 && pj < 32) {  // the pivot itself carries no conditional weight
+#pragma unroll
+        for (int j = 0; j < 32; ++j) om[j] = (j == pj) ? 0.f : om[j];
       }
     }
     // ---- stage fp16 omega / omega*(d|L) in the warp's rotating slabs (two 32-column chunks fill one 64-column slab)

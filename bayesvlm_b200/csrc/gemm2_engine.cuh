@@ -227,10 +227,12 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int n_inner = plan_inner<BN>(plan, item);
       TileCoord t0 = plan_tile<BN>(plan, item, 0);
       t0.row0 = t0.m * GEMM2_BM + static_cast<int>(rank) * GEMM_BM;
+      t0.row0_next = -1;
       Epi::item_begin(st, ep, ctx, t0);
       for (int inner = 0; inner < n_inner; ++inner) {
         TileCoord tc = plan_tile<BN>(plan, item, inner);
         tc.row0 = tc.m * GEMM2_BM + static_cast<int>(rank) * GEMM_BM;
+        tc.row0_next = (plan.mode == SCHED_COL_PANEL && inner + 1 < n_inner) ? tc.row0 + GEMM2_BM : -1;
         Epi::tile_begin(st, ep, ctx, tc);
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();

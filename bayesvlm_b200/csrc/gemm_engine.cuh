@@ -51,6 +51,7 @@ struct TileCoord {
   int m, n, kb0, kb1;
   int split;  // panel split index (row / column panels)
   int row0;  // first accumulator row of this CTA's 128-row slab of the tile (set by the kernel, engine specific)
+  int row0_next;  // row0 of the next tile of the same item when it is known to follow (column panels), else -1
 };
 
 template <int BN>
@@ -339,7 +340,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int n_inner = plan_inner<BN>(plan, item);
       Epi::item_begin(st, ep, ctx, plan_tile<BN>(plan, item, 0));
       for (int inner = 0; inner < n_inner; ++inner) {
-        const TileCoord tc = plan_tile<BN>(plan, item, inner);
+        TileCoord tc = plan_tile<BN>(plan, item, inner);
+        tc.row0_next = (plan.mode == SCHED_COL_PANEL && inner + 1 < n_inner) ? tc.row0 + GEMM_BM : -1;
         Epi::tile_begin(st, ep, ctx, tc);
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();

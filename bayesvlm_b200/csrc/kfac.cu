@@ -60,6 +60,7 @@ struct GgnLayout {
   __half *Xh16, *Yh16, *YhT16, *W16, *L16, *R16;
   float *inv_nx, *inv_ny, *w_raw, *w, *scalars, *rowmax2, *rest, *q, *mult_y, *mult_x, *MR, *RA, *Hinc;
   int* pivot;
+  float4* rowinfo;
 };
 
 GgnLayout ggn_layout(int64_t B, int64_t C, int64_t D, int siglip, int prec, void* ws) {
@@ -84,6 +85,7 @@ GgnLayout ggn_layout(int64_t B, int64_t C, int64_t D, int siglip, int prec, void
   g.rowmax2 = cv.take<float>(static_cast<size_t>(B) * (GGN_ROWSTAT_SPLITS_MAX + 1));  // per-column-range partials + merged
   g.rest = cv.take<float>(static_cast<size_t>(B) * (GGN_ROWSTAT_SPLITS_MAX + 1));
   g.pivot = cv.take<int>(static_cast<size_t>(B) * (GGN_ROWSTAT_SPLITS_MAX + 1));
+  g.rowinfo = cv.take<float4>(static_cast<size_t>(B));
   g.q = cv.take<float>(static_cast<size_t>(C));
   g.mult_y = cv.take<float>(static_cast<size_t>(C));
   g.mult_x = cv.take<float>(static_cast<size_t>(B));
@@ -158,6 +160,8 @@ int ggn_impl(const float* X, int64_t B, int64_t ldx, const float* Y, int64_t C, 
     }
   }
 
+  if ((rc = launch_ggn_rowinfo(rowmax2, rest, pivot, g.w, B, siglip, g.rowinfo, st))) return rc;
+
   // ---- pass 2: curvature weights omega (fp16), omega*(d|L) (fp16), q
   __half* W16 = g.W16;
   __half* WL16 = g.W16 + static_cast<size_t>(g.Bs) * g.Cp;
@@ -181,12 +185,11 @@ int ggn_impl(const float* X, int64_t B, int64_t ldx, const float* Y, int64_t C, 
                            static_cast<uint64_t>(g.Cp) * 2, 64, 32, 1)))
       return rc;
     if (siglip) {
-      EpiGgnWeights<GGN_BN, true>::Params e2{tmW, tmWL, nullptr, nullptr, nullptr, g.w, g.q, s / op2, 1.0f / op2, logit_bias};
+      EpiGgnWeights<GGN_BN, true>::Params e2{tmW, tmWL, g.rowinfo, g.q, s / op2, 1.0f / op2, logit_bias};
       if ((rc = launch_gemm2<GGN_BN, GGN_W_STAGES, 8, EpiGgnWeights<GGN_BN, true>>(tmX, tmY, p2, e2, st, TAG_GGN_WEIGHTS)))
         return rc;
     } else {
-      EpiGgnWeights<GGN_BN, false>::Params e2{tmW, tmWL, rowmax2, rest, pivot, g.w, g.q, s * kLog2e / op2, 1.0f / op2,
-                                              0.f};
+      EpiGgnWeights<GGN_BN, false>::Params e2{tmW, tmWL, g.rowinfo, g.q, s * kLog2e / op2, 1.0f / op2, 0.f};
       if ((rc = launch_gemm2<GGN_BN, GGN_W_STAGES, 8, EpiGgnWeights<GGN_BN, false>>(tmX, tmY, p2, e2, st, TAG_GGN_WEIGHTS)))
         return rc;
     }

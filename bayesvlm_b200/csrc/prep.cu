@@ -283,6 +283,22 @@ __global__ void k_merge_rowstats(float* __restrict__ m, float* __restrict__ rest
   piv[B * S + b] = pp;
 }
 
+// per-source constants of pass 2, packed so that the epilogue needs ONE 16-byte load per row and tile:
+//   InfoNCE: {m2, lgw = log2(rest) - 12 (+inf if rest == 0), wq = w * rest/(1+rest) / 4096, pivot}   SigLIP: {0, 0, w/4096, 0}
+__global__ void k_ggn_rowinfo(const float* __restrict__ m2, const float* __restrict__ rest, const int* __restrict__ piv,
+                              const float* __restrict__ w, int64_t B, int siglip, float4* __restrict__ out) {
+  const int64_t b = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float wscale_inv = 1.0f / 4096.f;
+  if (siglip) {
+    out[b] = make_float4(0.f, 0.f, w[b] * wscale_inv, 0.f);
+  } else {
+    const float rs = rest[b];
+    out[b] = make_float4(m2[b], rs > 0.f ? log2f(rs) - 12.f : INFINITY, w[b] * (rs / (1.f + rs)) * wscale_inv,
+                         __int_as_float(piv[b]));
+  }
+}
+
 // gamma = max_c q_c (q >= 0): atomicMax on the float bit pattern
 __global__ void k_max_nonneg(const float* __restrict__ q, int64_t n, unsigned int* __restrict__ out_bits) {
   float m = 0.f;
@@ -483,6 +499,15 @@ int launch_ggn_row_finalize(const float* x, int64_t B, int64_t D, int64_t ldx, c
 int launch_merge_rowstats(float* m, float* rest, int* piv, int64_t B, int S, cudaStream_t st) {
   if (B <= 0) return BVLM_OK;
   k_merge_rowstats<<<static_cast<unsigned>((B + 255) / 256), 256, 0, st>>>(m, rest, piv, B, S);
+  count_launch();
+  BVLM_CUDA_TRY(cudaGetLastError());
+  return BVLM_OK;
+}
+
+int launch_ggn_rowinfo(const float* m2, const float* rest, const int* piv, const float* w, int64_t B, int siglip, float4* out,
+                       cudaStream_t st) {
+  if (B <= 0) return BVLM_OK;
+  k_ggn_rowinfo<<<static_cast<unsigned>((B + 255) / 256), 256, 0, st>>>(m2, rest, piv, w, B, siglip, out);
   count_launch();
   BVLM_CUDA_TRY(cudaGetLastError());
   return BVLM_OK;

@@ -55,6 +55,10 @@ int launch_ggn_row_finalize(const float* x, int64_t B, int64_t D, int64_t ldx, c
 // (the arrays hold B*(S+1) entries).
 int launch_merge_rowstats(float* m, float* rest, int* piv, int64_t B, int S, cudaStream_t st);
 
+// rowinfo[b] = {m2, log2(rest) - 12, w * rho / 4096, pivot} (InfoNCE) or {0, 0, w / 4096, 0} (SigLIP): pass-2 row constants
+int launch_ggn_rowinfo(const float* m2, const float* rest, const int* piv, const float* w, int64_t B, int siglip, float4* out,
+                       cudaStream_t st);
+
 // scalars[2] = gamma = max_c q_c (scalars[2] must be zero on entry), then
 // scalars[1] = wbar = scalars[0] * inv_count, scalars[3] = wbar * gamma, scalars[4] = 1/gamma (0 when gamma == 0)
 int launch_ggn_scalars(const float* q, int64_t C, float* scalars, float inv_count, cudaStream_t st);
