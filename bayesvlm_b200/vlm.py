@@ -302,10 +302,11 @@ class CLIP(torch.nn.Module):
     def _target_side(self, target: EncoderResult, prec: int):
         src, tgt, (sum_beta, sum_delta, kappa) = self._sides()
         emb, act = target.embeds, target.activations
-        key = (self._cov_version, prec, emb.data_ptr(), act.data_ptr(), tuple(emb.shape), tuple(act.shape),
-               emb._version, act._version)
-        if self._target_cache is not None and self._target_cache[0] == key:
-            return self._target_cache[1:]
+        # the cache keeps the target tensors alive and compares identity + version (a data_ptr alone could be recycled)
+        key = (self._cov_version, prec, emb._version, act._version)
+        tc = self._target_cache
+        if tc is not None and tc[0] == key and tc[1] is emb and tc[2] is act:
+            return tc[3:]
         emb = _lib.rowmajor(_lib.require_cuda(emb.detach(), "target embeds"))
         act = _lib.rowmajor(_lib.require_cuda(act.detach(), "target activations"))
         c, d = emb.shape
@@ -325,7 +326,7 @@ class CLIP(torch.nn.Module):
             tgt.factor.dA, tgt.factor.k_pad, tgt.factor.scale, _lib.ptr(src.diag_b), sum_delta, kappa, prec,
             _lib.ptr(t16), _lib.ptr(col_a), _lib.ptr(col_b), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(emb.device))
         _lib.check(rc, "bvlm_predictive_target_prepare")
-        self._target_cache = (key, t16, col_a, col_b)
+        self._target_cache = (key, target.embeds, target.activations, t16, col_a, col_b)
         return t16, col_a, col_b
 
     def _smith_torch(self, source_results: EncoderResult, target_results: EncoderResult):
@@ -363,11 +364,26 @@ class CLIP(torch.nn.Module):
         if needs_grad:
             return self._smith_torch(source_results, target_results)
 
+        emb = _lib.rowmajor(_lib.require_cuda(source_results.embeds.detach(), "source embeds"))
+        act = _lib.rowmajor(_lib.require_cuda(source_results.activations.detach(), "source activations"))
+        n = emb.shape[0]
+        c = target_results.embeds.shape[0]
+        mean = torch.empty((n, c), dtype=torch.float32, device=emb.device)
+        var = torch.empty((n, c), dtype=torch.float32, device=emb.device)
+        probs = torch.empty((n, c), dtype=torch.float32, device=emb.device) if return_probs else None
+        self._smith_into(emb, act, target_results, mean, var, probs)
+        out = ProbabilisticLogits(mean=mean, var=var)
+        if return_probs:
+            return out, probs
+        return out
+
+    def _smith_into(self, emb: torch.Tensor, act: torch.Tensor, target_results: EncoderResult, mean: torch.Tensor,
+                    var: torch.Tensor, probs: Optional[torch.Tensor] = None):
+        """Enqueue the predictive kernels for CUDA `emb` [n, D] / `act` [n, d_in] into preallocated `mean` / `var`
+        ([n, C] fp32 views with unit column stride) on the current stream."""
         prec = _PRECISIONS[self.precision]
         src, tgt, (sum_beta, sum_delta, kappa) = self._sides()
         t16, col_a, col_b = self._target_side(target_results, prec)
-        emb = _lib.rowmajor(_lib.require_cuda(source_results.embeds.detach(), "source embeds"))
-        act = _lib.rowmajor(_lib.require_cuda(source_results.activations.detach(), "source activations"))
         n, d = emb.shape
         c = target_results.embeds.shape[0]
         if target_results.embeds.shape[1] != d:
@@ -376,23 +392,19 @@ class CLIP(torch.nn.Module):
         bias = 1 if self.source_projection_has_bias else 0
         if d_act + bias != src.factor.dA:
             raise ValueError(f"source activations have {d_act}(+{bias}) features but A_inv is {src.factor.dA}^2")
-        mean = torch.empty((n, c), dtype=torch.float32, device=emb.device)
-        var = torch.empty((n, c), dtype=torch.float32, device=emb.device)
-        probs = torch.empty((n, c), dtype=torch.float32, device=emb.device) if return_probs else None
-        if n > 0:
-            ws_bytes = lib.bvlm_predictive_workspace_bytes(n, d, d_act, bias, prec)
-            ws = _lib.workspace(emb.device, ws_bytes)
-            rc = lib.bvlm_predictive(
-                _lib.ptr(emb), n, d, emb.stride(0), _lib.ptr(act), d_act, act.stride(0), bias, _lib.ptr(src.factor.w16),
-                src.factor.dA, src.factor.k_pad, src.factor.scale, _lib.ptr(tgt.diag_b), sum_beta,
-                float(self.logit_scale.detach()), _lib.ptr(t16), _lib.ptr(col_a), _lib.ptr(col_b), c, prec,
-                _lib.ptr(mean), _lib.ptr(var), _lib.ptr(probs), c, _lib.ptr(ws), ws.numel(),
-                _lib.stream_ptr(emb.device))
-            _lib.check(rc, "bvlm_predictive")
-        out = ProbabilisticLogits(mean=mean, var=var)
-        if return_probs:
-            return out, probs
-        return out
+        if n == 0:
+            return
+        if mean.stride(0) != var.stride(0) or (probs is not None and probs.stride(0) != mean.stride(0)):
+            raise ValueError("mean / var / probs must share their row pitch")
+        ws_bytes = lib.bvlm_predictive_workspace_bytes(n, d, d_act, bias, prec)
+        ws = _lib.workspace(emb.device, ws_bytes)
+        rc = lib.bvlm_predictive(
+            _lib.ptr(emb), n, d, emb.stride(0), _lib.ptr(act), d_act, act.stride(0), bias, _lib.ptr(src.factor.w16),
+            src.factor.dA, src.factor.k_pad, src.factor.scale, _lib.ptr(tgt.diag_b), sum_beta,
+            float(self.logit_scale.detach()), _lib.ptr(t16), _lib.ptr(col_a), _lib.ptr(col_b), c, prec,
+            _lib.ptr(mean), _lib.ptr(var), _lib.ptr(probs), mean.stride(0), _lib.ptr(ws), ws.numel(),
+            _lib.stream_ptr(emb.device))
+        _lib.check(rc, "bvlm_predictive")
 
     def forward(self, source_embeds: Union[torch.Tensor, EncoderResult], target_embeds: Union[torch.Tensor, EncoderResult],
                 map_estimate: bool = False):
@@ -407,35 +419,79 @@ class CLIP(torch.nn.Module):
     # ------------------------------------------------------------------------------------------------------------
     @torch.no_grad()
     def predict_host(self, image_outputs: EncoderResult, text_outputs: EncoderResult, batch_size: int = 16384,
-                     return_probs: bool = False, out_pinned: bool = True):
-        """End-to-end predictive for HOST-resident features (the `make_predictions` data flow, precompute.py:18-65):
-        pinned host -> device copies of every image batch, kernels, device -> host copies of mean / var, all inside
-        this call.  Text-side quantities are computed once, not per batch as the reference does (vlm.py:663)."""
+                     return_probs: bool = False, out_pinned: bool = True, out=None):
+        """End-to-end predictive for HOST-resident features (the `make_predictions` data flow, precompute.py:18-65).
+
+        A three-stream pipeline: image batches are copied host -> device on a copy stream into double-buffered staging
+        tensors, the kernels run on a compute stream, and mean / var go device -> host on a third stream, so PCIe in,
+        the tensor cores and PCIe out overlap.  Text-side quantities are computed once, not per batch as the reference
+        does (vlm.py:663).  `out=(mean, var[, probs])` lets a serving loop reuse its own (pinned) host buffers; otherwise
+        fresh host tensors are allocated (pinned when `out_pinned`)."""
         dev = self.device
         if dev.type != "cuda":
             raise RuntimeError("predict_host needs the module on a CUDA device")
-        text_dev = EncoderResult(text_outputs.embeds.to(dev, non_blocking=True),
-                                 text_outputs.activations.to(dev, non_blocking=True))
-        n = len(image_outputs)
-        c = len(text_outputs)
-        mk = dict(dtype=torch.float32, pin_memory=out_pinned)
-        mean = torch.empty((n, c), **mk)
-        var = torch.empty((n, c), **mk)
-        probs = torch.empty((n, c), **mk) if return_probs else None
-        for lo in range(0, n, batch_size):
-            hi = min(n, lo + batch_size)
-            emb = image_outputs.embeds[lo:hi].to(dev, non_blocking=True)
-            act = image_outputs.activations[lo:hi].to(dev, non_blocking=True)
-            res = self._compute_probabilistic_logits_smith(EncoderResult(emb, act, emb), text_dev,
-                                                           return_probs=return_probs)
-            if return_probs:
-                res, pr = res
-                probs[lo:hi].copy_(pr, non_blocking=True)
-            mean[lo:hi].copy_(res.mean, non_blocking=True)
-            var[lo:hi].copy_(res.var, non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()
-        out = ProbabilisticLogits(mean=mean, var=var)
-        return (out, probs) if return_probs else out
+        n, c = len(image_outputs), len(text_outputs)
+        d, d_act = image_outputs.embeds.shape[1], image_outputs.activations.shape[1]
+        if out is not None:
+            mean, var = out[0], out[1]
+            probs = out[2] if return_probs else None
+            if tuple(mean.shape) != (n, c) or tuple(var.shape) != (n, c):
+                raise ValueError("out buffers must be [N, C]")
+        else:
+            mk = dict(dtype=torch.float32, pin_memory=out_pinned)
+            mean, var = torch.empty((n, c), **mk), torch.empty((n, c), **mk)
+            probs = torch.empty((n, c), **mk) if return_probs else None
+        bs = max(1, min(batch_size, n))
+        key = (dev, bs, c, d, d_act, return_probs)
+        pipe = getattr(self, "_host_pipe", None)
+        if pipe is None or pipe["key"] != key:
+            f32 = dict(dtype=torch.float32, device=dev)
+            pipe = {"key": key, "s_in": torch.cuda.Stream(dev), "s_cmp": torch.cuda.Stream(dev), "s_out": torch.cuda.Stream(dev),
+                    "bufs": [dict(emb=torch.empty((bs, d), **f32), act=torch.empty((bs, d_act), **f32),
+                                  mean=torch.empty((bs, c), **f32), var=torch.empty((bs, c), **f32),
+                                  probs=torch.empty((bs, c), **f32) if return_probs else None,
+                                  computed=None, drained=None) for _ in range(2)]}
+            self._host_pipe = pipe
+        s_in, s_cmp, s_out = pipe["s_in"], pipe["s_cmp"], pipe["s_out"]
+        cur = torch.cuda.current_stream(dev)
+        for st_ in (s_in, s_cmp, s_out):
+            st_.wait_stream(cur)
+        with torch.cuda.stream(s_cmp):
+            text_dev = EncoderResult(text_outputs.embeds.to(dev, non_blocking=True),
+                                     text_outputs.activations.to(dev, non_blocking=True))
+        for i, lo in enumerate(range(0, n, bs)):
+            hi = min(n, lo + bs)
+            m = hi - lo
+            b = pipe["bufs"][i % 2]
+            with torch.cuda.stream(s_in):
+                if b["computed"] is not None:
+                    s_in.wait_event(b["computed"])  # the kernels of two batches ago have consumed this staging buffer
+                b["emb"][:m].copy_(image_outputs.embeds[lo:hi], non_blocking=True)
+                b["act"][:m].copy_(image_outputs.activations[lo:hi], non_blocking=True)
+                loaded = torch.cuda.Event()
+                loaded.record(s_in)
+            with torch.cuda.stream(s_cmp):
+                s_cmp.wait_event(loaded)
+                if b["drained"] is not None:
+                    s_cmp.wait_event(b["drained"])  # the previous results in this buffer are on the host
+                self._smith_into(b["emb"][:m], b["act"][:m], text_dev, b["mean"][:m], b["var"][:m],
+                                 b["probs"][:m] if return_probs else None)
+                b["computed"] = torch.cuda.Event()
+                b["computed"].record(s_cmp)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(b["computed"])
+                mean[lo:hi].copy_(b["mean"][:m], non_blocking=True)
+                var[lo:hi].copy_(b["var"][:m], non_blocking=True)
+                if return_probs:
+                    probs[lo:hi].copy_(b["probs"][:m], non_blocking=True)
+                b["drained"] = torch.cuda.Event()
+                b["drained"].record(s_out)
+        s_out.synchronize()
+        cur.wait_stream(s_cmp)
+        for b in pipe["bufs"]:
+            b["computed"] = b["drained"] = None
+        res = ProbabilisticLogits(mean=mean, var=var)
+        return (res, probs) if return_probs else res
 
 
 class SIGLIP(CLIP):

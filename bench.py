@@ -260,20 +260,22 @@ def run_b200(args, rank, world, local_rank):
     # ------------------------------------------------------------------ end to end: host buffers through the public API
     img_host = EncoderResult(t["img_e"].pin_memory(), t["img_a"].pin_memory())
     txt_host = EncoderResult(t["txt_e"].pin_memory(), t["txt_a"].pin_memory())
-    e2e_steps = max(1, min(K, 5))
+    e2e_steps = max(1, min(K, 10))
+    host_out = (torch.empty((cfg["N"], cfg["C"]), pin_memory=True), torch.empty((cfg["N"], cfg["C"]), pin_memory=True))
     for _ in range(2):
-        model.predict_host(img_host, txt_host, batch_size=args.e2e_batch)
+        model.predict_host(img_host, txt_host, batch_size=args.e2e_batch, out=host_out)
     barrier_sync()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        res = model.predict_host(img_host, txt_host, batch_size=args.e2e_batch)
+        res = model.predict_host(img_host, txt_host, batch_size=args.e2e_batch, out=host_out)
     barrier_sync()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) / e2e_steps * 1e3)
     h2d = 4 * (t["img_e"].numel() + t["img_a"].numel() + t["txt_e"].numel() + t["txt_a"].numel())
     d2h = 4 * (res.mean.numel() + res.var.numel())
     e2e = {"value": world * pairs / (e2e_ms * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "ms_per_step": e2e_ms, "api": "CLIP.predict_host (make_predictions data flow): pinned host -> device, kernels, device -> pinned host"}
-    del img_host, txt_host, res, out, img, txt
+           "ms_per_step": e2e_ms, "api": "CLIP.predict_host (make_predictions data flow): pinned host -> device, kernels, device -> pinned host; "
+                  "three-stream pipeline over image batches, caller-owned pinned result buffers"}
+    del img_host, txt_host, res, out, img, txt, host_out
     torch.cuda.empty_cache()
 
     # ------------------------------------------------------------------ KFAC estimation (second headline)
@@ -348,7 +350,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--e2e-batch", type=int, default=12500)
+    ap.add_argument("--e2e-batch", type=int, default=6250)
     ap.add_argument("--kfac-class-batches", type=int, default=2, help="class batches of 32768 per GPU per KFAC step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
