@@ -34,6 +34,8 @@ sys.path.insert(0, str(ROOT))
 LS = math.log(100.0)
 PRED = dict(name="clip-vit-l-14 imagenet-1k-shaped predictive", N=50_000, C=1000, D=768, d_img=1024, d_txt=768,
             lam_img=605.255, lam_txt=220.124, seed=3001)
+EPIG = dict(name="siglip-shaped EPIG scoring: pool x target, Cl=10 classes, K=100 MC samples, chunk 4096", pool=16384,
+            target=10000, Cl=10, K=100, chunk=4096, seed=5001)
 KFAC = dict(name="clip-vit-b-32 kfac (InfoNCE), class batches of 32768", num_classes=32768, batch_size=5, D=512, d_img=768,
             d_txt=512, seed=2001)
 
@@ -313,6 +315,36 @@ def run_b200(args, rank, world, local_rank):
             "kernels": {k: {"launches": v[0], "avg_ms": v[1] / v[0]} for k, v in kk.items()},
             "gpu_launches": kfac_launches}
     assert torch.isfinite(A).all() and torch.isfinite(B).all()
+    del e_img, e_txt, a_img
+    torch.cuda.empty_cache()
+
+    # ------------------------------------------------------------------ EPIG scoring (config 5 shape; pool rows sharded, no collective)
+    from bayesvlm_b200.epig import epig_from_logits_using_matmul
+    from bayesvlm_b200.vlm import ProbabilisticLogits
+
+    ec = EPIG
+    geng = torch.Generator(device=dev).manual_seed(ec["seed"] + rank)
+    mk = lambda n: ProbabilisticLogits(torch.randn(n, ec["Cl"], generator=geng, device=dev) * 2,
+                                       torch.rand(n, ec["Cl"], generator=geng, device=dev) * 3 + 0.1)
+    lp, lt = mk(ec["pool"]), mk(ec["target"])
+    epig_from_logits_using_matmul(lp, lt, seed=0, num_samples=ec["K"], chunk_size=ec["chunk"])
+    barrier_sync()
+    _lib.timing_enable(True)
+    eb, ee = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    eb.record()
+    scores = epig_from_logits_using_matmul(lp, lt, seed=0, num_samples=ec["K"], chunk_size=ec["chunk"])
+    ee.record()
+    barrier_sync()
+    _lib.timing_enable(False)
+    ek = _lib.timing_collect()
+    epig_ms = max_over_ranks(eb.elapsed_time(ee))
+    epairs = float(ec["pool"]) * ec["target"]
+    epig = {"metric": "epig_pool_target_pairs_per_s", "value": world * epairs / (epig_ms * 1e-3), "unit": "pairs/s",
+            "ms": epig_ms, "workload": ec["name"], "pool_rows_per_gpu": ec["pool"], "target_rows": ec["target"],
+            "joint_kernel_ms": ek.get("epig_joint", (0, 0.0))[1],
+            "joint_log_evals_per_s": epairs * ec["Cl"] ** 2 / max(ek.get("epig_joint", (0, 1e-9))[1] * 1e-3, 1e-12)}
+    assert torch.isfinite(scores).all()
+    del lp, lt, scores
     clocks.__exit__()
 
     # ------------------------------------------------------------------ reference algorithm on the host cores (rank 0, N=1)
@@ -339,7 +371,7 @@ def run_b200(args, rank, world, local_rank):
                        "l2": "per-step inputs 359 MB + outputs 400 MB exceed the 126 MB L2 (no flush needed)",
                        "sharding": f"images row-sharded over {world} rank(s), classes replicated, no collective"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches,
-            "clocks": clocks.summary(), "kfac": kfac,
+            "clocks": clocks.summary(), "kfac": kfac, "epig": epig,
         }
         print(json.dumps(line), flush=True)
 

@@ -171,3 +171,23 @@ def test_torch_port_matches_reference_outputs(golden):
     assert np.abs(sc.float().numpy() - golden["epig_scores_f16"]).max() <= 2.0 ** -9
     np.testing.assert_allclose(T.epig_from_probs(t("epig_probs_p"), t("epig_probs_t"), chunk).numpy(),
                                golden["epig_scores_f32"], atol=5e-6)
+
+
+def test_product_prior_precision_matches_reference(golden):
+    """bayesvlm_b200.hessians.optimize_prior_precision (torch, eigenvalue form) against the reference's Adam result."""
+    import torch
+
+    from bayesvlm_b200.hessians import compute_log_det_kfac, optimize_prior_precision
+
+    lam0, n, lr, steps = golden["prior_cfg"]
+    proj = torch.nn.Linear(24, 16, bias=False)
+    with torch.no_grad():
+        proj.weight.copy_(torch.from_numpy(golden["prior_W"]))
+    A, B = torch.from_numpy(golden["prior_A"]), torch.from_numpy(golden["prior_B"])
+    lam = optimize_prior_precision(proj, A, B, lmbda_init=float(lam0), n=float(n), lr=float(lr), num_steps=int(steps),
+                                   device="cpu")
+    assert abs(lam.item() - float(golden["prior_lambda"][0])) <= 2e-3 * float(golden["prior_lambda"][0])
+    # the reference's log-det quirk: p * logdet(A) + q * logdet(B)
+    ld = compute_log_det_kfac(A + torch.eye(24), B + torch.eye(16))
+    ref = torch.logdet(A + torch.eye(24)) * 24 + torch.logdet(B + torch.eye(16)) * 16
+    assert torch.allclose(ld, ref)
