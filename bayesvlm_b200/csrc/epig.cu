@@ -8,6 +8,7 @@
 //   Hjoint += Hc  in fp32                              epig.py:381,393
 // while the [N_p*Cl, N_t*Cl] joint matrix only ever exists tile-by-tile in tensor memory.
 #include "epilogues.cuh"
+#include "gemm2_engine.cuh"
 #include "prep.cuh"
 
 using namespace bvlm;
@@ -98,54 +99,58 @@ k_epig_permute(const __half* __restrict__ in, int64_t N, int64_t K, int64_t Cl, 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// E2 epilogue. Tile rows are (pool row, class) pairs packed ppt = floor(128/Cl) pool rows per tile; tile columns are
-// the flattened (target, class) axis. Row panels: each CTA walks all column tiles of its pool rows.
+// E2 epilogue. Tile rows are (pool row, class) pairs packed ppt = floor(128/Cl) pool rows per 128-row CTA slab; tile
+// columns are the flattened (target, class) axis. Row panels: each CTA pair walks all column tiles of its pool rows.
+// Per element (two at a time in half2 registers where the arithmetic is fp16 anyway):
+//   h = fp16(acc); j = fp16(h / K); l = fp16(log j); t = fp16(j * l)  [= HMUL2, exact product rounded once]; sum += t
 // ---------------------------------------------------------------------------------------------------------------
 template <int BN>
 struct EpiEpigJoint {
-  static constexpr size_t scratch_bytes(int) { return 128 * sizeof(float); }
+  static constexpr size_t scratch_bytes(int warps) { return (warps / 4) * 128 * sizeof(float); }
   struct Params {
     float* Hjoint;      // [Np]
     int64_t Np;
     int Cl;
-    int ppt;            // pool rows per tile
+    int ppt;            // pool rows per 128-row slab
     int tiles_per_chunk;  // col_chunk / BN
-    float K;            // number of MC samples (divisor)
+    float inv_K;        // 1 / number of MC samples
     float Nt;           // number of target points (divisor)
   };
   struct State {
-    float chunk_acc;  // running fp32 sum of fp16(xlogy) over the current column chunk (this thread's row)
-    float hj;         // accumulated joint entropy of the pool row (held by the class-0 thread)
+    float chunk_acc;  // running fp32 sum of fp16(xlogy) over the current column chunk (this thread's row, its column half)
+    float hj;         // accumulated joint entropy of the pool row (held by the class-0 thread of the lower column half)
     bool valid;
     bool leader;
     int64_t p;
     int cur_chunk;
   };
+  static constexpr bool ALL_CHUNKS = false;
+  static constexpr bool UNROLL_CHUNKS = false;
+  __device__ static void kernel_begin(State&, const Params&, const EpiCtx&) {}
+  __device__ static void kernel_end(State&, const Params&, const EpiCtx&) {}
 
   __device__ static void flush(State& st, const Params& p, const EpiCtx& ctx) {
     const int r = ctx.ew * 32 + ctx.lane;
+    const uint32_t s = ctx.scratch_u32;
     epi_bar_sync(ctx);
-    ctx.scratch[r] = st.valid ? st.chunk_acc : 0.f;
+    sts_f32(s + 4u * static_cast<uint32_t>((ctx.wid / 4) * 128 + r), st.valid ? st.chunk_acc : 0.f);
     epi_bar_sync(ctx);
     if (st.leader) {
-      float s = 0.f;
-      for (int c = 0; c < p.Cl; ++c) s += ctx.scratch[r + c];
-      const float neg = -round_f16(s);                 // fp16(sum) then negate
+      float sum = 0.f;
+      for (int h = 0; h < ctx.n_warps / 4; ++h)
+        for (int c = 0; c < p.Cl; ++c) sum += lds_f32(s + 4u * static_cast<uint32_t>(h * 128 + r + c));
+      const float neg = -round_f16(sum);               // fp16(sum) then negate
       st.hj += round_f16(neg / p.Nt);                  // "/ N_t" on a Half tensor
     }
     st.chunk_acc = 0.f;
   }
 
-  static constexpr bool ALL_CHUNKS = false;
-  static constexpr bool UNROLL_CHUNKS = true;
-  __device__ static void kernel_begin(State&, const Params&, const EpiCtx&) {}
-  __device__ static void kernel_end(State&, const Params&, const EpiCtx&) {}
   __device__ static void item_begin(State& st, const Params& p, const EpiCtx& ctx, const TileCoord& tc) {
     const int r = ctx.ew * 32 + ctx.lane;
     const int pl = r / p.Cl;
-    st.p = static_cast<int64_t>(tc.m) * p.ppt + pl;
+    st.p = static_cast<int64_t>(tc.row0 / GEMM_BM) * p.ppt + pl;
     st.valid = (pl < p.ppt) && (st.p < p.Np);
-    st.leader = st.valid && (r - pl * p.Cl == 0);
+    st.leader = st.valid && (r - pl * p.Cl == 0) && ctx.wid < 4;
     st.chunk_acc = 0.f;
     st.hj = 0.f;
     st.cur_chunk = 0;
@@ -157,19 +162,21 @@ struct EpiEpigJoint {
       st.cur_chunk = ch;
     }
   }
-  __device__ static void chunk(State& st, const Params& p, const EpiCtx& ctx, const TileCoord& tc, float (&v)[32], int c) {
-    if (!st.valid) return;
-    const int n_valid = ctx.N - (tc.n * BN + c * 32);
+  __device__ static void chunk(State& st, const Params& p, const EpiCtx&, const TileCoord&, float (&v)[32], int) {
+    // columns beyond N are TMA zero fill: joint = 0 -> 0 * max(log 0, -65504) = -0, no masking needed
+    const __half2 lo_clamp = __floats2half2_rn(-65504.f, -65504.f);
     float s0 = 0.f, s1 = 0.f;
 #pragma unroll
     for (int j = 0; j < 32; j += 2) {
-      // columns beyond N are TMA zero fill: joint = 0 -> xlogy = 0, no masking needed (n_valid kept for clarity)
-      const float j0 = round_f16(round_f16(v[j]) / p.K);
-      const float j1 = round_f16(round_f16(v[j + 1]) / p.K);
-      s0 += xlogx_f16(j0);
-      s1 += xlogx_f16(j1);
+      const float2 h = __half22float2(__floats2half2_rn(v[j], v[j + 1]));            // matmul output rounded to fp16
+      const __half2 jt = __floats2half2_rn(h.x * p.inv_K, h.y * p.inv_K);             // "/ K" on a Half tensor
+      const float2 jf = __half22float2(jt);
+      __half2 lg = __floats2half2_rn(fast_log2(jf.x) * 0.6931471805599453f, fast_log2(jf.y) * 0.6931471805599453f);
+      lg = __hmax2(lg, lo_clamp);                                                     // log 0 = -inf would make 0 * inf
+      const float2 t = __half22float2(__hmul2(jt, lg));                               // fp16(j * fp16(log j))
+      s0 += t.x;
+      s1 += t.y;
     }
-    (void)n_valid;
     st.chunk_acc += s0 + s1;
   }
   __device__ static void tile_end(State&, const Params&, const EpiCtx&, const TileCoord&) {}
@@ -237,17 +244,17 @@ int bvlm_epig_joint_entropy_f16(const void* pool16, int64_t Np, const void* targ
                         GEMM_BK, static_cast<uint32_t>(Cl), static_cast<uint32_t>(ppt), 1);
   if (rc) return rc;
   Operand16 opB{targP, Nt * Cl, Kp, FMT_F16};
-  if ((rc = operand_tmap<EPIG_BN>(&tmB, opB))) return rc;
-  const int m_tiles = static_cast<int>(ceil_div_i64(Np, ppt));
-  GemmPlan plan = make_plan<EPIG_BN>(m_tiles * GEMM_BM, static_cast<int>(Nt * Cl), static_cast<int>(Kp), SCHED_ROW_PANEL,
-                                     1, FMT_F16, FMT_F16);
+  if ((rc = operand_tmap<EPIG_BN / 2>(&tmB, opB))) return rc;  // CTA pairs: each CTA loads half of the B tile
+  const int m_tiles = static_cast<int>(ceil_div_i64(Np, 2 * ppt));  // a CTA pair covers 2 * ppt pool rows
+  GemmPlan plan = make_plan2<EPIG_BN>(m_tiles * GEMM2_BM, static_cast<int>(Nt * Cl), static_cast<int>(Kp), SCHED_ROW_PANEL, 1,
+                                      FMT_F16);
   plan.m_tiles = m_tiles;
   plan.a_is_3d = 1;
   plan.a_outer_step = ppt;
   plan.a_tx_bytes = static_cast<uint32_t>(ppt * Cl * GEMM_BK * 2);
   EpiEpigJoint<EPIG_BN>::Params ep{Hjoint, Np, static_cast<int>(Cl), ppt, static_cast<int>(col_chunk / EPIG_BN),
-                                   static_cast<float>(K), static_cast<float>(Nt)};
-  return launch_gemm<EPIG_BN, EPIG_STAGES, EpiEpigJoint<EPIG_BN>>(tmA, tmB, plan, ep, st, TAG_EPIG_JOINT);
+                                   1.0f / static_cast<float>(K), static_cast<float>(Nt)};
+  return launch_gemm2<EPIG_BN, 6, 8, EpiEpigJoint<EPIG_BN>>(tmA, tmB, plan, ep, st, TAG_EPIG_JOINT);
 }
 
 }  // extern "C"

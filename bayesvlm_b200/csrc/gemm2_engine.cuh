@@ -45,6 +45,15 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorM
       : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d_pair(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int32_t c0,
+                                                 int32_t c1, int32_t c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1),
+        "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
                : "memory");
@@ -160,8 +169,13 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               }
             }
             mbar_wait(&empty_bar[stage], phase ^ 1u);
-            mbar_arrive_expect_tx_leader(&full_bar[stage], A_BYTES + B_BYTES);
-            tma_load_2d_pair(sA + stage * A_BYTES, &tmA, &full_bar[stage], col_a, row_a);
+            mbar_arrive_expect_tx_leader(&full_bar[stage], plan.a_tx_bytes + B_BYTES);
+            if (plan.a_is_3d) {  // a_outer_step outer items per CTA slab (EPIG: pool rows x classes x K)
+              tma_load_3d_pair(sA + stage * A_BYTES, &tmA, &full_bar[stage], col_a, 0,
+                               (tc.m * 2 + static_cast<int>(rank)) * plan.a_outer_step);
+            } else {
+              tma_load_2d_pair(sA + stage * A_BYTES, &tmA, &full_bar[stage], col_a, row_a);
+            }
             tma_load_2d_pair(sB + stage * B_BYTES, &tmB, &full_bar[stage], col_b, row_b);
             if (++stage == STAGES) {
               stage = 0;

@@ -224,7 +224,7 @@ def select_epig_online(label_features: EncoderResult, pool_features: EncoderResu
         picked_embed = pool_sub.embeds[best]
         picked_act = pool_sub.activations[best]
         # reference quirk (epig.py:240): a 1-D activation makes `a @ a.T` the SCALAR |a|^2, broadcast over A_img
-        A_new = picked_act @ picked_act.T
+        A_new = torch.dot(picked_act, picked_act)
         B_new = compute_hessian_analytic_InfoNCE(source_embeds=picked_embed.unsqueeze(0).to(device),
                                                  target_embeds=label_features.embeds.to(device),
                                                  logit_scale=clip.logit_scale.data.to(device))
