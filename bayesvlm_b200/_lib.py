@@ -70,6 +70,7 @@ SIGNATURES = {
     "bvlm_epig_joint_workspace_bytes": (c_size_t, [_I, _I, _I, _I]),
     "bvlm_epig_joint_entropy_f16": (c_int, [_P, _I, _P, _I, _I, _I, _I, _P, _P, c_size_t, _P]),
     "bvlm_gemm_tn_f32": (c_int, [_P, _I, _P, _I, _I, c_int, c_float, _P, _I, c_int, _P]),
+    "bvlm_gemm_mn_f32": (c_int, [_P, _I, _I, _P, _I, _I, _I, c_int, c_float, _P, _I, _P]),
     "bvlm_convert_rows_16": (c_int, [_P, _I, _I, _I, c_int, _P, _I, _P]),
     "bvlm_launch_count": (c_int64, []),
     "bvlm_timing_enable": (c_int, [c_int]),

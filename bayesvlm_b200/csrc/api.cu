@@ -171,4 +171,37 @@ int bvlm_gemm_tn_f32(const void* A16, int64_t M, const void* B16, int64_t N, int
   return launch_gemm<BN, 4, EpiStoreF32<BN>>(tmA, tmB, plan, ep, st, TAG_GEMM_DIAG);
 }
 
+
+/* Diagnostics: D[M,N] = alpha * A^T B with MN-major operands A16 [K, lda] (M valid columns), B16 [K, ldb] (N valid
+ * columns), K a multiple of 64, through the CTA-pair engine. mode bit 0: A is MN-major (else A16 is [M, K] K-major),
+ * bit 1: B is MN-major (else [N, K] K-major). */
+int bvlm_gemm_mn_f32(const void* A16, int64_t M, int64_t lda, const void* B16, int64_t N, int64_t ldb, int64_t K, int mode,
+                     float alpha, float* D, int64_t ldd, void* stream) {
+  if (A16 == nullptr || B16 == nullptr || D == nullptr || M <= 0 || N <= 0 || K <= 0 || (K % 64) != 0) return BVLM_EINVAL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  constexpr int BN = 256;
+  const bool amn = (mode & 1) != 0, bmn = (mode & 2) != 0;
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (amn) rc = operand_tmap_mn(&tmA, A16, K, M, lda, FMT_F16);
+  else {
+    Operand16 op{A16, M, K, FMT_F16, lda};
+    rc = operand_tmap<GEMM_BM>(&tmA, op);
+  }
+  if (rc) return rc;
+  if (bmn) rc = operand_tmap_mn(&tmB, B16, K, N, ldb, FMT_F16);
+  else {
+    Operand16 op{B16, N, K, FMT_F16, ldb};
+    rc = operand_tmap<BN / 2>(&tmB, op);
+  }
+  if (rc) return rc;
+  GemmPlan plan = make_plan2<BN>(static_cast<int>(M), static_cast<int>(N), static_cast<int>(K), SCHED_TILES, 1, FMT_F16);
+  plan.idesc = make_idesc_f16(GEMM2_BM, BN, FMT_F16, FMT_F16, amn, bmn);
+  EpiStoreF32<BN>::Params ep{D, ldd, alpha, 0, 0, nullptr, nullptr};
+  if (amn && bmn) return launch_gemm2<BN, 6, 4, EpiStoreF32<BN>, true, true>(tmA, tmB, plan, ep, st, TAG_GEMM_DIAG);
+  if (amn) return launch_gemm2<BN, 6, 4, EpiStoreF32<BN>, true, false>(tmA, tmB, plan, ep, st, TAG_GEMM_DIAG);
+  if (bmn) return launch_gemm2<BN, 6, 4, EpiStoreF32<BN>, false, true>(tmA, tmB, plan, ep, st, TAG_GEMM_DIAG);
+  return launch_gemm2<BN, 6, 4, EpiStoreF32<BN>>(tmA, tmB, plan, ep, st, TAG_GEMM_DIAG);
+}
+
 }  // extern "C"

@@ -229,11 +229,27 @@ __device__ __forceinline__ uint64_t make_smem_desc_kmajor_sw128(uint32_t smem_ad
   return d;
 }
 
+// MN-major, SWIZZLE_128B tile: the operand's M (or N) index is contiguous in memory. Shared memory holds 64-element
+// (128-byte) wide column blocks of [K rows x 128 bytes]; inside a block 8-row groups are 1024 bytes apart (SBO), blocks
+// are `block_bytes` apart (LBO). Canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units.
+__device__ __forceinline__ uint64_t make_smem_desc_mnmajor_sw128(uint32_t smem_addr, uint32_t block_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);          // start address
+  d |= static_cast<uint64_t>((block_bytes >> 4) & 0x3FFFu) << 16;    // leading byte offset: next 64-wide MN block
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;                       // stride byte offset: next 8 K rows
+  d |= static_cast<uint64_t>(1) << 46;                               // descriptor version (Blackwell)
+  d |= static_cast<uint64_t>(2) << 61;                               // layout type: SWIZZLE_128B
+  return d;
+}
+
 enum OperandFormat : int { FMT_F16 = 0, FMT_BF16 = 1 };
 
 // kind::f16 instruction descriptor: fp32 accumulate, both operands K-major.
-__host__ __device__ inline uint32_t make_idesc_f16(int m, int n, int a_fmt, int b_fmt) {
+__host__ __device__ inline uint32_t make_idesc_f16(int m, int n, int a_fmt, int b_fmt, int a_mn_major = 0,
+                                                   int b_mn_major = 0) {
   uint32_t d = 0;
+  d |= static_cast<uint32_t>(a_mn_major & 1) << 15;  // A major-ness: 0 = K-major, 1 = MN-major
+  d |= static_cast<uint32_t>(b_mn_major & 1) << 16;  // B major-ness
   d |= 1u << 4;                                  // D format: F32
   d |= static_cast<uint32_t>(a_fmt & 7) << 7;    // A format
   d |= static_cast<uint32_t>(b_fmt & 7) << 10;   // B format

@@ -88,7 +88,10 @@ constexpr size_t gemm2_smem_bytes() {
          ((Epi::scratch_bytes(EPI_WARPS) + 1023) / 1024) * 1024;
 }
 
-template <int BN, int STAGES, int EPI_WARPS, class Epi>
+// A_MN / B_MN: the operand is MN-major (its M / N index is contiguous in global memory, i.e. the tensor is stored
+// [K rows, M or N columns] row-major -- a plain row-major activation matrix is the "transposed" operand of X^T X without
+// any transposing pass). Such a tile is fetched as 64-column boxes of [64 K rows x 128 bytes].
+template <int BN, int STAGES, int EPI_WARPS, class Epi, bool A_MN = false, bool B_MN = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * EPI_WARPS, 1)
 gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmPlan plan,
                 const __grid_constant__ typename Epi::Params ep) {
@@ -170,13 +173,23 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
             mbar_wait(&empty_bar[stage], phase ^ 1u);
             mbar_arrive_expect_tx_leader(&full_bar[stage], plan.a_tx_bytes + B_BYTES);
-            if (plan.a_is_3d) {  // a_outer_step outer items per CTA slab (EPIG: pool rows x classes x K)
+            if constexpr (A_MN) {  // [K, M] storage: two 64-column boxes of 64 K rows
+#pragma unroll
+              for (int blk = 0; blk < GEMM_BM / 64; ++blk)
+                tma_load_2d_pair(sA + stage * A_BYTES + blk * (GEMM_BK * 128), &tmA, &full_bar[stage], row_a + blk * 64, col_a);
+            } else if (plan.a_is_3d) {  // a_outer_step outer items per CTA slab (EPIG: pool rows x classes x K)
               tma_load_3d_pair(sA + stage * A_BYTES, &tmA, &full_bar[stage], col_a, 0,
                                (tc.m * 2 + static_cast<int>(rank)) * plan.a_outer_step);
             } else {
               tma_load_2d_pair(sA + stage * A_BYTES, &tmA, &full_bar[stage], col_a, row_a);
             }
-            tma_load_2d_pair(sB + stage * B_BYTES, &tmB, &full_bar[stage], col_b, row_b);
+            if constexpr (B_MN) {
+#pragma unroll
+              for (int blk = 0; blk < (BN / 2) / 64; ++blk)
+                tma_load_2d_pair(sB + stage * B_BYTES + blk * (GEMM_BK * 128), &tmB, &full_bar[stage], row_b + blk * 64, col_b);
+            } else {
+              tma_load_2d_pair(sB + stage * B_BYTES, &tmB, &full_bar[stage], col_b, row_b);
+            }
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1u;
@@ -202,12 +215,16 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
-            const uint64_t da = make_smem_desc_kmajor_sw128(smem_u32(sA + stage * A_BYTES));
-            const uint64_t db = make_smem_desc_kmajor_sw128(smem_u32(sB + stage * B_BYTES));
+            const uint64_t da = A_MN ? make_smem_desc_mnmajor_sw128(smem_u32(sA + stage * A_BYTES), GEMM_BK * 128)
+                                     : make_smem_desc_kmajor_sw128(smem_u32(sA + stage * A_BYTES));
+            const uint64_t db = B_MN ? make_smem_desc_mnmajor_sw128(smem_u32(sB + stage * B_BYTES), GEMM_BK * 128)
+                                     : make_smem_desc_kmajor_sw128(smem_u32(sB + stage * B_BYTES));
+            // one UMMA consumes 16 K elements: 32 bytes along a K-major row, 16 rows (2048 bytes) of an MN-major block
+            constexpr uint64_t STEP_A = A_MN ? (16 * 128) >> 4 : 2, STEP_B = B_MN ? (16 * 128) >> 4 : 2;
 #pragma unroll
             for (int k = 0; k < GEMM_BK / GEMM_UMMA_K; ++k) {
-              umma_f16_ss_pair(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), plan.idesc,
-                               (kb > tc.kb0 || k > 0) ? 1u : 0u);
+              umma_f16_ss_pair(tmem_d, da + STEP_A * static_cast<uint64_t>(k), db + STEP_B * static_cast<uint64_t>(k),
+                               plan.idesc, (kb > tc.kb0 || k > 0) ? 1u : 0u);
             }
             umma_commit_pair(&empty_bar[stage]);
             if (++stage == STAGES) {
@@ -302,6 +319,12 @@ inline GemmPlan make_plan2(int M, int N, int K_padded, int mode, int splits, int
   p.idesc = make_idesc_f16(GEMM2_BM, BN, fmt, fmt);
   return p;
 }
+// tensor map of an MN-major operand stored [k_rows, mn_cols] row-major (pitch in elements), 16-bit
+inline int operand_tmap_mn(CUtensorMap* out, const void* ptr, int64_t k_rows, int64_t mn_cols, int64_t pitch, int fmt) {
+  return make_tmap_2d(out, ptr, fmt == FMT_BF16 ? TM_BF16 : TM_F16, static_cast<uint64_t>(mn_cols),
+                      static_cast<uint64_t>(k_rows), static_cast<uint64_t>(pitch) * 2, 64, GEMM_BK, 1);
+}
+
 template <int BN>
 inline GemmPlan make_split_plan2(int M, int N, int seg, int mode, int fmt) {
   GemmPlan p = make_split_plan<BN>(M, N, seg, mode, fmt);
@@ -311,7 +334,7 @@ inline GemmPlan make_split_plan2(int M, int N, int seg, int mode, int fmt) {
 }
 
 // number of CTA pairs that can be co-resident for this instantiation (queried once)
-template <int BN, int STAGES, int EPI_WARPS, class Epi>
+template <int BN, int STAGES, int EPI_WARPS, class Epi, bool A_MN = false, bool B_MN = false>
 inline int gemm2_max_clusters(size_t smem) {
   static int cached = -1;
   if (cached >= 0) return cached;
@@ -327,7 +350,8 @@ inline int gemm2_max_clusters(size_t smem) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, gemm2_tn_kernel<BN, STAGES, EPI_WARPS, Epi>, &cfg) != cudaSuccess || n <= 0) {
+  if (cudaOccupancyMaxActiveClusters(&n, gemm2_tn_kernel<BN, STAGES, EPI_WARPS, Epi, A_MN, B_MN>, &cfg) != cudaSuccess ||
+      n <= 0) {
     (void)cudaGetLastError();
     n = device_sm_count() / 2;
   }
@@ -335,21 +359,22 @@ inline int gemm2_max_clusters(size_t smem) {
   return n;
 }
 
-// B operand tensor map box rows = BN / 2 (each CTA of the pair loads half of the B tile)
-template <int BN, int STAGES, int EPI_WARPS, class Epi>
+// K-major B operand: tensor map box rows = BN / 2 (each CTA of the pair loads half of the B tile).
+// MN-major operands: tensor map over the [K, M|N] storage with box {64 columns, 64 K rows} (operand_tmap_mn).
+template <int BN, int STAGES, int EPI_WARPS, class Epi, bool A_MN = false, bool B_MN = false>
 inline int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmPlan& plan,
                         const typename Epi::Params& ep, cudaStream_t stream, int tag) {
   if (plan.kb_total <= 0 || plan.M <= 0 || plan.N <= 0) return BVLM_EINVAL;
   constexpr size_t smem = gemm2_smem_bytes<BN, STAGES, EPI_WARPS, Epi>();
   static_assert(smem <= 232448, "shared memory budget exceeded");
-  auto kfn = gemm2_tn_kernel<BN, STAGES, EPI_WARPS, Epi>;
+  auto kfn = gemm2_tn_kernel<BN, STAGES, EPI_WARPS, Epi, A_MN, B_MN>;
   static bool configured = false;  // per instantiation
   if (!configured) {
     BVLM_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     configured = true;
   }
   const int items = plan_num_items<BN>(plan);
-  int clusters = gemm2_max_clusters<BN, STAGES, EPI_WARPS, Epi>(smem);
+  int clusters = gemm2_max_clusters<BN, STAGES, EPI_WARPS, Epi, A_MN, B_MN>(smem);
   if (items < clusters) clusters = items;
   timing_begin(tag, stream);
   kfn<<<2 * clusters, 128 + 32 * EPI_WARPS, smem, stream>>>(tmA, tmB, plan, ep);

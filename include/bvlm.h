@@ -135,6 +135,10 @@ int bvlm_epig_joint_entropy_f16(const void* pool16, int64_t Np, const void* targ
  * --------------------------------------------------------------------------------------------------------- */
 int bvlm_gemm_tn_f32(const void* A16, int64_t M, const void* B16, int64_t N, int64_t k_pad, int fmt, float alpha,
                      float* D, int64_t ldd, int split_k, void* stream);
+/* D[M,N] = alpha * op(A) op(B)^T through the CTA-pair engine with MN-major operands: mode bit 0 -> A16 is [K, lda]
+ * (M valid columns) instead of [M, lda] (K valid columns), bit 1 -> the same for B16. fp16, K a multiple of 64. */
+int bvlm_gemm_mn_f32(const void* A16, int64_t M, int64_t lda, const void* B16, int64_t N, int64_t ldb, int64_t K, int mode,
+                     float alpha, float* D, int64_t ldd, void* stream);
 int bvlm_convert_rows_16(const float* in, int64_t R, int64_t d, int64_t ld, int fmt, void* out, int64_t k_pad,
                          void* stream);
 /* number of kernel launches issued through this library since load (for bench.py's gpu_launches claim). */

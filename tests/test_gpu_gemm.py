@@ -59,3 +59,34 @@ def test_gemm_identity_layout():
     B = torch.arange(300 * K, device="cuda", dtype=torch.float32).reshape(300, K) % 1024
     D, ref = _gemm(A, B, 0)
     assert torch.equal(D.double(), ref)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+@pytest.mark.parametrize("shape", [(256, 256, 64), (300, 520, 192), (1000, 512, 1024), (77, 40, 128), (512, 512, 4096)])
+def test_gemm_pair_engine_mn_major(shape, mode):
+    """CTA-pair engine with MN-major operands (stored [K, M] / [K, N]): no transposing pass for X^T X shaped products."""
+    from bayesvlm_b200 import _lib
+    from bayesvlm_b200._lib import lib
+
+    M, N, K = shape
+    g = torch.Generator(device="cuda").manual_seed(M + 3 * N + mode)
+    A = torch.randn(M, K, device="cuda", generator=g).half()
+    B = torch.randn(N, K, device="cuda", generator=g).half()
+    pad8 = lambda n: (n + 7) // 8 * 8
+    if mode & 1:
+        A_st = torch.zeros(K, pad8(M), device="cuda", dtype=torch.float16)
+        A_st[:, :M] = A.T
+    else:
+        A_st = A.contiguous()
+    if mode & 2:
+        B_st = torch.zeros(K, pad8(N), device="cuda", dtype=torch.float16)
+        B_st[:, :N] = B.T
+    else:
+        B_st = B.contiguous()
+    D = torch.full((M, N), float("nan"), device="cuda")
+    _lib.check(lib.bvlm_gemm_mn_f32(_lib.ptr(A_st), M, A_st.stride(0), _lib.ptr(B_st), N, B_st.stride(0), K, mode, 1.0,
+                                    _lib.ptr(D), D.stride(0), _lib.stream_ptr(D.device)), "gemm_mn")
+    torch.cuda.synchronize()
+    ref = A.double() @ B.double().T
+    assert torch.isfinite(D).all()
+    assert (D.double() - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
