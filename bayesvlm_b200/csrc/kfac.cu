@@ -55,10 +55,12 @@ struct Carver {
 };
 
 struct GgnLayout {
-  int64_t Dp, Cp, Bp, Bs, Ktot;
+  int64_t Dp, Cp, Bp, Bs, Ktot, Kst;
   size_t bytes;
-  __half *Xh16, *Yh16, *YhT16, *W16, *L16, *R16;
-  float *inv_nx, *inv_ny, *w_raw, *w, *scalars, *rowmax2, *rest, *q, *mult_y, *mult_x, *MR, *RA, *Hinc;
+  // Yh16 doubles as the unscaled (B) side of pass 4: [Ktot rows, Kst] = [yh (C rows) | R_A (B rows) | R_B (B rows)], of which
+  // the tensor map of pass 4 reads the first Dp columns.  L16 [Ktot, Dp] is the scaled (A) side [q yh | L_A | L_B].
+  __half *Xh16, *Yh16, *W16, *L16;
+  float *inv_nx, *inv_ny, *w_raw, *w, *scalars, *rowmax2, *rest, *q, *MR, *Hinc;
   int* pivot;
   float4* rowinfo;
 };
@@ -70,13 +72,12 @@ GgnLayout ggn_layout(int64_t B, int64_t C, int64_t D, int siglip, int prec, void
   g.Bp = pad64(B);
   g.Bs = pad128(B);
   g.Ktot = g.Cp + (siglip ? 1 : 2) * g.Bp;
+  g.Kst = g.Dp * (prec == 3 ? 2 : 1);  // stored operand width: [hi | lo] for the split-precision logits
   Carver cv(ws);
-  g.Xh16 = cv.take<__half>(static_cast<size_t>(B) * g.Dp * (prec == 3 ? 2 : 1));
-  g.Yh16 = cv.take<__half>(static_cast<size_t>(C) * g.Dp * (prec == 3 ? 2 : 1));
-  g.YhT16 = cv.take<__half>(static_cast<size_t>(D) * g.Cp);
+  g.Xh16 = cv.take<__half>(static_cast<size_t>(B) * g.Kst);
+  g.Yh16 = cv.take<__half>(static_cast<size_t>(g.Ktot) * g.Kst);
   g.W16 = cv.take<__half>(static_cast<size_t>(2 * g.Bs) * g.Cp);  // [omega ; omega*d] stacked (SigLIP uses the 2nd half)
-  g.L16 = cv.take<__half>(static_cast<size_t>(D) * g.Ktot);
-  g.R16 = cv.take<__half>(static_cast<size_t>(D) * g.Ktot);
+  g.L16 = cv.take<__half>(static_cast<size_t>(g.Ktot) * g.Dp);
   g.inv_nx = cv.take<float>(static_cast<size_t>(B));
   g.inv_ny = cv.take<float>(static_cast<size_t>(C));
   g.w_raw = cv.take<float>(static_cast<size_t>(B));
@@ -87,10 +88,7 @@ GgnLayout ggn_layout(int64_t B, int64_t C, int64_t D, int siglip, int prec, void
   g.pivot = cv.take<int>(static_cast<size_t>(B) * (GGN_ROWSTAT_SPLITS_MAX + 1));
   g.rowinfo = cv.take<float4>(static_cast<size_t>(B));
   g.q = cv.take<float>(static_cast<size_t>(C));
-  g.mult_y = cv.take<float>(static_cast<size_t>(C));
-  g.mult_x = cv.take<float>(static_cast<size_t>(B));
   g.MR = cv.take<float>(static_cast<size_t>(2 * g.Bs) * D);
-  g.RA = cv.take<float>(static_cast<size_t>(B) * D);
   g.Hinc = cv.take<float>(static_cast<size_t>(D) * D);
   g.bytes = cv.used() + 256;
   return g;
@@ -119,12 +117,10 @@ int ggn_impl(const float* X, int64_t B, int64_t ldx, const float* Y, int64_t C, 
   if ((rc = launch_ggn_row_prep(X, B, D, ldx, GGN_OPSCALE, prec, 0, g.Xh16, g.Dp, g.inv_nx, g.w_raw, w_sum, st))) return rc;
   if ((rc = launch_ggn_row_prep(Y, C, D, ldy, GGN_OPSCALE, prec, 1, g.Yh16, g.Dp, g.inv_ny, nullptr, nullptr, st))) return rc;
   if ((rc = launch_normalize_weights(g.w_raw, w_sum, B, g.w, st))) return rc;
-  if ((rc = launch_transpose_to_16(Y, C, D, ldy, g.inv_ny, 0, nullptr, GGN_OPSCALE, 0, FMT_F16, g.YhT16, g.Cp, 0, g.Cp, st)))
-    return rc;
 
   CUtensorMap tmX, tmY;
   // logit GEMM: X1 = one fp16 pass; X3 = hi.hi + lo.hi + hi.lo over operands stored as [hi | lo]
-  const int64_t Kst = g.Dp * (prec == 3 ? 2 : 1);
+  const int64_t Kst = g.Kst;
   Operand16 opX{g.Xh16, B, Kst, FMT_F16};
   Operand16 opY{g.Yh16, C, Kst, FMT_F16};
   auto logit_plan = [&](int mode) {
@@ -207,60 +203,65 @@ int ggn_impl(const float* X, int64_t B, int64_t ldx, const float* Y, int64_t C, 
   if ((rc = launch_ggn_scalars(g.q, C, g.scalars, 1.0f / static_cast<float>(B), st))) return rc;
   const float* inv_gamma = g.scalars + 4;
 
-  // ---- pass 3: InfoNCE [n ; r] = [omega ; omega*d] Yh (M = Bs + B stacked rows) | SigLIP r = (omega*L) Yh ; K = C
+  // ---- pass 3: InfoNCE [n ; r] = [omega ; omega*d] Yh (M = Bs + B stacked rows) | SigLIP r = (omega*L) Yh ; K = C.
+  //      The B operand is Yh16 itself ([C, Dp] row-major = MN-major): no transposed copy of the targets.
   float* Nn = g.MR;
   float* Rr = siglip ? g.MR : g.MR + static_cast<size_t>(g.Bs) * D;
   {
-    CUtensorMap tmW, tmYT;
+    CUtensorMap tmW, tmYmn;
     Operand16 opW{siglip ? WL16 : W16, siglip ? B : g.Bs + B, g.Cp, FMT_F16};
-    Operand16 opYT{g.YhT16, D, g.Cp, FMT_F16};
     if ((rc = operand_tmap<GEMM_BM>(&tmW, opW))) return rc;
-    if ((rc = operand_tmap<GGN_BN / 2>(&tmYT, opYT))) return rc;
+    if ((rc = operand_tmap_mn(&tmYmn, g.Yh16, C, g.Dp, Kst, FMT_F16))) return rc;  // hi segment; K rows beyond C read as zero
     GemmPlan p3 = make_plan2<GGN_BN>(static_cast<int>(opW.rows), static_cast<int>(D), static_cast<int>(g.Cp), SCHED_TILES, 1,
                                      FMT_F16);
+    p3.idesc = make_idesc_f16(GEMM2_BM, GGN_BN, FMT_F16, FMT_F16, 0, 1);
     EpiStoreF32<GGN_BN>::Params e3{g.MR, D, 1.0f, 0, 0, nullptr, nullptr};
-    if ((rc = launch_gemm2<GGN_BN, GGN_STAGES, 4, EpiStoreF32<GGN_BN>>(tmW, tmYT, p3, e3, st, TAG_GGN_MOMENTS))) return rc;
+    if ((rc = launch_gemm2<GGN_BN, GGN_STAGES, 4, EpiStoreF32<GGN_BN>, false, true>(tmW, tmYmn, p3, e3, st, TAG_GGN_MOMENTS)))
+      return rc;
   }
 
-  // ---- per-source finalisation and stacked operands of pass 4
+  // ---- stacked MN-major operands of pass 4 (row-major [K, Dp] fp16, written directly -- no transposes):
+  //        scaled side   L16  = [ (q/gamma) yh * g^2/opscale | L_A | L_B ]
+  //        unscaled side Yh16 = [ yh * opscale               | R_A | R_B ]      (first Dp columns of the Kst-wide rows)
   const float unscale_n = 1.0f / (GGN_WSCALE * GGN_OPSCALE);
   const float unscale_r =  // InfoNCE: d is in log2-logit units and stored with GGN_WDSCALE
       siglip ? unscale_n : 1.0f / (GGN_WDSCALE * GGN_OPSCALE * s * kLog2e);
-  if ((rc = launch_ggn_row_finalize(X, B, D, ldx, g.inv_nx, g.w, Y, ldy, g.inv_ny, pivot, rest, inv_gamma, Nn, Rr, g.RA, D,
-                                    unscale_n, unscale_r, siglip, g.mult_x, st)))
-    return rc;
-  if ((rc = launch_ggn_col_mult(g.q, g.inv_ny, inv_gamma, C, GGN_G, g.mult_y, st))) return rc;
-
-  const int64_t K = g.Ktot;
-  int64_t off = 0;
-  // seg 0: Yh^T diag(q) Yh
-  if ((rc = launch_transpose_to_16(Y, C, D, ldy, g.mult_y, 0, nullptr, 1.f, 0, FMT_F16, g.L16, K, off, g.Cp, st))) return rc;
-  if ((rc = launch_transpose_to_16(Y, C, D, ldy, g.mult_y, 0, nullptr, 1.f, 0, FMT_F16, g.R16, K, off, g.Cp, st))) return rc;
-  off += g.Cp;
-  if (!siglip) {  // seg A: L_A^T R_A
-    if ((rc = launch_transpose_to_16(Nn, B, D, D, nullptr, 0, nullptr, GGN_G, 0, FMT_F16, g.L16, K, off, g.Bp, st))) return rc;
-    if ((rc = launch_transpose_to_16(g.RA, B, D, D, nullptr, 0, nullptr, GGN_G, 0, FMT_F16, g.R16, K, off, g.Bp, st))) return rc;
-    off += g.Bp;
+  __half* R16 = g.Yh16;
+  const int64_t rowA = g.Cp, rowB = siglip ? g.Cp : g.Cp + g.Bp;
+  auto zero_rows = [&](__half* base, int64_t pitch, int64_t r0, int64_t r1) -> int {
+    if (r1 > r0) BVLM_CUDA_TRY(cudaMemsetAsync(base + r0 * pitch, 0, static_cast<size_t>(r1 - r0) * pitch * 2, st));
+    return BVLM_OK;
+  };
+  if ((rc = zero_rows(g.L16, g.Dp, C, g.Cp))) return rc;
+  if ((rc = zero_rows(R16, Kst, C, g.Cp))) return rc;
+  if (!siglip) {
+    if ((rc = zero_rows(g.L16, g.Dp, rowA + B, rowA + g.Bp))) return rc;
+    if ((rc = zero_rows(R16, Kst, rowA + B, rowA + g.Bp))) return rc;
   }
-  // seg B: (-2 sqrt(w) xh)^T (sqrt(w) (u - a/2 xh))
-  if ((rc = launch_transpose_to_16(X, B, D, ldx, g.mult_x, 0, nullptr, GGN_G, 0, FMT_F16, g.L16, K, off, g.Bp, st))) return rc;
-  if ((rc = launch_transpose_to_16(Rr, B, D, D, nullptr, 0, nullptr, GGN_G, 0, FMT_F16, g.R16, K, off, g.Bp, st))) return rc;
-  off += g.Bp;
+  if ((rc = zero_rows(g.L16, g.Dp, rowB + B, rowB + g.Bp))) return rc;
+  if ((rc = zero_rows(R16, Kst, rowB + B, rowB + g.Bp))) return rc;
+  if ((rc = launch_ggn_scale_targets(Y, C, D, g.Dp, ldy, g.inv_ny, g.q, inv_gamma, GGN_G * GGN_G / GGN_OPSCALE, g.L16, g.Dp, st)))
+    return rc;
+  if ((rc = launch_ggn_row_finalize(X, B, D, g.Dp, ldx, g.inv_nx, g.w, Y, ldy, g.inv_ny, pivot, rest, inv_gamma, Nn, Rr, D,
+                                    unscale_n, unscale_r, siglip, GGN_G, g.L16 + rowA * g.Dp, R16 + rowA * Kst,
+                                    g.L16 + rowB * g.Dp, R16 + rowB * Kst, g.Dp, Kst, st)))
+    return rc;
 
-  // ---- pass 4: stacked GEMM, split along K, accumulated into Hinc with red.global.add
+  // ---- pass 4: Hinc = L16^T R16 (both MN-major), split along K, accumulated with red.global.add
   {
+    const int64_t K = g.Ktot;
     CUtensorMap tmL, tmR;
-    Operand16 opL{g.L16, D, K, FMT_F16};
-    Operand16 opR{g.R16, D, K, FMT_F16};
-    if ((rc = operand_tmap<GEMM_BM>(&tmL, opL))) return rc;
-    if ((rc = operand_tmap<GGN_BN / 2>(&tmR, opR))) return rc;
+    if ((rc = operand_tmap_mn(&tmL, g.L16, K, g.Dp, g.Dp, FMT_F16))) return rc;
+    if ((rc = operand_tmap_mn(&tmR, R16, K, g.Dp, Kst, FMT_F16))) return rc;
     const int tiles = static_cast<int>(ceil_div_i64(D, GEMM2_BM) * ceil_div_i64(D, GGN_BN));
     int splits = pairs / tiles;
     if (splits < 1) splits = 1;
     GemmPlan p4 = make_plan2<GGN_BN>(static_cast<int>(D), static_cast<int>(D), static_cast<int>(K), SCHED_TILES, splits,
                                      FMT_F16);
+    p4.idesc = make_idesc_f16(GEMM2_BM, GGN_BN, FMT_F16, FMT_F16, 1, 1);
     EpiStoreF32<GGN_BN>::Params e4{g.Hinc, D, 1.0f, 1, 0, nullptr, nullptr};
-    if ((rc = launch_gemm2<GGN_BN, GGN_STAGES, 4, EpiStoreF32<GGN_BN>>(tmL, tmR, p4, e4, st, TAG_GGN_STACKED))) return rc;
+    if ((rc = launch_gemm2<GGN_BN, GGN_STAGES, 4, EpiStoreF32<GGN_BN>, true, true>(tmL, tmR, p4, e4, st, TAG_GGN_STACKED)))
+      return rc;
   }
   // ---- H (+)= s^2 wbar gamma / g^2 * (Hinc + Hinc^T)/2
   return launch_sym_add(g.Hinc, D, D, H, ldh, s * s / (GGN_G * GGN_G), g.scalars + 3, accumulate, st);

@@ -200,65 +200,112 @@ k_transpose_to_16(const float* __restrict__ src, int64_t R, int64_t d, int64_t l
 }
 
 // ------------------------------------------------------------------------------------------------
-// Per-source finalisation of the pivot-centred GGN (see kfac.cu). One warp per source row.
+// Per-source finalisation of the pivot-centred GGN (see kfac.cu). One warp per source row; writes the fp16 ROW-MAJOR
+// stacked operands of pass 4 directly (they are MN-major operands of the tensor-core kernel: no transposes).
+__device__ __forceinline__ void store_row_f16(__half* dst, int64_t j, int64_t D, float v0, float v1) {
+  // j even; pads beyond D with zeros
+  *reinterpret_cast<__half2*>(dst + j) = __floats2half2_rn(j < D ? v0 : 0.f, j + 1 < D ? v1 : 0.f);
+}
+
 __global__ void __launch_bounds__(ROW_BLOCK)
-k_ggn_row_finalize(const float* __restrict__ x, int64_t B, int64_t D, int64_t ldx, const float* __restrict__ inv_norm,
-                   const float* __restrict__ w, const float* __restrict__ y, int64_t ldy,
-                   const float* __restrict__ inv_norm_y, const int* __restrict__ pivot, const float* __restrict__ rest,
-                   const float* __restrict__ inv_gamma, float* __restrict__ Nraw, float* __restrict__ Rraw,
-                   float* __restrict__ RA, int64_t ldm, float unscale_n, float unscale_r, int siglip,
-                   float* __restrict__ mult_x) {
+k_ggn_row_finalize(const float* __restrict__ x, int64_t B, int64_t D, int64_t Dp, int64_t ldx,
+                   const float* __restrict__ inv_norm, const float* __restrict__ w, const float* __restrict__ y,
+                   int64_t ldy, const float* __restrict__ inv_norm_y, const int* __restrict__ pivot,
+                   const float* __restrict__ rest, const float* __restrict__ inv_gamma, const float* __restrict__ Nraw,
+                   const float* __restrict__ Rraw, int64_t ldm, float unscale_n, float unscale_r, int siglip, float g,
+                   __half* __restrict__ LA, __half* __restrict__ RA, __half* __restrict__ LB, __half* __restrict__ RB,
+                   int64_t ldl, int64_t ldr) {
   const int64_t row = static_cast<int64_t>(blockIdx.x) * WARPS_PER_BLOCK + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= B) return;
   const float inv = inv_norm[row];
   const float* xr = x + row * ldx;
-  float* rr = Rraw + row * ldm;
-  float kappa;
+  const float* rr = Rraw + row * ldm;
+  __half* lb = LB + row * ldl;
+  __half* rb = RB + row * ldr;
   if (siglip) {
-    // u = r (cosine-weighted), a = u.xh ;  R_B = kappa (u - a/2 xh),  kappa = sqrt(w / gamma)
-    kappa = sqrtf(fmaxf(w[row] * (*inv_gamma), 0.f));
+    // u = r (cosine-weighted), a = u.xh ;  L_B = -2 kappa xh,  R_B = kappa (u - a/2 xh),  kappa = sqrt(w / gamma)
+    const float kappa = g * sqrtf(fmaxf(w[row] * (*inv_gamma), 0.f));
     float a = 0.f;
     for (int64_t j = lane; j < D; j += 32) a = fmaf(rr[j] * unscale_r, xr[j] * inv, a);
     a = warp_sum(a);
-    for (int64_t j = lane; j < D; j += 32) rr[j] = kappa * fmaf(-0.5f * a, xr[j] * inv, rr[j] * unscale_r);
-  } else {
-    // conditional (rho-free) quantities: nbar = E[yh | c != pivot], ebar = nbar - g, rbar = E[d yh | c != pivot] ...
-    const int pv = pivot[row];
-    const float* gr = y + static_cast<int64_t>(pv) * ldy;
-    const float ginv = inv_norm_y[pv];
-    const float rs = rest[row];
-    const float rho = rs / (1.f + rs);         // 1 - softmax(pivot), no cancellation
-    const float sq = sqrtf(1.f / (1.f + rs));  // sqrt(softmax(pivot))
-    const float c1 = 1.f / (1.f + sq);         // (1 - sqrt p*) / rho
-    const float c2 = 1.f + sq;
-    kappa = sqrtf(fmaxf(w[row] * rho * (*inv_gamma), 0.f));
-    float* nr = Nraw + row * ldm;
-    float* ra = RA + row * ldm;
-    float tau = 0.f;  // ebar . xh
-    for (int64_t j = lane; j < D; j += 32) {
-      const float e = fmaf(nr[j], unscale_n, -gr[j] * ginv);
-      tau = fmaf(e, xr[j] * inv, tau);
+    for (int64_t j = 2 * lane; j < Dp; j += 64) {
+      float lv[2], rv[2];
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int64_t jj = j + t;
+        const float xh = jj < D ? xr[jj] * inv : 0.f;
+        const float u = jj < D ? rr[jj] * unscale_r : 0.f;
+        lv[t] = -2.f * kappa * xh;
+        rv[t] = kappa * fmaf(-0.5f * a, xh, u);
+      }
+      store_row_f16(lb, j, D, lv[0], lv[1]);
+      store_row_f16(rb, j, D, rv[0], rv[1]);
     }
-    tau = warp_sum(tau);
-    float a = 0.f;  // ubar . xh,  ubar = rbar - tau (g + rho ebar)
-    for (int64_t j = lane; j < D; j += 32) {
-      const float g = gr[j] * ginv;
-      const float e = fmaf(nr[j], unscale_n, -g);
-      const float u = fmaf(-tau, fmaf(rho, e, g), rr[j] * unscale_r);
-      a = fmaf(u, xr[j] * inv, a);
-    }
-    a = warp_sum(a);
-    for (int64_t j = lane; j < D; j += 32) {
-      const float g = gr[j] * ginv;
-      const float e = fmaf(nr[j], unscale_n, -g);
-      const float u = fmaf(-tau, fmaf(rho, e, g), rr[j] * unscale_r);
-      nr[j] = -kappa * fmaf(c1, g, e);                        // L_A
-      ra[j] = kappa * fmaf(rho, e, c2 * g);                   // R_A
-      rr[j] = kappa * fmaf(-0.5f * a, xr[j] * inv, u);        // R_B
-    }
+    return;
   }
-  if (lane == 0) mult_x[row] = -2.f * kappa * inv;            // L_B = -2 kappa xh, written by the transposing writer
+  // conditional (rho-free) quantities: nbar = E[yh | c != pivot], ebar = nbar - g, rbar = E[d yh | c != pivot] ...
+  const int pv = pivot[row];
+  const float* gr = y + static_cast<int64_t>(pv) * ldy;
+  const float ginv = inv_norm_y[pv];
+  const float rs = rest[row];
+  const float rho = rs / (1.f + rs);         // 1 - softmax(pivot), no cancellation
+  const float sq = sqrtf(1.f / (1.f + rs));  // sqrt(softmax(pivot))
+  const float c1 = 1.f / (1.f + sq);         // (1 - sqrt p*) / rho
+  const float c2 = 1.f + sq;
+  const float kappa = g * sqrtf(fmaxf(w[row] * rho * (*inv_gamma), 0.f));
+  const float* nr = Nraw + row * ldm;
+  __half* la = LA + row * ldl;
+  __half* ra = RA + row * ldr;
+  float tau = 0.f;  // ebar . xh
+  for (int64_t j = lane; j < D; j += 32) {
+    const float e = fmaf(nr[j], unscale_n, -gr[j] * ginv);
+    tau = fmaf(e, xr[j] * inv, tau);
+  }
+  tau = warp_sum(tau);
+  float a = 0.f;  // ubar . xh,  ubar = rbar - tau (g + rho ebar)
+  for (int64_t j = lane; j < D; j += 32) {
+    const float gg = gr[j] * ginv;
+    const float e = fmaf(nr[j], unscale_n, -gg);
+    const float u = fmaf(-tau, fmaf(rho, e, gg), rr[j] * unscale_r);
+    a = fmaf(u, xr[j] * inv, a);
+  }
+  a = warp_sum(a);
+  for (int64_t j = 2 * lane; j < Dp; j += 64) {
+    float v[4][2];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int64_t jj = j + t;
+      const bool ok = jj < D;
+      const float gg = ok ? gr[jj] * ginv : 0.f;
+      const float xh = ok ? xr[jj] * inv : 0.f;
+      const float e = ok ? fmaf(nr[jj], unscale_n, -gg) : 0.f;
+      const float u = ok ? fmaf(-tau, fmaf(rho, e, gg), rr[jj] * unscale_r) : 0.f;
+      v[0][t] = -kappa * fmaf(c1, gg, e);              // L_A
+      v[1][t] = kappa * fmaf(rho, e, c2 * gg);         // R_A
+      v[2][t] = -2.f * kappa * xh;                     // L_B
+      v[3][t] = kappa * fmaf(-0.5f * a, xh, u);        // R_B
+    }
+    store_row_f16(la, j, D, v[0][0], v[0][1]);
+    store_row_f16(ra, j, D, v[1][0], v[1][1]);
+    store_row_f16(lb, j, D, v[2][0], v[2][1]);
+    store_row_f16(rb, j, D, v[3][0], v[3][1]);
+  }
+}
+
+// out[c, :] = fp16( y_c / |y_c| * q_c * inv_gamma * mult ), zero padded to Dp columns: the scaled side of Yh^T diag(q) Yh
+__global__ void __launch_bounds__(ROW_BLOCK)
+k_ggn_scale_targets(const float* __restrict__ y, int64_t C, int64_t D, int64_t Dp, int64_t ldy,
+                    const float* __restrict__ inv_norm_y, const float* __restrict__ q, const float* __restrict__ inv_gamma,
+                    float mult, __half* __restrict__ out, int64_t ldo) {
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= C) return;
+  const float m = inv_norm_y[row] * fmaxf(q[row] * (*inv_gamma), 0.f) * mult;
+  const float* yr = y + row * ldy;
+  __half* o = out + row * ldo;
+  for (int64_t j = 2 * lane; j < Dp; j += 64)
+    store_row_f16(o, j, D, j < D ? yr[j] * m : 0.f, j + 1 < D ? yr[j + 1] * m : 0.f);
 }
 
 // combine the per-column-range online-softmax partials of pass 1: [B, S] -> [B] (written to the first B entries)
@@ -360,12 +407,6 @@ __global__ void k_col_pow2_scale(const unsigned int* __restrict__ amax_bits, int
   }
   scale[j] = ldexpf(1.f, e);
   unscale[j] = ldexpf(1.f, -e);
-}
-
-__global__ void k_ggn_col_mult(const float* __restrict__ q, const float* __restrict__ inv_norm_y,
-                               const float* __restrict__ inv_gamma, int64_t C, float g, float* __restrict__ mult_y) {
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < C) mult_y[i] = g * sqrtf(fmaxf(q[i] * (*inv_gamma), 0.f)) * inv_norm_y[i];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -484,13 +525,25 @@ int launch_transpose_to_16(const float* src, int64_t R, int64_t d, int64_t ld, c
   return BVLM_OK;
 }
 
-int launch_ggn_row_finalize(const float* x, int64_t B, int64_t D, int64_t ldx, const float* inv_norm, const float* w,
+int launch_ggn_row_finalize(const float* x, int64_t B, int64_t D, int64_t Dp, int64_t ldx, const float* inv_norm, const float* w,
                             const float* y, int64_t ldy, const float* inv_norm_y, const int* pivot, const float* rest,
-                            const float* inv_gamma, float* Nraw, float* Rraw, float* RA, int64_t ldm, float unscale_n,
-                            float unscale_r, int siglip, float* mult_x, cudaStream_t st) {
+                            const float* inv_gamma, const float* Nraw, const float* Rraw, int64_t ldm, float unscale_n,
+                            float unscale_r, int siglip, float g, __half* LA, __half* RA, __half* LB, __half* RB, int64_t ldl,
+                            int64_t ldr, cudaStream_t st) {
   if (B <= 0) return BVLM_OK;
-  k_ggn_row_finalize<<<row_grid(B), ROW_BLOCK, 0, st>>>(x, B, D, ldx, inv_norm, w, y, ldy, inv_norm_y, pivot, rest,
-                                                        inv_gamma, Nraw, Rraw, RA, ldm, unscale_n, unscale_r, siglip, mult_x);
+  if ((Dp & 1) || (ldl & 1) || (ldr & 1)) return BVLM_EINVAL;
+  k_ggn_row_finalize<<<row_grid(B), ROW_BLOCK, 0, st>>>(x, B, D, Dp, ldx, inv_norm, w, y, ldy, inv_norm_y, pivot, rest,
+                                                        inv_gamma, Nraw, Rraw, ldm, unscale_n, unscale_r, siglip, g, LA, RA,
+                                                        LB, RB, ldl, ldr);
+  count_launch();
+  BVLM_CUDA_TRY(cudaGetLastError());
+  return BVLM_OK;
+}
+
+int launch_ggn_scale_targets(const float* y, int64_t C, int64_t D, int64_t Dp, int64_t ldy, const float* inv_norm_y,
+                             const float* q, const float* inv_gamma, float mult, __half* out, int64_t ldo, cudaStream_t st) {
+  if (C <= 0) return BVLM_OK;
+  k_ggn_scale_targets<<<row_grid(C), ROW_BLOCK, 0, st>>>(y, C, D, Dp, ldy, inv_norm_y, q, inv_gamma, mult, out, ldo);
   count_launch();
   BVLM_CUDA_TRY(cudaGetLastError());
   return BVLM_OK;
@@ -544,15 +597,6 @@ int launch_col_pow2_scale(const float* x, int64_t n, int64_t d, int64_t ld, int 
   count_launch();
   const int64_t dA = d + (append_one ? 1 : 0);
   k_col_pow2_scale<<<static_cast<unsigned>((dA + 255) / 256), 256, 0, st>>>(amax_bits, d, append_one, scale, unscale);
-  count_launch();
-  BVLM_CUDA_TRY(cudaGetLastError());
-  return BVLM_OK;
-}
-
-int launch_ggn_col_mult(const float* q, const float* inv_norm_y, const float* inv_gamma, int64_t C, float g, float* mult_y,
-                        cudaStream_t st) {
-  if (C <= 0) return BVLM_OK;
-  k_ggn_col_mult<<<static_cast<unsigned>((C + 255) / 256), 256, 0, st>>>(q, inv_norm_y, inv_gamma, C, g, mult_y);
   count_launch();
   BVLM_CUDA_TRY(cudaGetLastError());
   return BVLM_OK;

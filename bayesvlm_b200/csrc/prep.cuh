@@ -39,17 +39,22 @@ int launch_transpose_to_16(const float* src, int64_t R, int64_t d, int64_t ld, c
 
 // Per-source finalisation of the pivot-centred GGN (collapsed form of hessians.py:30-46 / 103-113; see kfac.cu).
 // gamma = max_c q_c normalises the stacked operands of pass 4 into fp16's range whatever the curvature scale is.
-//   InfoNCE (conditional, rho-free inputs from pass 3): nbar = Nraw*unscale_n, rbar = Rraw*unscale_r, g = yh[pivot],
-//            rho = rest/(1+rest), p* = 1/(1+rest), ebar = nbar - g, tau = ebar.xh, ubar = rbar - tau (g + rho ebar),
-//            abar = ubar.xh, kappa = sqrt(w rho / gamma)
-//            Nraw <- L_A = -kappa (ebar + g/(1+sqrt p*)),  RA <- R_A = kappa (rho ebar + (1+sqrt p*) g),
-//            Rraw <- R_B = kappa (ubar - abar/2 xh)
-//   SigLIP : u = Rraw*unscale_r, a = u.xh, kappa = sqrt(w / gamma), Rraw <- R_B = kappa (u - a/2 xh)
-//   mult_x[b] = -2 kappa_b/|x_b|   (row multiplier that turns X into L_B)
-int launch_ggn_row_finalize(const float* x, int64_t B, int64_t D, int64_t ldx, const float* inv_norm, const float* w,
+// Outputs are fp16 ROW-MAJOR [B, Dp] blocks (zero padded beyond D) written straight into the stacked MN-major operands:
+//   InfoNCE (conditional, rho-free inputs from pass 3): nbar = Nraw*unscale_n, rbar = Rraw*unscale_r, gv = yh[pivot],
+//            rho = rest/(1+rest), p* = 1/(1+rest), ebar = nbar - gv, tau = ebar.xh, ubar = rbar - tau (gv + rho ebar),
+//            abar = ubar.xh, kappa = g sqrt(w rho / gamma)
+//            L_A = -kappa (ebar + gv/(1+sqrt p*)),  R_A = kappa (rho ebar + (1+sqrt p*) gv),
+//            L_B = -2 kappa xh,                     R_B = kappa (ubar - abar/2 xh)
+//   SigLIP : u = Rraw*unscale_r, a = u.xh, kappa = g sqrt(w / gamma), L_B = -2 kappa xh, R_B = kappa (u - a/2 xh)
+int launch_ggn_row_finalize(const float* x, int64_t B, int64_t D, int64_t Dp, int64_t ldx, const float* inv_norm, const float* w,
                             const float* y, int64_t ldy, const float* inv_norm_y, const int* pivot, const float* rest,
-                            const float* inv_gamma, float* Nraw, float* Rraw, float* RA, int64_t ldm, float unscale_n,
-                            float unscale_r, int siglip, float* mult_x, cudaStream_t st);
+                            const float* inv_gamma, const float* Nraw, const float* Rraw, int64_t ldm, float unscale_n,
+                            float unscale_r, int siglip, float g, __half* LA, __half* RA, __half* LB, __half* RB, int64_t ldl,
+                            int64_t ldr, cudaStream_t st);
+
+// out[c, :] = fp16( yh_c * q_c / gamma * mult ) -- the scaled side of the Yh^T diag(q) Yh segment of pass 4
+int launch_ggn_scale_targets(const float* y, int64_t C, int64_t D, int64_t Dp, int64_t ldy, const float* inv_norm_y,
+                             const float* q, const float* inv_gamma, float mult, __half* out, int64_t ldo, cudaStream_t st);
 
 // Pass-1 partials [B, S] (row max, rest, pivot per column range) -> merged stats written at offset B*S of each array
 // (the arrays hold B*(S+1) entries).
@@ -70,10 +75,6 @@ int launch_sym_add(const float* S, int64_t d, int64_t lds, float* out, int64_t l
 // per-feature power-of-two scale: scale[j] = 2^e_j with max_r |x_rj| 2^e_j in [512,1024); unscale[j] = 2^-e_j
 int launch_col_pow2_scale(const float* x, int64_t n, int64_t d, int64_t ld, int append_one, unsigned int* amax_bits,
                           float* scale, float* unscale, cudaStream_t st);
-
-// mult_y[c] = g * sqrt(max(q_c / gamma, 0)) / |y_c|
-int launch_ggn_col_mult(const float* q, const float* inv_norm_y, const float* inv_gamma, int64_t C, float g, float* mult_y,
-                        cudaStream_t st);
 
 // Canonical probit softmax (scripts/zeroshot.py:119-120): probs = softmax_j(mean / sqrt(1 + pi/8 var)).
 int launch_probit_softmax(const float* mean, const float* var, int64_t N, int64_t C, int64_t ld, float* probs,
