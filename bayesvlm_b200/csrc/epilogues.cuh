@@ -183,13 +183,13 @@ struct EpiPredictive {
     int64_t ld;
     const float* u;
     const float* v;
-    const float* a;  // padded to a multiple of BN entries (zeros beyond C)
+    const float* rm;  // per-row factor: mean_ij = rm_i * acc_ij
+    const float* a;   // padded to a multiple of BN entries (zeros beyond C)
     const float* b;
-    float mean_scale;
-    int use_tma;     // 0: row pitch not a multiple of 16 bytes -> direct stores
+    int use_tma;      // 0: row pitch not a multiple of 16 bytes -> direct stores
   };
   struct State {
-    float u, v;
+    float u, v, rm;
   };
   static constexpr bool ALL_CHUNKS = false;
   static constexpr bool UNROLL_CHUNKS = true;
@@ -202,6 +202,7 @@ struct EpiPredictive {
     const int row = epi_row(ctx, tc);
     st.u = row < ctx.M ? p.u[row] : 0.f;
     st.v = row < ctx.M ? p.v[row] : 0.f;
+    st.rm = row < ctx.M ? p.rm[row] : 0.f;
   }
   __device__ static void chunk(State& st, const Params& p, const EpiCtx& ctx, const TileCoord& tc, float (&v)[32], int c) {
     const int row = epi_row(ctx, tc);
@@ -219,7 +220,7 @@ struct EpiPredictive {
       var[4 * j + 3] = fmaf(st.u, a4.w, st.v * b4.w);
     }
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] *= p.mean_scale;
+    for (int j = 0; j < 32; ++j) v[j] *= st.rm;
     if (p.use_tma) {
       // rows beyond N and columns beyond C are clipped by the tensor map
       const uint32_t slab_m = ctx.scratch_u32 + static_cast<uint32_t>(ctx.wid) * (2 * SLAB_BYTES);

@@ -31,9 +31,36 @@ struct Carver {
 
 inline int64_t pad64(int64_t k) { return round_up_i64(k, 64); }
 
+// Lazily created side stream + fork/join events (one set per device) for intra-call concurrency.
+struct SideStream {
+  cudaStream_t stream;
+  cudaEvent_t fork, join;
+};
+SideStream* side_stream() {
+  static SideStream per_dev[16];
+  static bool ready[16] = {false};
+  static const bool enabled = [] {
+    const char* e = getenv("BVLM_PRED_SIDE_STREAM");
+    return e == nullptr || atoi(e) != 0;
+  }();
+  if (!enabled) return nullptr;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  if (!ready[dev]) {
+    SideStream s{};
+    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    per_dev[dev] = s;
+    ready[dev] = true;
+  }
+  return &per_dev[dev];
+}
+
 // out[i] = | W16 act16_i |^2  through the row-panel GEMM with the sum-of-squares epilogue.
 int quadform_impl(const float* act, int64_t n, int64_t d, int64_t ld, int append_one, const void* W16, int64_t dA,
-                  int64_t k_pad, float w_scale, float* out, void* ws, size_t ws_bytes, cudaStream_t st) {
+                  int64_t k_pad, float w_scale, float* out, void* ws, size_t ws_bytes, cudaStream_t st,
+                  cudaEvent_t after_convert = nullptr) {
   if (n <= 0) return BVLM_OK;
   if (dA != d + (append_one ? 1 : 0) || k_pad != pad64(dA)) return BVLM_EINVAL;
   if (ws_bytes < bvlm_quadform_workspace_bytes(n, d, append_one)) return BVLM_EWORKSPACE;
@@ -42,6 +69,8 @@ int quadform_impl(const float* act, int64_t n, int64_t d, int64_t ld, int append
   float* row_unscale = cv.take<float>(static_cast<size_t>(n));
   int rc = launch_rows_to_16(act, n, d, ld, append_one, FMT_F16, 1, 1.0f, act16, k_pad, row_unscale, st);
   if (rc) return rc;
+  // the HBM-bound conversion is done: work forked here overlaps the tensor-bound GEMM below
+  if (after_convert != nullptr) BVLM_CUDA_TRY(cudaEventRecord(after_convert, st));
   CUtensorMap tmA, tmB;
   Operand16 opA{act16, n, k_pad, FMT_F16};
   Operand16 opB{W16, dA, k_pad, FMT_F16};
@@ -116,7 +145,7 @@ int bvlm_predictive_target_prepare(const float* T, int64_t C, int64_t D, int64_t
 
 size_t bvlm_predictive_workspace_bytes(int64_t N, int64_t D, int64_t d_act, int append_one, int precision) {
   size_t b = bvlm_quadform_workspace_bytes(N, d_act, append_one);
-  b += 3 * (round_up_i64(N * 4, 256) + 256);
+  b += 7 * (round_up_i64(N * 4, 256) + 256);
   b += round_up_i64(N * operand_pitch(pad64(D) * (precision == 3 ? 2 : 1)) * 2, 256) + 256;
   return b;
 }
@@ -140,16 +169,36 @@ int bvlm_predictive(const float* E, int64_t N, int64_t D, int64_t lde, const flo
   float* alpha = cv.take<float>(static_cast<size_t>(N));
   float* rowU = cv.take<float>(static_cast<size_t>(N));
   float* rowV = cv.take<float>(static_cast<size_t>(N));
+  float* rowM = cv.take<float>(static_cast<size_t>(N));
+  float* n2 = cv.take<float>(static_cast<size_t>(N));
+  float* pd = cv.take<float>(static_cast<size_t>(N));
+  float* esc = cv.take<float>(static_cast<size_t>(N));
   const int64_t e_pitch = operand_pitch(kp);
   __half* E16 = cv.take<__half>(static_cast<size_t>(N) * e_pitch);
   const size_t used = cv.used();
-  int rc = quadform_impl(Eact, N, d_act, ldact, append_one, Wi16, dA, k_pad, w_scale, alpha,
-                         static_cast<uint8_t*>(ws) + used, ws_bytes - used, st);
-  if (rc) return rc;
   const float s = expf(logit_scale);
-  // side 0: out0 = s^2 (sum_d e_d^2 delta_d)/E, out1 = s^2 alpha/E ; E = |e|^2 + alpha * sum(beta)
-  rc = launch_predictive_row_prep(E, N, D, lde, alpha, delta, sum_beta, 0.f, s * s, /*side=*/0, precision, PRED_OPSCALE,
-                                  E16, seg, e_pitch, rowU, rowV, st);
+  // The embedding operand does not depend on the quadratic forms: convert it on a side stream while the activation
+  // conversion + quadratic-form GEMM run on the caller's stream (HBM-bound and tensor-bound work overlap).
+  SideStream* side = side_stream();
+  int rc;
+  // caller's stream: activation conversion (HBM bound) -> [fork] -> quadratic-form GEMM (tensor bound)
+  rc = quadform_impl(Eact, N, d_act, ldact, append_one, Wi16, dA, k_pad, w_scale, alpha,
+                     static_cast<uint8_t*>(ws) + used, ws_bytes - used, st, side != nullptr ? side->fork : nullptr);
+  if (rc) return rc;
+  // side stream: embedding conversion (HBM bound), concurrent with the GEMM above
+  cudaStream_t st_e = st;
+  if (side != nullptr) {
+    st_e = side->stream;
+    BVLM_CUDA_TRY(cudaStreamWaitEvent(st_e, side->fork, 0));
+  }
+  rc = launch_predictive_embed_prep(E, N, D, lde, delta, precision, E16, seg, e_pitch, n2, pd, esc, st_e);
+  if (rc) return rc;
+  if (side != nullptr) {
+    BVLM_CUDA_TRY(cudaEventRecord(side->join, st_e));
+    BVLM_CUDA_TRY(cudaStreamWaitEvent(st, side->join, 0));
+  }
+  // E_i, u_i, v_i and the per-row mean factor (T16 carries PRED_OPSCALE, E16 its own power-of-two row scale)
+  rc = launch_predictive_row_scalars(N, alpha, n2, pd, esc, sum_beta, s * s, s / PRED_OPSCALE, rowU, rowV, rowM, st);
   if (rc) return rc;
   CUtensorMap tmA, tmB;
   Operand16 opA{E16, N, kp, FMT_F16, e_pitch};
@@ -158,7 +207,7 @@ int bvlm_predictive(const float* E, int64_t N, int64_t D, int64_t lde, const flo
   if ((rc = operand_tmap<PRED_BN>(&tmB, opB))) return rc;
   static const int variant = [] {
     const char* e = getenv("BVLM_PRED_VARIANT");  // 0: one-CTA engine, 1: CTA pairs + 4 epilogue warps, 2: pairs + 8 warps
-    return e != nullptr ? atoi(e) : 2;
+    return e != nullptr ? atoi(e) : 1;
   }();
   GemmPlan plan;
   if (variant == 0) {
@@ -177,9 +226,9 @@ int bvlm_predictive(const float* E, int64_t N, int64_t D, int64_t lde, const flo
   ep.ld = ldo;
   ep.u = rowU;
   ep.v = rowV;
+  ep.rm = rowM;
   ep.a = colA;
   ep.b = colB;
-  ep.mean_scale = s / (PRED_OPSCALE * PRED_OPSCALE);
   // TMA stores need 16-byte aligned rows; tiny class counts (e.g. C = 10) fall back to direct stores
   ep.use_tma = ((ldo * 4) % 16 == 0 && (reinterpret_cast<uintptr_t>(mean) & 15) == 0 &&
                 (reinterpret_cast<uintptr_t>(var) & 15) == 0) ? 1 : 0;

@@ -105,6 +105,71 @@ k_predictive_row_prep(const float* __restrict__ x, int64_t R, int64_t D, int64_t
 }
 
 // ------------------------------------------------------------------------------------------------
+// Source-side operand of the predictive that does NOT depend on the quadratic forms: e_i * 2^k (row power-of-two scale,
+// exact) as fp16 [hi | lo], plus |e_i|^2, sum_d e_id^2 delta_d and 2^-k.  The 1/sqrt(E_i) normalisation is applied by the
+// GEMM epilogue (a per-row factor), so this pass can overlap the quadratic-form GEMM on another stream.
+__global__ void __launch_bounds__(ROW_BLOCK)
+k_predictive_embed_prep(const float* __restrict__ x, int64_t R, int64_t D, int64_t ld, const float* __restrict__ diag_other,
+                        int nsplit, __half* __restrict__ packed, int64_t seg_pad, int64_t out_pitch,
+                        float* __restrict__ n2_out, float* __restrict__ pd_out, float* __restrict__ unscale_out) {
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= R) return;
+  const float* xr = x + row * ld;
+  float n2 = 0.f, pd = 0.f, amax = 0.f;
+  for (int64_t j = lane; j < D; j += 32) {
+    const float v = xr[j];
+    const float v2 = v * v;
+    n2 += v2;
+    pd = fmaf(v2, diag_other[j], pd);
+    amax = fmaxf(amax, fabsf(v));
+  }
+  n2 = warp_sum(n2);
+  pd = warp_sum(pd);
+  amax = warp_max(amax);
+  int e = 0;
+  if (amax > 0.f && isfinite(amax)) {
+    int ex;
+    frexpf(amax, &ex);
+    e = 9 - ex;  // scaled absmax lands in [256, 512)
+    e = e < -60 ? -60 : (e > 60 ? 60 : e);
+  }
+  const float sc = ldexpf(1.f, e);
+  const int64_t pitch = out_pitch > 0 ? out_pitch : seg_pad * (nsplit == 3 ? 2 : 1);
+  __half* o = packed + row * pitch;
+  for (int64_t j = 2 * lane; j < seg_pad; j += 64) {
+    const float v0 = j < D ? xr[j] * sc : 0.f;
+    const float v1 = j + 1 < D ? xr[j + 1] * sc : 0.f;
+    const __half2 hi = __floats2half2_rn(v0, v1);
+    *reinterpret_cast<__half2*>(o + j) = hi;
+    if (nsplit == 3) {
+      const float2 hf = __half22float2(hi);
+      *reinterpret_cast<__half2*>(o + seg_pad + j) = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+    }
+  }
+  if (lane == 0) {
+    n2_out[row] = n2;
+    pd_out[row] = pd;
+    unscale_out[row] = ldexpf(1.f, -e);
+  }
+}
+
+// E_i = |e_i|^2 + alpha_i sum(beta);  u_i = s^2 (e_i^2 . delta) / E_i;  v_i = s^2 alpha_i / E_i;
+// rm_i = mean_scale * 2^-k_i / sqrt(E_i)   (per-row factor that turns the raw accumulator into the mean logit)
+__global__ void k_predictive_row_scalars(int64_t R, const float* __restrict__ alpha, const float* __restrict__ n2,
+                                         const float* __restrict__ pd, const float* __restrict__ unscale, float sum_beta,
+                                         float s2, float mean_scale, float* __restrict__ u, float* __restrict__ v,
+                                         float* __restrict__ rm) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= R) return;
+  const float a = alpha[i];
+  const float E = n2[i] + a * sum_beta;
+  u[i] = s2 * pd[i] / E;
+  v[i] = s2 * a / E;
+  rm[i] = mean_scale * unscale[i] / sqrtf(E);
+}
+
+// ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(ROW_BLOCK)
 k_ggn_row_prep(const float* __restrict__ x, int64_t R, int64_t D, int64_t ld, float opscale, int nsplit, int side,
                __half* __restrict__ xhat, int64_t d_pad, float* __restrict__ inv_norm, float* __restrict__ w_raw,
@@ -487,6 +552,28 @@ int launch_predictive_row_prep(const float* x, int64_t R, int64_t D, int64_t ld,
   if ((nsplit != 1 && nsplit != 3) || seg_pad < D || (seg_pad & 1)) return BVLM_EINVAL;
   k_predictive_row_prep<<<row_grid(R), ROW_BLOCK, 0, st>>>(x, R, D, ld, quad, diag_other, sum_diag_self, kappa, s2, side,
                                                            nsplit, opscale, packed, seg_pad, out_pitch, out0, out1);
+  count_launch();
+  BVLM_CUDA_TRY(cudaGetLastError());
+  return BVLM_OK;
+}
+
+int launch_predictive_embed_prep(const float* x, int64_t R, int64_t D, int64_t ld, const float* diag_other, int nsplit,
+                                 __half* packed, int64_t seg_pad, int64_t out_pitch, float* n2, float* pd, float* unscale,
+                                 cudaStream_t st) {
+  if (R <= 0) return BVLM_OK;
+  if ((nsplit != 1 && nsplit != 3) || seg_pad < D || (seg_pad & 1)) return BVLM_EINVAL;
+  k_predictive_embed_prep<<<row_grid(R), ROW_BLOCK, 0, st>>>(x, R, D, ld, diag_other, nsplit, packed, seg_pad, out_pitch, n2,
+                                                             pd, unscale);
+  count_launch();
+  BVLM_CUDA_TRY(cudaGetLastError());
+  return BVLM_OK;
+}
+
+int launch_predictive_row_scalars(int64_t R, const float* alpha, const float* n2, const float* pd, const float* unscale,
+                                  float sum_beta, float s2, float mean_scale, float* u, float* v, float* rm, cudaStream_t st) {
+  if (R <= 0) return BVLM_OK;
+  k_predictive_row_scalars<<<static_cast<unsigned>((R + 255) / 256), 256, 0, st>>>(R, alpha, n2, pd, unscale, sum_beta, s2,
+                                                                                   mean_scale, u, v, rm);
   count_launch();
   BVLM_CUDA_TRY(cudaGetLastError());
   return BVLM_OK;

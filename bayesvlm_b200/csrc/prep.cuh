@@ -21,6 +21,15 @@ int launch_predictive_row_prep(const float* x, int64_t R, int64_t D, int64_t ld,
                                int nsplit, float opscale, __half* packed, int64_t seg_pad, int64_t out_pitch, float* out0,
                                float* out1, cudaStream_t st);
 
+// Source side of the predictive, independent of the quadratic forms (so it can overlap them): packed = fp16 [hi | lo] of
+// x_r * 2^k_r (exact power-of-two row scale), n2 = |x_r|^2, pd = sum_d x_rd^2 diag_other_d, unscale = 2^-k_r.
+int launch_predictive_embed_prep(const float* x, int64_t R, int64_t D, int64_t ld, const float* diag_other, int nsplit,
+                                 __half* packed, int64_t seg_pad, int64_t out_pitch, float* n2, float* pd, float* unscale,
+                                 cudaStream_t st);
+// E = n2 + alpha sum_beta; u = s2 pd / E; v = s2 alpha / E; rm = mean_scale * unscale / sqrt(E)   (vlm.py:665-684)
+int launch_predictive_row_scalars(int64_t R, const float* alpha, const float* n2, const float* pd, const float* unscale,
+                                  float sum_beta, float s2, float mean_scale, float* u, float* v, float* rm, cudaStream_t st);
+
 // GGN row prep (hessians.py:15-21): xhat = x/|x| * opscale -> fp16 [R, d_pad] (nsplit 1) or [R, 2*d_pad] = [hi | lo]
 // (nsplit 3; `side` is ignored); inv_norm[r] = 1/|x_r|;
 // w_raw[r] = 1/|x_r|^2 ; *w_sum += sum_r w_raw[r] (atomic).
