@@ -17,6 +17,7 @@ _PKG_DIR = Path(__file__).resolve().parent
 LIB_PATH = _PKG_DIR / "libbvlm.so"
 
 PREC_X1 = 1
+PREC_X2F8 = 2
 PREC_X3 = 3
 
 
@@ -54,14 +55,15 @@ SIGNATURES = {
     "bvlm_quadform_workspace_bytes": (c_size_t, [_I, _I, c_int]),
     "bvlm_quadform": (c_int, [_P, _I, _I, _I, c_int, _P, _I, _I, c_float, _P, _P, c_size_t, _P]),
     "bvlm_predictive_target_workspace_bytes": (c_size_t, [_I, _I, _I, c_int]),
+    "bvlm_predictive_t8_cols": (c_int64, [_I]),
     "bvlm_predictive_target_prepare": (
         c_int,
-        [_P, _I, _I, _I, _P, _I, _I, c_int, _P, _I, _I, c_float, _P, c_float, c_float, c_int, _P, _P, _P, _P, c_size_t, _P],
+        [_P, _I, _I, _I, _P, _I, _I, c_int, _P, _I, _I, c_float, _P, c_float, c_float, c_int, _P, _P, _P, _P, _P, c_size_t, _P],
     ),
     "bvlm_predictive_workspace_bytes": (c_size_t, [_I, _I, _I, c_int, c_int]),
     "bvlm_predictive": (
         c_int,
-        [_P, _I, _I, _I, _P, _I, _I, c_int, _P, _I, _I, c_float, _P, c_float, c_float, _P, _P, _P, _I, c_int, _P, _P, _P,
+        [_P, _I, _I, _I, _P, _I, _I, c_int, _P, _I, _I, c_float, _P, c_float, c_float, _P, _P, _P, _P, _I, c_int, _P, _P, _P,
          _I, _P, c_size_t, _P],
     ),
     "bvlm_probit_softmax": (c_int, [_P, _P, _I, _I, _I, _P, _P]),

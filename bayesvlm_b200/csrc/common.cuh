@@ -258,6 +258,15 @@ __host__ __device__ inline uint32_t make_idesc_f16(int m, int n, int a_fmt, int 
   return d;
 }
 
+// kind::f8f6f4 instruction descriptor for two E4M3 operands (format code 0), fp32 accumulate, K-major.
+__host__ __device__ inline uint32_t make_idesc_e4m3(int m, int n) {
+  uint32_t d = 0;
+  d |= 1u << 4;                              // D format: F32
+  d |= static_cast<uint32_t>(n >> 3) << 17;  // N >> 3
+  d |= static_cast<uint32_t>(m >> 4) << 24;  // M >> 4
+  return d;
+}
+
 // ---------------------------------------------------------------------------------------------
 // small math / memory helpers
 // ---------------------------------------------------------------------------------------------

@@ -181,9 +181,13 @@ struct EpiPredictive {
     float* mean;
     float* var;
     int64_t ld;
-    const float* u;
-    const float* v;
-    const float* rm;  // per-row factor: mean_ij = rm_i * acc_ij
+    // per-row inputs (vlm.py:659-668): alpha_i = a_i^T A^-1 a_i, n2_i = |e_i|^2, pd_i = sum_d e_id^2 delta_d, esc_i = 2^-k_i;
+    // E_i = n2_i + alpha_i sum_beta, u_i = s2 pd_i / E_i, v_i = s2 alpha_i / E_i, mean_ij = acc_ij mean_scale esc_i / sqrt(E_i)
+    const float* alpha;
+    const float* n2;
+    const float* pd;
+    const float* esc;
+    float sum_beta, s2, mean_scale;
     const float* a;   // padded to a multiple of BN entries (zeros beyond C)
     const float* b;
     int use_tma;      // 0: row pitch not a multiple of 16 bytes -> direct stores
@@ -200,9 +204,15 @@ struct EpiPredictive {
   __device__ static void item_begin(State&, const Params&, const EpiCtx&, const TileCoord&) {}
   __device__ static void tile_begin(State& st, const Params& p, const EpiCtx& ctx, const TileCoord& tc) {
     const int row = epi_row(ctx, tc);
-    st.u = row < ctx.M ? p.u[row] : 0.f;
-    st.v = row < ctx.M ? p.v[row] : 0.f;
-    st.rm = row < ctx.M ? p.rm[row] : 0.f;
+    st.u = st.v = st.rm = 0.f;
+    if (row < ctx.M) {
+      const float al = p.alpha[row];
+      const float E = fmaf(al, p.sum_beta, p.n2[row]);
+      const float rE = 1.0f / E;
+      st.u = p.s2 * p.pd[row] * rE;
+      st.v = p.s2 * al * rE;
+      st.rm = p.mean_scale * p.esc[row] * rsqrtf(E);
+    }
   }
   __device__ static void chunk(State& st, const Params& p, const EpiCtx& ctx, const TileCoord& tc, float (&v)[32], int c) {
     const int row = epi_row(ctx, tc);

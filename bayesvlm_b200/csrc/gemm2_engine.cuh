@@ -74,6 +74,16 @@ __device__ __forceinline__ void umma_f16_ss_pair(uint32_t tmem_d, uint64_t desc_
       : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void umma_f8_ss_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // arrive on the barrier at this offset in BOTH CTAs once all previously issued MMAs of the pair have completed
 __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
   asm volatile(
@@ -93,7 +103,8 @@ constexpr size_t gemm2_smem_bytes() {
 // any transposing pass). Such a tile is fetched as 64-column boxes of [64 K rows x 128 bytes].
 template <int BN, int STAGES, int EPI_WARPS, class Epi, bool A_MN = false, bool B_MN = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * EPI_WARPS, 1)
-gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmPlan plan,
+gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmA8, const __grid_constant__ CUtensorMap tmB8, const GemmPlan plan,
                 const __grid_constant__ typename Epi::Params ep) {
   static_assert(BN % 64 == 0 && BN >= 64 && BN <= 256, "BN must be a multiple of 64 in [64,256]");
   static_assert(EPI_WARPS == 4 || EPI_WARPS == 8, "4 or 8 epilogue warps");
@@ -173,6 +184,11 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
             mbar_wait(&empty_bar[stage], phase ^ 1u);
             mbar_arrive_expect_tx_leader(&full_bar[stage], plan.a_tx_bytes + B_BYTES);
+            if (kb >= plan.kb_alt) {  // FP8 phase: same 128-byte K blocks, 128 elements each, second pair of tensor maps
+              const int col8 = (kb - plan.kb_alt) * 128;
+              tma_load_2d_pair(sA + stage * A_BYTES, &tmA8, &full_bar[stage], col8, row_a);
+              tma_load_2d_pair(sB + stage * B_BYTES, &tmB8, &full_bar[stage], col8, row_b);
+            } else {
             if constexpr (A_MN) {  // [K, M] storage: two 64-column boxes of 64 K rows
 #pragma unroll
               for (int blk = 0; blk < GEMM_BM / 64; ++blk)
@@ -189,6 +205,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 tma_load_2d_pair(sB + stage * B_BYTES + blk * (GEMM_BK * 128), &tmB, &full_bar[stage], row_b + blk * 64, col_b);
             } else {
               tma_load_2d_pair(sB + stage * B_BYTES, &tmB, &full_bar[stage], col_b, row_b);
+            }
             }
             if (++stage == STAGES) {
               stage = 0;
@@ -221,10 +238,19 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                                      : make_smem_desc_kmajor_sw128(smem_u32(sB + stage * B_BYTES));
             // one UMMA consumes 16 K elements: 32 bytes along a K-major row, 16 rows (2048 bytes) of an MN-major block
             constexpr uint64_t STEP_A = A_MN ? (16 * 128) >> 4 : 2, STEP_B = B_MN ? (16 * 128) >> 4 : 2;
+            if (kb >= plan.kb_alt) {  // FP8 phase: K = 32 per instruction = 32 bytes, same descriptor step as fp16
+              const uint64_t da8 = make_smem_desc_kmajor_sw128(smem_u32(sA + stage * A_BYTES));
+              const uint64_t db8 = make_smem_desc_kmajor_sw128(smem_u32(sB + stage * B_BYTES));
 #pragma unroll
-            for (int k = 0; k < GEMM_BK / GEMM_UMMA_K; ++k) {
-              umma_f16_ss_pair(tmem_d, da + STEP_A * static_cast<uint64_t>(k), db + STEP_B * static_cast<uint64_t>(k),
-                               plan.idesc, (kb > tc.kb0 || k > 0) ? 1u : 0u);
+              for (int k = 0; k < 4; ++k)
+                umma_f8_ss_pair(tmem_d, da8 + static_cast<uint64_t>(2 * k), db8 + static_cast<uint64_t>(2 * k), plan.idesc_alt,
+                                (kb > tc.kb0 || k > 0) ? 1u : 0u);
+            } else {
+#pragma unroll
+              for (int k = 0; k < GEMM_BK / GEMM_UMMA_K; ++k) {
+                umma_f16_ss_pair(tmem_d, da + STEP_A * static_cast<uint64_t>(k), db + STEP_B * static_cast<uint64_t>(k),
+                                 plan.idesc, (kb > tc.kb0 || k > 0) ? 1u : 0u);
+              }
             }
             umma_commit_pair(&empty_bar[stage]);
             if (++stage == STAGES) {
@@ -363,7 +389,8 @@ inline int gemm2_max_clusters(size_t smem) {
 // MN-major operands: tensor map over the [K, M|N] storage with box {64 columns, 64 K rows} (operand_tmap_mn).
 template <int BN, int STAGES, int EPI_WARPS, class Epi, bool A_MN = false, bool B_MN = false>
 inline int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmPlan& plan,
-                        const typename Epi::Params& ep, cudaStream_t stream, int tag) {
+                        const typename Epi::Params& ep, cudaStream_t stream, int tag, const CUtensorMap* tmA8 = nullptr,
+                        const CUtensorMap* tmB8 = nullptr) {
   if (plan.kb_total <= 0 || plan.M <= 0 || plan.N <= 0) return BVLM_EINVAL;
   constexpr size_t smem = gemm2_smem_bytes<BN, STAGES, EPI_WARPS, Epi>();
   static_assert(smem <= 232448, "shared memory budget exceeded");
@@ -377,7 +404,8 @@ inline int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ge
   int clusters = gemm2_max_clusters<BN, STAGES, EPI_WARPS, Epi, A_MN, B_MN>(smem);
   if (items < clusters) clusters = items;
   timing_begin(tag, stream);
-  kfn<<<2 * clusters, 128 + 32 * EPI_WARPS, smem, stream>>>(tmA, tmB, plan, ep);
+  kfn<<<2 * clusters, 128 + 32 * EPI_WARPS, smem, stream>>>(tmA, tmB, tmA8 != nullptr ? *tmA8 : tmA,
+                                                            tmB8 != nullptr ? *tmB8 : tmB, plan, ep);
   timing_end(tag, stream);
   count_launch();
   BVLM_CUDA_TRY(cudaGetLastError());

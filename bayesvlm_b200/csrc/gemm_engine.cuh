@@ -45,6 +45,11 @@ struct GemmPlan {
   int seg_kb;
   uint32_t a_seg_mask;
   uint32_t b_seg_mask;
+  // CTA-pair engine only: K blocks >= kb_alt come from a second pair of tensor maps holding FP8 (E4M3) operands -- 128
+  // elements per 128-byte K block -- and are multiplied with tcgen05.mma.kind::f8f6f4 (idesc_alt) into the SAME fp32
+  // accumulator (error-compensation terms at twice the fp16 rate).  kb_alt >= kb_total: no alternate phase.
+  int kb_alt;
+  uint32_t idesc_alt;
 };
 
 struct TileCoord {
@@ -406,6 +411,8 @@ inline GemmPlan make_plan(int M, int N, int K_padded, int mode, int splits, int 
   p.a_tx_bytes = GEMM_BM * GEMM_BK * 2;
   p.b_tx_bytes = BN * GEMM_BK * 2;
   p.seg_kb = 0;
+  p.kb_alt = 0x7fffffff;
+  p.idesc_alt = 0;
   return p;
 }
 

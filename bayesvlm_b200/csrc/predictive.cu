@@ -30,57 +30,35 @@ struct Carver {
 };
 
 inline int64_t pad64(int64_t k) { return round_up_i64(k, 64); }
-
-// Lazily created side stream + fork/join events (one set per device) for intra-call concurrency.
-struct SideStream {
-  cudaStream_t stream;
-  cudaEvent_t fork, join;
-};
-SideStream* side_stream() {
-  static SideStream per_dev[16];
-  static bool ready[16] = {false};
-  static const bool enabled = [] {
-    const char* e = getenv("BVLM_PRED_SIDE_STREAM");
-    return e == nullptr || atoi(e) != 0;
-  }();
-  if (!enabled) return nullptr;
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
-  if (!ready[dev]) {
-    SideStream s{};
-    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-    if (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    if (cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    per_dev[dev] = s;
-    ready[dev] = true;
-  }
-  return &per_dev[dev];
-}
+inline int64_t pad128(int64_t k) { return round_up_i64(k, 128); }
+constexpr float PRED_OPSCALE_F8 = 128.f * 32.f;  // target side of the fp16 + fp8 mode: unit-energy * 128 (fp8) * 2^5 (fp16)
 
 // out[i] = | W16 act16_i |^2  through the row-panel GEMM with the sum-of-squares epilogue.
 int quadform_impl(const float* act, int64_t n, int64_t d, int64_t ld, int append_one, const void* W16, int64_t dA,
                   int64_t k_pad, float w_scale, float* out, void* ws, size_t ws_bytes, cudaStream_t st,
-                  cudaEvent_t after_convert = nullptr) {
+                  bool converted = false) {
   if (n <= 0) return BVLM_OK;
   if (dA != d + (append_one ? 1 : 0) || k_pad != pad64(dA)) return BVLM_EINVAL;
   if (ws_bytes < bvlm_quadform_workspace_bytes(n, d, append_one)) return BVLM_EWORKSPACE;
   Carver cv(ws);
   __half* act16 = cv.take<__half>(static_cast<size_t>(n) * k_pad);
   float* row_unscale = cv.take<float>(static_cast<size_t>(n));
-  int rc = launch_rows_to_16(act, n, d, ld, append_one, FMT_F16, 1, 1.0f, act16, k_pad, row_unscale, st);
-  if (rc) return rc;
-  // the HBM-bound conversion is done: work forked here overlaps the tensor-bound GEMM below
-  if (after_convert != nullptr) BVLM_CUDA_TRY(cudaEventRecord(after_convert, st));
+  int rc = BVLM_OK;
+  if (!converted) {  // (the predictive converts the activations in its fused row-prep kernel)
+    rc = launch_rows_to_16(act, n, d, ld, append_one, FMT_F16, 1, 1.0f, act16, k_pad, row_unscale, st);
+    if (rc) return rc;
+  }
   CUtensorMap tmA, tmB;
   Operand16 opA{act16, n, k_pad, FMT_F16};
   Operand16 opB{W16, dA, k_pad, FMT_F16};
   if ((rc = operand_tmap<GEMM_BM>(&tmA, opA))) return rc;
-  if ((rc = operand_tmap<PRED_BN>(&tmB, opB))) return rc;
-  GemmPlan plan = make_plan<PRED_BN>(static_cast<int>(n), static_cast<int>(dA), static_cast<int>(k_pad), SCHED_ROW_PANEL,
-                                     1, FMT_F16, FMT_F16);
+  if ((rc = operand_tmap<PRED_BN / 2>(&tmB, opB))) return rc;  // CTA pairs: each CTA loads half of the B tile
+  // row panels on CTA pairs; W is lower triangular, so the K loop of column tile n stops at its diagonal block
+  GemmPlan plan = make_plan2<PRED_BN>(static_cast<int>(n), static_cast<int>(dA), static_cast<int>(k_pad), SCHED_ROW_PANEL, 1,
+                                      FMT_F16);
   plan.tri_k = 1;
   EpiRowSumSq<PRED_BN>::Params ep{out, row_unscale, 1.0f / (w_scale * w_scale)};
-  return launch_gemm<PRED_BN, PRED_STAGES, EpiRowSumSq<PRED_BN>>(tmA, tmB, plan, ep, st, TAG_QUADFORM);
+  return launch_gemm2<PRED_BN, 6, 4, EpiRowSumSq<PRED_BN>>(tmA, tmB, plan, ep, st, TAG_QUADFORM);
 }
 
 }  // namespace
@@ -116,14 +94,17 @@ size_t bvlm_predictive_target_workspace_bytes(int64_t C, int64_t D, int64_t d_ac
   return bvlm_quadform_workspace_bytes(C, d_act, append_one) + round_up_i64(C * 4, 256) + 512;
 }
 
+int64_t bvlm_predictive_t8_cols(int64_t D) { return 2 * pad128(D); }
+
 int bvlm_predictive_target_prepare(const float* T, int64_t C, int64_t D, int64_t ldt, const float* Tact, int64_t d_act,
                                    int64_t ldact, int append_one, const void* Wt16, int64_t dA, int64_t k_pad,
                                    float w_scale, const float* beta, float sum_delta, float kappa, int precision,
-                                   void* T16, float* colA, float* colB, void* ws, size_t ws_bytes, void* stream) {
+                                   void* T16, void* T8, float* colA, float* colB, void* ws, size_t ws_bytes, void* stream) {
   if (T == nullptr || Tact == nullptr || Wt16 == nullptr || beta == nullptr || T16 == nullptr || colA == nullptr ||
       colB == nullptr || ws == nullptr)
     return BVLM_EINVAL;
-  if (precision != BVLM_PREC_X1 && precision != BVLM_PREC_X3) return BVLM_EINVAL;
+  if (precision != BVLM_PREC_X1 && precision != BVLM_PREC_X3 && precision != BVLM_PREC_X2F8) return BVLM_EINVAL;
+  if (precision == BVLM_PREC_X2F8 && T8 == nullptr) return BVLM_EINVAL;
   if (ws_bytes < bvlm_predictive_target_workspace_bytes(C, D, d_act, append_one)) return BVLM_EWORKSPACE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   Carver cv(ws);
@@ -140,25 +121,28 @@ int bvlm_predictive_target_prepare(const float* T, int64_t C, int64_t D, int64_t
   }
   // side 1: out0 = gamma/E, out1 = (gamma*kappa + sum_d beta_d t_d^2)/E ; E = |t|^2 + gamma * sum(delta)
   return launch_predictive_row_prep(T, C, D, ldt, gamma, beta, sum_delta, kappa, 0.f, /*side=*/1, precision,
-                                    PRED_OPSCALE, static_cast<__half*>(T16), pad64(D), 0, colA, colB, st);
+                                    precision == BVLM_PREC_X2F8 ? PRED_OPSCALE_F8 : PRED_OPSCALE, static_cast<__half*>(T16),
+                                    pad64(D), 0, static_cast<uint8_t*>(T8), pad128(D), colA, colB, st);
 }
 
 size_t bvlm_predictive_workspace_bytes(int64_t N, int64_t D, int64_t d_act, int append_one, int precision) {
   size_t b = bvlm_quadform_workspace_bytes(N, d_act, append_one);
   b += 7 * (round_up_i64(N * 4, 256) + 256);
   b += round_up_i64(N * operand_pitch(pad64(D) * (precision == 3 ? 2 : 1)) * 2, 256) + 256;
+  if (precision == BVLM_PREC_X2F8) b += round_up_i64(N * 2 * pad128(D), 256) + 256;
   return b;
 }
 
 int bvlm_predictive(const float* E, int64_t N, int64_t D, int64_t lde, const float* Eact, int64_t d_act, int64_t ldact,
                     int append_one, const void* Wi16, int64_t dA, int64_t k_pad, float w_scale, const float* delta,
-                    float sum_beta, float logit_scale, const void* T16, const float* colA, const float* colB, int64_t C,
-                    int precision, float* mean, float* var, float* probs, int64_t ldo, void* ws, size_t ws_bytes,
+                    float sum_beta, float logit_scale, const void* T16, const void* T8, const float* colA, const float* colB,
+                    int64_t C, int precision, float* mean, float* var, float* probs, int64_t ldo, void* ws, size_t ws_bytes,
                     void* stream) {
   if (E == nullptr || Eact == nullptr || Wi16 == nullptr || delta == nullptr || T16 == nullptr || colA == nullptr ||
       colB == nullptr || mean == nullptr || var == nullptr || ws == nullptr)
     return BVLM_EINVAL;
-  if (precision != BVLM_PREC_X1 && precision != BVLM_PREC_X3) return BVLM_EINVAL;
+  if (precision != BVLM_PREC_X1 && precision != BVLM_PREC_X3 && precision != BVLM_PREC_X2F8) return BVLM_EINVAL;
+  if (precision == BVLM_PREC_X2F8 && T8 == nullptr) return BVLM_EINVAL;
   if (N <= 0 || C <= 0) return BVLM_OK;
   if (ldo < C || N > 0x7fffffff || C > 0x7fffffff) return BVLM_EINVAL;
   if (ws_bytes < bvlm_predictive_workspace_bytes(N, D, d_act, append_one, precision)) return BVLM_EWORKSPACE;
@@ -167,38 +151,29 @@ int bvlm_predictive(const float* E, int64_t N, int64_t D, int64_t lde, const flo
   const int64_t kp = seg * (precision == 3 ? 2 : 1);  // stored operand width: [hi | lo] for the split mode
   Carver cv(ws);
   float* alpha = cv.take<float>(static_cast<size_t>(N));
-  float* rowU = cv.take<float>(static_cast<size_t>(N));
-  float* rowV = cv.take<float>(static_cast<size_t>(N));
-  float* rowM = cv.take<float>(static_cast<size_t>(N));
   float* n2 = cv.take<float>(static_cast<size_t>(N));
   float* pd = cv.take<float>(static_cast<size_t>(N));
   float* esc = cv.take<float>(static_cast<size_t>(N));
   const int64_t e_pitch = operand_pitch(kp);
   __half* E16 = cv.take<__half>(static_cast<size_t>(N) * e_pitch);
+  const int64_t seg8 = pad128(D);
+  uint8_t* A8 = precision == BVLM_PREC_X2F8 ? cv.take<uint8_t>(static_cast<size_t>(N) * 2 * seg8) : nullptr;
   const size_t used = cv.used();
   const float s = expf(logit_scale);
-  // The embedding operand does not depend on the quadratic forms: convert it on a side stream while the activation
-  // conversion + quadratic-form GEMM run on the caller's stream (HBM-bound and tensor-bound work overlap).
-  SideStream* side = side_stream();
+  // One HBM-bound pass over the image rows converts BOTH operands (activations -> fp16 for the quadratic forms,
+  // embeddings -> fp16 [+ fp16 lo | + fp8 compensation terms]); neither depends on the quadratic forms, whose 1/sqrt(E_i)
+  // normalisation is applied by the epilogue of the mean GEMM.
   int rc;
-  // caller's stream: activation conversion (HBM bound) -> [fork] -> quadratic-form GEMM (tensor bound)
-  rc = quadform_impl(Eact, N, d_act, ldact, append_one, Wi16, dA, k_pad, w_scale, alpha,
-                     static_cast<uint8_t*>(ws) + used, ws_bytes - used, st, side != nullptr ? side->fork : nullptr);
+  if (dA != d_act + (append_one ? 1 : 0) || k_pad != pad64(dA)) return BVLM_EINVAL;
+  uint8_t* qws = static_cast<uint8_t*>(ws) + used;
+  Carver qcv(qws);  // same carve as quadform_impl
+  __half* act16 = qcv.take<__half>(static_cast<size_t>(N) * k_pad);
+  float* act_unscale = qcv.take<float>(static_cast<size_t>(N));
+  rc = launch_predictive_embed_prep(E, N, D, lde, delta, precision, E16, seg, e_pitch, A8, seg8, n2, pd, esc, Eact, d_act,
+                                    ldact, append_one, act16, k_pad, act_unscale, st);
   if (rc) return rc;
-  // side stream: embedding conversion (HBM bound), concurrent with the GEMM above
-  cudaStream_t st_e = st;
-  if (side != nullptr) {
-    st_e = side->stream;
-    BVLM_CUDA_TRY(cudaStreamWaitEvent(st_e, side->fork, 0));
-  }
-  rc = launch_predictive_embed_prep(E, N, D, lde, delta, precision, E16, seg, e_pitch, n2, pd, esc, st_e);
-  if (rc) return rc;
-  if (side != nullptr) {
-    BVLM_CUDA_TRY(cudaEventRecord(side->join, st_e));
-    BVLM_CUDA_TRY(cudaStreamWaitEvent(st, side->join, 0));
-  }
-  // E_i, u_i, v_i and the per-row mean factor (T16 carries PRED_OPSCALE, E16 its own power-of-two row scale)
-  rc = launch_predictive_row_scalars(N, alpha, n2, pd, esc, sum_beta, s * s, s / PRED_OPSCALE, rowU, rowV, rowM, st);
+  rc = quadform_impl(Eact, N, d_act, ldact, append_one, Wi16, dA, k_pad, w_scale, alpha, qws, ws_bytes - used, st,
+                     /*converted=*/true);
   if (rc) return rc;
   CUtensorMap tmA, tmB;
   Operand16 opA{E16, N, kp, FMT_F16, e_pitch};
@@ -220,13 +195,32 @@ int bvlm_predictive(const float* E, int64_t N, int64_t D, int64_t lde, const flo
                : make_plan2<PRED_BN>(static_cast<int>(N), static_cast<int>(C), static_cast<int>(kp), SCHED_TILES, 1, FMT_F16);
     if ((rc = operand_tmap<PRED_BN / 2>(&tmB, opB))) return rc;  // each CTA of a pair loads half of the B tile
   }
+  CUtensorMap tmA8, tmB8;
+  if (precision == BVLM_PREC_X2F8) {
+    if (variant == 0) return BVLM_ENOTSUP;  // the FP8 phase lives in the CTA-pair engine
+    if ((rc = make_tmap_2d(&tmA8, A8, TM_U8, static_cast<uint64_t>(2 * seg8), static_cast<uint64_t>(N),
+                           static_cast<uint64_t>(2 * seg8), 128, GEMM_BM, 1)))
+      return rc;
+    if ((rc = make_tmap_2d(&tmB8, T8, TM_U8, static_cast<uint64_t>(2 * seg8), static_cast<uint64_t>(C),
+                           static_cast<uint64_t>(2 * seg8), 128, PRED_BN / 2, 1)))
+      return rc;
+    plan.kb_alt = plan.kb_total;                           // fp16 hi.hi blocks first ...
+    plan.kb_total += static_cast<int>(2 * seg8 / 128);     // ... then [lo8 | e8] x [t8 | tlo8] in E4M3
+    plan.idesc_alt = make_idesc_e4m3(GEMM2_BM, PRED_BN);
+  }
+  const CUtensorMap* pA8 = precision == BVLM_PREC_X2F8 ? &tmA8 : nullptr;
+  const CUtensorMap* pB8 = precision == BVLM_PREC_X2F8 ? &tmB8 : nullptr;
   EpiPredictive<PRED_BN>::Params ep{};
   ep.mean = mean;
   ep.var = var;
   ep.ld = ldo;
-  ep.u = rowU;
-  ep.v = rowV;
-  ep.rm = rowM;
+  ep.alpha = alpha;
+  ep.n2 = n2;
+  ep.pd = pd;
+  ep.esc = esc;
+  ep.sum_beta = sum_beta;
+  ep.s2 = s * s;
+  ep.mean_scale = precision == BVLM_PREC_X2F8 ? s / (128.f * 1024.f) : s / PRED_OPSCALE;
   ep.a = colA;
   ep.b = colB;
   // TMA stores need 16-byte aligned rows; tiny class counts (e.g. C = 10) fall back to direct stores
@@ -241,8 +235,10 @@ int bvlm_predictive(const float* E, int64_t N, int64_t D, int64_t lde, const flo
       return rc;
   }
   if (variant == 0) rc = launch_gemm<PRED_BN, PRED_STAGES, EpiPredictive<PRED_BN>>(tmA, tmB, plan, ep, st, TAG_PREDICTIVE);
-  else if (variant == 1) rc = launch_gemm2<PRED_BN, 6, 4, EpiPredictive<PRED_BN>>(tmA, tmB, plan, ep, st, TAG_PREDICTIVE);
-  else rc = launch_gemm2<PRED_BN, 5, 8, EpiPredictive<PRED_BN>>(tmA, tmB, plan, ep, st, TAG_PREDICTIVE);
+  else if (variant == 1)
+    rc = launch_gemm2<PRED_BN, 6, 4, EpiPredictive<PRED_BN>>(tmA, tmB, plan, ep, st, TAG_PREDICTIVE, pA8, pB8);
+  else
+    rc = launch_gemm2<PRED_BN, 5, 8, EpiPredictive<PRED_BN>>(tmA, tmB, plan, ep, st, TAG_PREDICTIVE, pA8, pB8);
   if (rc) return rc;
   if (probs != nullptr) rc = launch_probit_softmax(mean, var, N, C, ldo, probs, st);
   return rc;

@@ -1,5 +1,7 @@
 #include "prep.cuh"
 
+#include <cuda_fp8.h>
+
 namespace bvlm {
 
 namespace {
@@ -61,7 +63,7 @@ __global__ void __launch_bounds__(ROW_BLOCK)
 k_predictive_row_prep(const float* __restrict__ x, int64_t R, int64_t D, int64_t ld, const float* __restrict__ quad,
                       const float* __restrict__ diag_other, float sum_diag_self, float kappa, float s2, int side,
                       int nsplit, float opscale, __half* __restrict__ packed, int64_t seg_pad, int64_t out_pitch,
-                      float* __restrict__ out0, float* __restrict__ out1) {
+                      uint8_t* __restrict__ packed8, int64_t seg8, float* __restrict__ out0, float* __restrict__ out1) {
   const int64_t row = static_cast<int64_t>(blockIdx.x) * WARPS_PER_BLOCK + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= R) return;
@@ -93,6 +95,18 @@ k_predictive_row_prep(const float* __restrict__ x, int64_t R, int64_t D, int64_t
       *reinterpret_cast<__half2*>(o + seg_pad + j) = lo;
     }
   }
+  if (nsplit == 2) {  // fp16 + fp8 error compensation: [x8 | lo8] (B side); see k_predictive_embed_prep
+    uint8_t* o8 = packed8 + row * 2 * seg8;
+    for (int64_t j = 2 * lane; j < seg8; j += 64) {
+      const float v0 = j < D ? xr[j] * mul : 0.f;
+      const float v1 = j + 1 < D ? xr[j + 1] * mul : 0.f;
+      const float2 hf = __half22float2(__floats2half2_rn(v0, v1));
+      *reinterpret_cast<__nv_fp8x2_storage_t*>(o8 + j) =
+          __nv_cvt_float2_to_fp8x2(make_float2(v0 * 0.03125f, v1 * 0.03125f), __NV_SATFINITE, __NV_E4M3);
+      *reinterpret_cast<__nv_fp8x2_storage_t*>(o8 + seg8 + j) =
+          __nv_cvt_float2_to_fp8x2(make_float2((v0 - hf.x) * 32.f, (v1 - hf.y) * 32.f), __NV_SATFINITE, __NV_E4M3);
+    }
+  }
   if (lane == 0) {
     if (side == 0) {
       out0[row] = s2 * pd / E;
@@ -111,10 +125,38 @@ k_predictive_row_prep(const float* __restrict__ x, int64_t R, int64_t D, int64_t
 __global__ void __launch_bounds__(ROW_BLOCK)
 k_predictive_embed_prep(const float* __restrict__ x, int64_t R, int64_t D, int64_t ld, const float* __restrict__ diag_other,
                         int nsplit, __half* __restrict__ packed, int64_t seg_pad, int64_t out_pitch,
-                        float* __restrict__ n2_out, float* __restrict__ pd_out, float* __restrict__ unscale_out) {
+                        uint8_t* __restrict__ packed8, int64_t seg8, float* __restrict__ n2_out,
+                        float* __restrict__ pd_out, float* __restrict__ unscale_out,
+                        // optional fused activation conversion (the quadratic-form operand of the same row)
+                        const float* __restrict__ act, int64_t d_act, int64_t ld_act, int append_one,
+                        __half* __restrict__ act16, int64_t act_kpad, float* __restrict__ act_unscale) {
   const int64_t row = static_cast<int64_t>(blockIdx.x) * WARPS_PER_BLOCK + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= R) return;
+  if (act != nullptr) {  // fp16 activations with an exact per-row power-of-two scale (as k_rows_to_16)
+    const float* ar = act + row * ld_act;
+    float am = append_one ? 1.f : 0.f;
+    for (int64_t j = lane; j < d_act; j += 32) am = fmaxf(am, fabsf(ar[j]));
+    am = warp_max(am);
+    int ea = 0;
+    if (am > 0.f && isfinite(am)) {
+      int ex;
+      frexpf(am, &ex);
+      ea = 10 - ex;
+      ea = ea < -30 ? -30 : (ea > 30 ? 30 : ea);
+    }
+    const float sa = ldexpf(1.f, ea);
+    if (lane == 0) act_unscale[row] = ldexpf(1.f, -2 * ea);
+    __half* oa = act16 + row * act_kpad;
+    for (int64_t j = 2 * lane; j < act_kpad; j += 64) {
+      float v0 = 0.f, v1 = 0.f;
+      if (j < d_act) v0 = ar[j] * sa;
+      else if (j == d_act && append_one) v0 = sa;
+      if (j + 1 < d_act) v1 = ar[j + 1] * sa;
+      else if (j + 1 == d_act && append_one) v1 = sa;
+      *reinterpret_cast<__half2*>(oa + j) = __floats2half2_rn(v0, v1);
+    }
+  }
   const float* xr = x + row * ld;
   float n2 = 0.f, pd = 0.f, amax = 0.f;
   for (int64_t j = lane; j < D; j += 32) {
@@ -131,10 +173,11 @@ k_predictive_embed_prep(const float* __restrict__ x, int64_t R, int64_t D, int64
   if (amax > 0.f && isfinite(amax)) {
     int ex;
     frexpf(amax, &ex);
-    e = 9 - ex;  // scaled absmax lands in [256, 512)
+    e = (nsplit == 2 ? 8 : 9) - ex;  // scaled absmax lands in [256, 512) ([128, 256) when the values also go to fp8)
     e = e < -60 ? -60 : (e > 60 ? 60 : e);
   }
-  const float sc = ldexpf(1.f, e);
+  // fp16 + fp8 mode: the fp16 operand carries an extra 2^5 so that hi.hi, lo8.t8 and e8.tlo8 share the scale 2^10
+  const float sc = ldexpf(1.f, e) * (nsplit == 2 ? 32.f : 1.f);
   const int64_t pitch = out_pitch > 0 ? out_pitch : seg_pad * (nsplit == 3 ? 2 : 1);
   __half* o = packed + row * pitch;
   for (int64_t j = 2 * lane; j < seg_pad; j += 64) {
@@ -147,10 +190,22 @@ k_predictive_embed_prep(const float* __restrict__ x, int64_t R, int64_t D, int64
       *reinterpret_cast<__half2*>(o + seg_pad + j) = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
     }
   }
+  if (nsplit == 2) {  // A side of the FP8 phase: [lo8 | x8], paired with the target's [t8 | tlo8]
+    uint8_t* o8 = packed8 + row * 2 * seg8;
+    for (int64_t j = 2 * lane; j < seg8; j += 64) {
+      const float v0 = j < D ? xr[j] * sc : 0.f;
+      const float v1 = j + 1 < D ? xr[j + 1] * sc : 0.f;
+      const float2 hf = __half22float2(__floats2half2_rn(v0, v1));
+      *reinterpret_cast<__nv_fp8x2_storage_t*>(o8 + j) =
+          __nv_cvt_float2_to_fp8x2(make_float2((v0 - hf.x) * 32.f, (v1 - hf.y) * 32.f), __NV_SATFINITE, __NV_E4M3);
+      *reinterpret_cast<__nv_fp8x2_storage_t*>(o8 + seg8 + j) =
+          __nv_cvt_float2_to_fp8x2(make_float2(v0 * 0.03125f, v1 * 0.03125f), __NV_SATFINITE, __NV_E4M3);
+    }
+  }
   if (lane == 0) {
     n2_out[row] = n2;
     pd_out[row] = pd;
-    unscale_out[row] = ldexpf(1.f, -e);
+    unscale_out[row] = ldexpf(1.f, -e);  // (the extra 2^5 of the fp16 + fp8 mode is folded into the caller's mean_scale)
   }
 }
 
@@ -546,24 +601,31 @@ int launch_rows_to_16(const float* in, int64_t R, int64_t d, int64_t ld, int app
 
 int launch_predictive_row_prep(const float* x, int64_t R, int64_t D, int64_t ld, const float* quad,
                                const float* diag_other, float sum_diag_self, float kappa, float s2, int side,
-                               int nsplit, float opscale, __half* packed, int64_t seg_pad, int64_t out_pitch, float* out0,
-                               float* out1, cudaStream_t st) {
+                               int nsplit, float opscale, __half* packed, int64_t seg_pad, int64_t out_pitch,
+                               uint8_t* packed8, int64_t seg8, float* out0, float* out1, cudaStream_t st) {
   if (R <= 0) return BVLM_OK;
-  if ((nsplit != 1 && nsplit != 3) || seg_pad < D || (seg_pad & 1)) return BVLM_EINVAL;
+  if ((nsplit != 1 && nsplit != 2 && nsplit != 3) || seg_pad < D || (seg_pad & 1)) return BVLM_EINVAL;
+  if (nsplit == 2 && (packed8 == nullptr || seg8 < D || (seg8 & 1))) return BVLM_EINVAL;
   k_predictive_row_prep<<<row_grid(R), ROW_BLOCK, 0, st>>>(x, R, D, ld, quad, diag_other, sum_diag_self, kappa, s2, side,
-                                                           nsplit, opscale, packed, seg_pad, out_pitch, out0, out1);
+                                                           nsplit, opscale, packed, seg_pad, out_pitch, packed8, seg8, out0,
+                                                           out1);
   count_launch();
   BVLM_CUDA_TRY(cudaGetLastError());
   return BVLM_OK;
 }
 
 int launch_predictive_embed_prep(const float* x, int64_t R, int64_t D, int64_t ld, const float* diag_other, int nsplit,
-                                 __half* packed, int64_t seg_pad, int64_t out_pitch, float* n2, float* pd, float* unscale,
-                                 cudaStream_t st) {
+                                 __half* packed, int64_t seg_pad, int64_t out_pitch, uint8_t* packed8, int64_t seg8, float* n2,
+                                 float* pd, float* unscale, const float* act, int64_t d_act, int64_t ld_act, int append_one,
+                                 __half* act16, int64_t act_kpad, float* act_unscale, cudaStream_t st) {
   if (R <= 0) return BVLM_OK;
-  if ((nsplit != 1 && nsplit != 3) || seg_pad < D || (seg_pad & 1)) return BVLM_EINVAL;
-  k_predictive_embed_prep<<<row_grid(R), ROW_BLOCK, 0, st>>>(x, R, D, ld, diag_other, nsplit, packed, seg_pad, out_pitch, n2,
-                                                             pd, unscale);
+  if (act != nullptr && (act16 == nullptr || act_unscale == nullptr || act_kpad < d_act + (append_one ? 1 : 0) || (act_kpad & 1)))
+    return BVLM_EINVAL;
+  if ((nsplit != 1 && nsplit != 2 && nsplit != 3) || seg_pad < D || (seg_pad & 1)) return BVLM_EINVAL;
+  if (nsplit == 2 && (packed8 == nullptr || seg8 < D || (seg8 & 1))) return BVLM_EINVAL;
+  k_predictive_embed_prep<<<row_grid(R), ROW_BLOCK, 0, st>>>(x, R, D, ld, diag_other, nsplit, packed, seg_pad, out_pitch,
+                                                             packed8, seg8, n2, pd, unscale, act, d_act, ld_act, append_one,
+                                                             act16, act_kpad, act_unscale);
   count_launch();
   BVLM_CUDA_TRY(cudaGetLastError());
   return BVLM_OK;

@@ -18,14 +18,19 @@ int launch_rows_to_16(const float* in, int64_t R, int64_t d, int64_t ld, int app
 //   side 1 (target/text) :  out0 = quad_r / E_r ,  out1 = (quad_r * kappa + sum_d diag_other_d * x_d^2) / E_r
 int launch_predictive_row_prep(const float* x, int64_t R, int64_t D, int64_t ld, const float* quad,
                                const float* diag_other, float sum_diag_self, float kappa, float s2, int side,
-                               int nsplit, float opscale, __half* packed, int64_t seg_pad, int64_t out_pitch, float* out0,
-                               float* out1, cudaStream_t st);
+                               int nsplit, float opscale, __half* packed, int64_t seg_pad, int64_t out_pitch,
+                               uint8_t* packed8, int64_t seg8, float* out0, float* out1, cudaStream_t st);
 
 // Source side of the predictive, independent of the quadratic forms (so it can overlap them): packed = fp16 [hi | lo] of
 // x_r * 2^k_r (exact power-of-two row scale), n2 = |x_r|^2, pd = sum_d x_rd^2 diag_other_d, unscale = 2^-k_r.
+// nsplit 2 (fp16 + fp8 error compensation): packed = fp16(x 2^k 32) [R, seg_pad]; packed8 [R, 2*seg8] E4M3 =
+// [32 (v - fp16(v)) | v / 32] for the source side (embed prep) and [v / 32 | 32 (v - fp16(v))] for the target side.
 int launch_predictive_embed_prep(const float* x, int64_t R, int64_t D, int64_t ld, const float* diag_other, int nsplit,
-                                 __half* packed, int64_t seg_pad, int64_t out_pitch, float* n2, float* pd, float* unscale,
-                                 cudaStream_t st);
+                                 __half* packed, int64_t seg_pad, int64_t out_pitch, uint8_t* packed8, int64_t seg8, float* n2,
+                                 float* pd, float* unscale, const float* act, int64_t d_act, int64_t ld_act, int append_one,
+                                 __half* act16, int64_t act_kpad, float* act_unscale, cudaStream_t st);
+// (act != NULL additionally converts the row's activations: act16 [R, act_kpad] fp16 with an exact per-row power-of-two
+//  scale, act_unscale[r] = 2^(-2 e_r) -- the same operand launch_rows_to_16(row_pow2_scale = 1) produces.)
 // E = n2 + alpha sum_beta; u = s2 pd / E; v = s2 alpha / E; rm = mean_scale * unscale / sqrt(E)   (vlm.py:665-684)
 int launch_predictive_row_scalars(int64_t R, const float* alpha, const float* n2, const float* pd, const float* unscale,
                                   float sum_beta, float s2, float mean_scale, float* u, float* v, float* rm, cudaStream_t st);

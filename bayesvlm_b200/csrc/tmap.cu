@@ -27,6 +27,7 @@ CUtensorMapDataType to_cu_dtype(int dt) {
   switch (dt) {
     case TM_F16: return CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
     case TM_BF16: return CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    case TM_U8: return CU_TENSOR_MAP_DATA_TYPE_UINT8;
     default: return CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   }
 }

@@ -6,7 +6,7 @@
 
 namespace bvlm {
 
-enum TmapDtype : int { TM_F16 = 0, TM_BF16 = 1, TM_F32 = 2 };
+enum TmapDtype : int { TM_F16 = 0, TM_BF16 = 1, TM_F32 = 2, TM_U8 = 3 };
 
 // 2-D row-major tensor [outer, inner] with row pitch `pitch_bytes`; box = [box_outer, box_inner].
 int make_tmap_2d(CUtensorMap* out, const void* base, int dtype, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,

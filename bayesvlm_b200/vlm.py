@@ -18,7 +18,10 @@ from . import _lib
 from ._lib import lib
 from .hessians import KroneckerFactorizedCovariance
 
-_PRECISIONS = {"fp16x3": _lib.PREC_X3, "fp16": _lib.PREC_X1, "x3": _lib.PREC_X3, "x1": _lib.PREC_X1}
+# mean-logit GEMM: "fp16x3" = hi/lo split, three fp16 tensor-core products (~2^-22); "fp16+fp8" = fp16 hi.hi plus the two
+# error-compensation products in FP8 at twice the rate (~2^-15, 2/3 of the cost); "fp16" = single pass (~2^-11)
+_PRECISIONS = {"fp16x3": _lib.PREC_X3, "fp16+fp8": _lib.PREC_X2F8, "fp16": _lib.PREC_X1, "x3": _lib.PREC_X3,
+               "x2f8": _lib.PREC_X2F8, "x1": _lib.PREC_X1}
 
 
 class EncoderResult:
@@ -238,7 +241,7 @@ class CLIP(torch.nn.Module):
     target_projection_has_bias = False
 
     def __init__(self, logit_scale: float, logit_bias: float = 0, source_covariance=None, target_covariance=None,
-                 device: Optional[str] = None, precision: str = "fp16x3"):
+                 device: Optional[str] = None, precision: str = "fp16+fp8"):
         super().__init__()
         self.logit_scale = torch.nn.Parameter(torch.ones([], device=device) * logit_scale)
         self.logit_bias = torch.nn.Parameter(torch.ones([], device=device) * logit_bias)
@@ -316,6 +319,8 @@ class CLIP(torch.nn.Module):
             raise ValueError(f"target activations have {d_act}(+{bias}) features but A_inv is {tgt.factor.dA}^2")
         seg = int(lib.bvlm_padded_k(d))
         t16 = torch.empty((c, seg * (2 if prec == _lib.PREC_X3 else 1)), dtype=torch.float16, device=emb.device)
+        t8 = (torch.empty((c, int(lib.bvlm_predictive_t8_cols(d))), dtype=torch.uint8, device=emb.device)
+              if prec == _lib.PREC_X2F8 else None)
         c_pad = int(lib.bvlm_padded_cols(c))  # the epilogue reads whole 256-column tiles
         col_a = torch.empty(c_pad, dtype=torch.float32, device=emb.device)
         col_b = torch.empty(c_pad, dtype=torch.float32, device=emb.device)
@@ -324,10 +329,11 @@ class CLIP(torch.nn.Module):
         rc = lib.bvlm_predictive_target_prepare(
             _lib.ptr(emb), c, d, emb.stride(0), _lib.ptr(act), d_act, act.stride(0), bias, _lib.ptr(tgt.factor.w16),
             tgt.factor.dA, tgt.factor.k_pad, tgt.factor.scale, _lib.ptr(src.diag_b), sum_delta, kappa, prec,
-            _lib.ptr(t16), _lib.ptr(col_a), _lib.ptr(col_b), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(emb.device))
+            _lib.ptr(t16), _lib.ptr(t8), _lib.ptr(col_a), _lib.ptr(col_b), _lib.ptr(ws), ws.numel(),
+            _lib.stream_ptr(emb.device))
         _lib.check(rc, "bvlm_predictive_target_prepare")
-        self._target_cache = (key, target.embeds, target.activations, t16, col_a, col_b)
-        return t16, col_a, col_b
+        self._target_cache = (key, target.embeds, target.activations, t16, t8, col_a, col_b)
+        return t16, t8, col_a, col_b
 
     def _smith_torch(self, source_results: EncoderResult, target_results: EncoderResult):
         """Differentiable on-device torch expression of the predictive, used only when an input requires grad
@@ -383,7 +389,7 @@ class CLIP(torch.nn.Module):
         ([n, C] fp32 views with unit column stride) on the current stream."""
         prec = _PRECISIONS[self.precision]
         src, tgt, (sum_beta, sum_delta, kappa) = self._sides()
-        t16, col_a, col_b = self._target_side(target_results, prec)
+        t16, t8, col_a, col_b = self._target_side(target_results, prec)
         n, d = emb.shape
         c = target_results.embeds.shape[0]
         if target_results.embeds.shape[1] != d:
@@ -401,7 +407,7 @@ class CLIP(torch.nn.Module):
         rc = lib.bvlm_predictive(
             _lib.ptr(emb), n, d, emb.stride(0), _lib.ptr(act), d_act, act.stride(0), bias, _lib.ptr(src.factor.w16),
             src.factor.dA, src.factor.k_pad, src.factor.scale, _lib.ptr(tgt.diag_b), sum_beta,
-            float(self.logit_scale.detach()), _lib.ptr(t16), _lib.ptr(col_a), _lib.ptr(col_b), c, prec,
+            float(self.logit_scale.detach()), _lib.ptr(t16), _lib.ptr(t8), _lib.ptr(col_a), _lib.ptr(col_b), c, prec,
             _lib.ptr(mean), _lib.ptr(var), _lib.ptr(probs), mean.stride(0), _lib.ptr(ws), ws.numel(),
             _lib.stream_ptr(emb.device))
         _lib.check(rc, "bvlm_predictive")

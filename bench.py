@@ -216,7 +216,8 @@ def run_b200(args, rank, world, local_rank):
     cfg = PRED
     t = predictive_inputs(cfg, rank)
     Ai, Bi, At, Bt = covariances(t, cfg, dev)
-    model = CLIP(logit_scale=LS, device=dev)  # default precision: hi/lo split mean GEMM (~fp32 logits)
+    model = CLIP(logit_scale=LS, device=dev) if args.precision is None else CLIP(logit_scale=LS, device=dev,
+                                                                                 precision=args.precision)
     model.set_covariances(KFC(Ai, Bi), KFC(At, Bt))
     img = EncoderResult(t["img_e"].to(dev), t["img_a"].to(dev))
     txt = EncoderResult(t["txt_e"].to(dev), t["txt_a"].to(dev))
@@ -385,6 +386,7 @@ def main():
     ap.add_argument("--e2e-batch", type=int, default=6250)
     ap.add_argument("--kfac-class-batches", type=int, default=2, help="class batches of 32768 per GPU per KFAC step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default=None, help="mean-logit GEMM precision: fp16x3 | fp16+fp8 | fp16 (default: the library's)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

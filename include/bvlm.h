@@ -34,6 +34,8 @@ extern "C" {
  * BVLM_PREC_X1: single fp16 pass (unit-norm embeddings as they are; raw activations with per-feature power-of-two scaling).
  * BVLM_PREC_X3: hi/lo split, three tensor-core passes (a_hi b_hi + a_lo b_hi + a_hi b_lo), ~2^-22 relative. */
 #define BVLM_PREC_X1 1
+#define BVLM_PREC_X2F8 2 /* predictive mean only: fp16 hi.hi + the two error-compensation terms lo.hi, hi.lo in FP8 (E4M3)
+                            at twice the fp16 tensor rate; ~2^-15 relative, i.e. 2/3 of the cost of BVLM_PREC_X3 */
 #define BVLM_PREC_X3 3
 
 const char* bvlm_version(void);
@@ -97,15 +99,17 @@ int bvlm_quadform(const float* act, int64_t n, int64_t d, int64_t ld, int append
  * (logit_bias is NOT added to the probabilistic mean -- vlm.py:681-684.)
  * --------------------------------------------------------------------------------------------------------- */
 size_t bvlm_predictive_target_workspace_bytes(int64_t C, int64_t D, int64_t d_act, int append_one);
+/* T8: [C, bvlm_predictive_t8_cols(D)] bytes of E4M3 operands, only for BVLM_PREC_X2F8 (NULL otherwise). */
+int64_t bvlm_predictive_t8_cols(int64_t D);
 int bvlm_predictive_target_prepare(const float* T, int64_t C, int64_t D, int64_t ldt, const float* Tact, int64_t d_act,
                                    int64_t ldact, int append_one, const void* Wt16, int64_t dA, int64_t k_pad,
                                    float w_scale, const float* beta, float sum_delta, float kappa, int precision,
-                                   void* T16, float* colA, float* colB, void* ws, size_t ws_bytes, void* stream);
+                                   void* T16, void* T8, float* colA, float* colB, void* ws, size_t ws_bytes, void* stream);
 size_t bvlm_predictive_workspace_bytes(int64_t N, int64_t D, int64_t d_act, int append_one, int precision);
 int bvlm_predictive(const float* E, int64_t N, int64_t D, int64_t lde, const float* Eact, int64_t d_act, int64_t ldact,
                     int append_one, const void* Wi16, int64_t dA, int64_t k_pad, float w_scale, const float* delta,
-                    float sum_beta, float logit_scale, const void* T16, const float* colA, const float* colB, int64_t C,
-                    int precision, float* mean, float* var, float* probs, int64_t ldo, void* ws, size_t ws_bytes,
+                    float sum_beta, float logit_scale, const void* T16, const void* T8, const float* colA, const float* colB,
+                    int64_t C, int precision, float* mean, float* var, float* probs, int64_t ldo, void* ws, size_t ws_bytes,
                     void* stream);
 
 /* P3 -- standalone canonical probit softmax (scripts/zeroshot.py:119-120). */
