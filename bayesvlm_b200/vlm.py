@@ -258,6 +258,17 @@ class CLIP(torch.nn.Module):
     def device(self):
         return self.logit_scale.data.device
 
+    def _logit_scale_value(self) -> float:
+        """Host copy of the (log-space) logit scale, refreshed only when the parameter is modified: reading a CUDA
+        scalar synchronises the stream, which would serialise every kernel call behind the previous one."""
+        p = self.logit_scale
+        key = (p._version, p.data_ptr())
+        cached = getattr(self, "_ls_cache", None)
+        if cached is None or cached[0] != key:
+            cached = (key, float(p.detach()))
+            self._ls_cache = cached
+        return cached[1]
+
     def set_covariances(self, source_covariance=None, target_covariance=None):
         def _own(cov):
             if cov is None:
@@ -407,7 +418,7 @@ class CLIP(torch.nn.Module):
         rc = lib.bvlm_predictive(
             _lib.ptr(emb), n, d, emb.stride(0), _lib.ptr(act), d_act, act.stride(0), bias, _lib.ptr(src.factor.w16),
             src.factor.dA, src.factor.k_pad, src.factor.scale, _lib.ptr(tgt.diag_b), sum_beta,
-            float(self.logit_scale.detach()), _lib.ptr(t16), _lib.ptr(t8), _lib.ptr(col_a), _lib.ptr(col_b), c, prec,
+            self._logit_scale_value(), _lib.ptr(t16), _lib.ptr(t8), _lib.ptr(col_a), _lib.ptr(col_b), c, prec,
             _lib.ptr(mean), _lib.ptr(var), _lib.ptr(probs), mean.stride(0), _lib.ptr(ws), ws.numel(),
             _lib.stream_ptr(emb.device))
         _lib.check(rc, "bvlm_predictive")
