@@ -209,6 +209,133 @@ k_predictive_embed_prep(const float* __restrict__ x, int64_t R, int64_t D, int64
   }
 }
 
+// Register-resident variant of k_predictive_embed_prep for 16-byte aligned rows: every lane keeps its float4 slices of
+// the row in registers (one global read per element, 512 contiguous bytes per warp instruction), EV / AV = float4 slices
+// per lane for the embedding / activation row (rows up to 128*EV / 128*AV floats).
+template <int EV, int AV>
+__global__ void __launch_bounds__(ROW_BLOCK)
+k_predictive_prep_vec(const float* __restrict__ x, int64_t R, int64_t D, int64_t ld, const float* __restrict__ diag_other,
+                      int nsplit, __half* __restrict__ packed, int64_t seg_pad, int64_t out_pitch,
+                      uint8_t* __restrict__ packed8, int64_t seg8, float* __restrict__ n2_out, float* __restrict__ pd_out,
+                      float* __restrict__ unscale_out, const float* __restrict__ act, int64_t d_act, int64_t ld_act,
+                      int append_one, __half* __restrict__ act16, int64_t act_kpad, float* __restrict__ act_unscale) {
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= R) return;
+  // ---------------- activations -> fp16, exact per-row power-of-two scale
+  {
+    const float* ar = act + row * ld_act;
+    float4 a[AV];
+    float am = append_one ? 1.f : 0.f;
+#pragma unroll
+    for (int i = 0; i < AV; ++i) {
+      const int64_t c = (static_cast<int64_t>(i) * 32 + lane) * 4;
+      a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c + 3 < d_act) a[i] = __ldg(reinterpret_cast<const float4*>(ar + c));
+      else if (c < d_act) {
+        a[i].x = ar[c];
+        if (c + 1 < d_act) a[i].y = ar[c + 1];
+        if (c + 2 < d_act) a[i].z = ar[c + 2];
+      }
+      am = fmaxf(am, fmaxf(fmaxf(fabsf(a[i].x), fabsf(a[i].y)), fmaxf(fabsf(a[i].z), fabsf(a[i].w))));
+    }
+    am = warp_max(am);
+    int ea = 0;
+    if (am > 0.f && isfinite(am)) {
+      int ex;
+      frexpf(am, &ex);
+      ea = 10 - ex;
+      ea = ea < -30 ? -30 : (ea > 30 ? 30 : ea);
+    }
+    const float sa = ldexpf(1.f, ea);
+    if (lane == 0) act_unscale[row] = ldexpf(1.f, -2 * ea);
+    __half* oa = act16 + row * act_kpad;
+#pragma unroll
+    for (int i = 0; i < AV; ++i) {
+      const int64_t c = (static_cast<int64_t>(i) * 32 + lane) * 4;
+      if (c >= act_kpad) continue;
+      float v[4] = {a[i].x * sa, a[i].y * sa, a[i].z * sa, a[i].w * sa};
+      if (append_one && d_act >= c && d_act < c + 4) v[d_act - c] = sa;
+      const __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+      uint2 pk;
+      pk.x = *reinterpret_cast<const uint32_t*>(&h0);
+      pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+      *reinterpret_cast<uint2*>(oa + c) = pk;
+    }
+  }
+  // ---------------- embeddings -> fp16 (+ lo fp16 | + fp8 compensation terms), row statistics
+  const float* xr = x + row * ld;
+  float4 e[EV];
+  float n2 = 0.f, pd = 0.f, amax = 0.f;
+#pragma unroll
+  for (int i = 0; i < EV; ++i) {
+    const int64_t c = (static_cast<int64_t>(i) * 32 + lane) * 4;
+    e[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 dl = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c + 3 < D) {
+      e[i] = __ldg(reinterpret_cast<const float4*>(xr + c));
+      dl = __ldg(reinterpret_cast<const float4*>(diag_other + c));
+    } else if (c < D) {
+      e[i].x = xr[c];
+      dl.x = diag_other[c];
+      if (c + 1 < D) e[i].y = xr[c + 1], dl.y = diag_other[c + 1];
+      if (c + 2 < D) e[i].z = xr[c + 2], dl.z = diag_other[c + 2];
+    }
+    const float4 q = make_float4(e[i].x * e[i].x, e[i].y * e[i].y, e[i].z * e[i].z, e[i].w * e[i].w);
+    n2 += (q.x + q.y) + (q.z + q.w);
+    pd = fmaf(q.x, dl.x, fmaf(q.y, dl.y, fmaf(q.z, dl.z, fmaf(q.w, dl.w, pd))));
+    amax = fmaxf(amax, fmaxf(fmaxf(fabsf(e[i].x), fabsf(e[i].y)), fmaxf(fabsf(e[i].z), fabsf(e[i].w))));
+  }
+  n2 = warp_sum(n2);
+  pd = warp_sum(pd);
+  amax = warp_max(amax);
+  int ee = 0;
+  if (amax > 0.f && isfinite(amax)) {
+    int ex;
+    frexpf(amax, &ex);
+    ee = (nsplit == 2 ? 8 : 9) - ex;
+    ee = ee < -60 ? -60 : (ee > 60 ? 60 : ee);
+  }
+  const float sc = ldexpf(1.f, ee) * (nsplit == 2 ? 32.f : 1.f);
+  const int64_t pitch = out_pitch > 0 ? out_pitch : seg_pad * (nsplit == 3 ? 2 : 1);
+  __half* o = packed + row * pitch;
+  uint8_t* o8 = nsplit == 2 ? packed8 + row * 2 * seg8 : nullptr;
+#pragma unroll
+  for (int i = 0; i < EV; ++i) {
+    const int64_t c = (static_cast<int64_t>(i) * 32 + lane) * 4;
+    const float v0 = e[i].x * sc, v1 = e[i].y * sc, v2 = e[i].z * sc, v3 = e[i].w * sc;
+    const __half2 h0 = __floats2half2_rn(v0, v1), h1 = __floats2half2_rn(v2, v3);
+    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+    if (c < seg_pad) {
+      uint2 pk;
+      pk.x = *reinterpret_cast<const uint32_t*>(&h0);
+      pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+      *reinterpret_cast<uint2*>(o + c) = pk;
+      if (nsplit == 3) {
+        const __half2 l0 = __floats2half2_rn(v0 - f0.x, v1 - f0.y), l1 = __floats2half2_rn(v2 - f1.x, v3 - f1.y);
+        pk.x = *reinterpret_cast<const uint32_t*>(&l0);
+        pk.y = *reinterpret_cast<const uint32_t*>(&l1);
+        *reinterpret_cast<uint2*>(o + seg_pad + c) = pk;
+      }
+    }
+    if (nsplit == 2 && c < seg8) {
+      const uint32_t lo8 =
+          static_cast<uint32_t>(__nv_cvt_float2_to_fp8x2(make_float2((v0 - f0.x) * 32.f, (v1 - f0.y) * 32.f), __NV_SATFINITE, __NV_E4M3)) |
+          (static_cast<uint32_t>(__nv_cvt_float2_to_fp8x2(make_float2((v2 - f1.x) * 32.f, (v3 - f1.y) * 32.f), __NV_SATFINITE, __NV_E4M3)) << 16);
+      const uint32_t x8 =
+          static_cast<uint32_t>(__nv_cvt_float2_to_fp8x2(make_float2(v0 * 0.03125f, v1 * 0.03125f), __NV_SATFINITE, __NV_E4M3)) |
+          (static_cast<uint32_t>(__nv_cvt_float2_to_fp8x2(make_float2(v2 * 0.03125f, v3 * 0.03125f), __NV_SATFINITE, __NV_E4M3)) << 16);
+      *reinterpret_cast<uint32_t*>(o8 + c) = lo8;
+      *reinterpret_cast<uint32_t*>(o8 + seg8 + c) = x8;
+    }
+  }
+  if (lane == 0) {
+    n2_out[row] = n2;
+    pd_out[row] = pd;
+    unscale_out[row] = ldexpf(1.f, -ee);
+  }
+}
+
 // E_i = |e_i|^2 + alpha_i sum(beta);  u_i = s^2 (e_i^2 . delta) / E_i;  v_i = s^2 alpha_i / E_i;
 // rm_i = mean_scale * 2^-k_i / sqrt(E_i)   (per-row factor that turns the raw accumulator into the mean logit)
 __global__ void k_predictive_row_scalars(int64_t R, const float* __restrict__ alpha, const float* __restrict__ n2,
@@ -623,9 +750,27 @@ int launch_predictive_embed_prep(const float* x, int64_t R, int64_t D, int64_t l
     return BVLM_EINVAL;
   if ((nsplit != 1 && nsplit != 2 && nsplit != 3) || seg_pad < D || (seg_pad & 1)) return BVLM_EINVAL;
   if (nsplit == 2 && (packed8 == nullptr || seg8 < D || (seg8 & 1))) return BVLM_EINVAL;
-  k_predictive_embed_prep<<<row_grid(R), ROW_BLOCK, 0, st>>>(x, R, D, ld, diag_other, nsplit, packed, seg_pad, out_pitch,
-                                                             packed8, seg8, n2, pd, unscale, act, d_act, ld_act, append_one,
-                                                             act16, act_kpad, act_unscale);
+  // fast path: 16-byte aligned rows that fit the register-resident kernel (covers every model of the reference)
+  const auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  const int64_t ecols = seg_pad > seg8 && nsplit == 2 ? seg_pad : (nsplit == 2 ? seg8 : seg_pad);
+  const bool vec_ok = act != nullptr && al16(x) && al16(act) && al16(diag_other) && al16(packed) && al16(act16) &&
+                      (ld % 4) == 0 && (ld_act % 4) == 0 && (seg_pad % 4) == 0 && (act_kpad % 4) == 0 &&
+                      ((out_pitch > 0 ? out_pitch : seg_pad) % 4) == 0 && (nsplit != 2 || ((seg8 % 4) == 0 && al16(packed8))) &&
+                      ecols <= 1024 && act_kpad <= 3200;
+  if (vec_ok) {
+#define BVLM_PREP_VEC(EVV, AVV)                                                                                            \
+    k_predictive_prep_vec<EVV, AVV><<<row_grid(R), ROW_BLOCK, 0, st>>>(x, R, D, ld, diag_other, nsplit, packed, seg_pad,      \
+                                                                       out_pitch, packed8, seg8, n2, pd, unscale, act, d_act, \
+                                                                       ld_act, append_one, act16, act_kpad, act_unscale)
+    if (act_kpad <= 1024) BVLM_PREP_VEC(8, 8);
+    else if (act_kpad <= 1536) BVLM_PREP_VEC(8, 12);
+    else BVLM_PREP_VEC(8, 25);
+#undef BVLM_PREP_VEC
+  } else {
+    k_predictive_embed_prep<<<row_grid(R), ROW_BLOCK, 0, st>>>(x, R, D, ld, diag_other, nsplit, packed, seg_pad, out_pitch,
+                                                               packed8, seg8, n2, pd, unscale, act, d_act, ld_act, append_one,
+                                                               act16, act_kpad, act_unscale);
+  }
   count_launch();
   BVLM_CUDA_TRY(cudaGetLastError());
   return BVLM_OK;
