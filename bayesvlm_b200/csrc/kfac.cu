@@ -274,7 +274,7 @@ extern "C" {
 size_t bvlm_syrk_workspace_bytes(int64_t n, int64_t d, int append_one, int precision) {
   (void)precision;
   const int64_t dA = d + (append_one ? 1 : 0);
-  return static_cast<size_t>(round_up_i64(dA * pad64(n) * 2, 256)) + 3 * static_cast<size_t>(round_up_i64(dA * 4, 256)) + 512;
+  return static_cast<size_t>(round_up_i64(n * pad64(dA) * 2, 256)) + 3 * static_cast<size_t>(round_up_i64(dA * 4, 256)) + 512;
 }
 
 int bvlm_syrk_f32acc(const float* X, int64_t n, int64_t d, int64_t ldx, int append_one, int precision, float* C,
@@ -286,9 +286,9 @@ int bvlm_syrk_f32acc(const float* X, int64_t n, int64_t d, int64_t ldx, int appe
   if (ws_bytes < bvlm_syrk_workspace_bytes(n, d, append_one, precision)) return BVLM_EWORKSPACE;
   if ((reinterpret_cast<uintptr_t>(ws) & 255) != 0) return BVLM_EINVAL;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int64_t Kp = pad64(n);
+  const int64_t dP = pad64(dA);
   Carver cv(ws);
-  __half* Xt16 = cv.take<__half>(static_cast<size_t>(dA) * Kp);
+  __half* X16 = cv.take<__half>(static_cast<size_t>(n) * dP);
   float* scale = cv.take<float>(static_cast<size_t>(dA));
   float* unscale = cv.take<float>(static_cast<size_t>(dA));
   unsigned int* amax = cv.take<unsigned int>(static_cast<size_t>(dA));
@@ -298,22 +298,22 @@ int bvlm_syrk_f32acc(const float* X, int64_t n, int64_t d, int64_t ldx, int appe
   }
   // per-feature power-of-two scaling keeps every feature inside fp16's normal range whatever its magnitude
   if ((rc = launch_col_pow2_scale(X, n, d, ldx, append_one, amax, scale, unscale, st))) return rc;
-  // [X 1]^T as an fp16 K-major operand: rows = features, K = samples
-  if ((rc = launch_transpose_to_16(X, n, d, ldx, nullptr, 0, scale, 1.f, append_one, FMT_F16, Xt16, Kp, 0, Kp, st)))
-    return rc;
-  CUtensorMap tmA, tmB;
-  Operand16 op{Xt16, dA, Kp, FMT_F16};
-  if ((rc = operand_tmap<GEMM_BM>(&tmA, op))) return rc;
-  if ((rc = operand_tmap<SYRK_BN>(&tmB, op))) return rc;
-  const int m_tiles = static_cast<int>(ceil_div_i64(dA, GEMM_BM));
-  const int tri = m_tiles * (m_tiles + 1) / 2;
-  int splits = device_sm_count() / tri;
+  // [X 1] as a row-major fp16 copy: it IS the MN-major operand of [X 1]^T [X 1] (rows = samples = K) -- no transpose
+  if ((rc = launch_scale_cols_f16(X, n, d, ldx, scale, append_one, X16, dP, st))) return rc;
+  CUtensorMap tm;
+  if ((rc = operand_tmap_mn(&tm, X16, n, dA, dP, FMT_F16))) return rc;
+  constexpr int BN = 256;  // square 256 x 256 tiles on CTA pairs; only the lower triangle of tiles is computed
+  const int kp = static_cast<int>(pad64(n));
+  GemmPlan plan = make_plan2<BN>(static_cast<int>(dA), static_cast<int>(dA), kp, SCHED_TRI_TILES, 1, FMT_F16);
+  const int tri = plan.m_tiles * (plan.m_tiles + 1) / 2;
+  int splits = (device_sm_count() / 2) / tri;
   if (splits < 1) splits = 1;
-  GemmPlan plan = make_plan<SYRK_BN>(static_cast<int>(dA), static_cast<int>(dA), static_cast<int>(Kp), SCHED_TRI_TILES,
-                                     splits, FMT_F16, FMT_F16);
+  if (splits > plan.kb_total) splits = plan.kb_total;
+  plan.splits = splits;
+  plan.idesc = make_idesc_f16(GEMM2_BM, BN, FMT_F16, FMT_F16, 1, 1);
   // lower triangle accumulated with red.global.add, then mirrored: C stays exactly symmetric
-  EpiStoreF32<SYRK_BN>::Params ep{C, ldc, alpha, 1, 1, nullptr, unscale};
-  if ((rc = launch_gemm<SYRK_BN, SYRK_STAGES, EpiStoreF32<SYRK_BN>>(tmA, tmB, plan, ep, st, TAG_SYRK))) return rc;
+  EpiStoreF32<BN>::Params ep{C, ldc, alpha, 1, 1, nullptr, unscale};
+  if ((rc = launch_gemm2<BN, 6, 4, EpiStoreF32<BN>, true, true>(tm, tm, plan, ep, st, TAG_SYRK))) return rc;
   return launch_symmetrize_scale(C, dA, ldc, 1.0f, st);
 }
 

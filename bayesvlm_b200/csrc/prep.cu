@@ -639,6 +639,25 @@ __global__ void __launch_bounds__(256) k_col_absmax(const float* __restrict__ x,
   if (m > 0.f && isfinite(m)) atomicMax(amax_bits + j, __float_as_uint(m));
 }
 
+// out[r, j] = fp16(x[r, j] * scale[j]) row-major [n, ldo] (a ones column at j == d when append_one, zeros up to ldo):
+// the MN-major SYRK operand -- no transpose
+__global__ void __launch_bounds__(256)
+k_scale_cols_f16(const float* __restrict__ x, int64_t n, int64_t d, int64_t ld, const float* __restrict__ scale,
+                 int append_one, __half* __restrict__ out, int64_t ldo) {
+  const int64_t r = static_cast<int64_t>(blockIdx.y) * 8 + threadIdx.y;
+  if (r >= n) return;
+  const float* xr = x + r * ld;
+  __half* o = out + r * ldo;
+  for (int64_t j = 2 * (static_cast<int64_t>(blockIdx.x) * 32 + threadIdx.x); j < ldo; j += 64 * gridDim.x) {
+    float v0 = 0.f, v1 = 0.f;
+    if (j < d) v0 = xr[j] * scale[j];
+    else if (j == d && append_one) v0 = scale[j];
+    if (j + 1 < d) v1 = xr[j + 1] * scale[j + 1];
+    else if (j + 1 == d && append_one) v1 = scale[j + 1];
+    *reinterpret_cast<__half2*>(o + j) = __floats2half2_rn(v0, v1);
+  }
+}
+
 // scale[j] = 2^e with absmax * 2^e in [512, 1024); unscale[j] = 2^-e. Feature d (the ones column) gets absmax 1.
 __global__ void k_col_pow2_scale(const unsigned int* __restrict__ amax_bits, int64_t d, int append_one,
                                  float* __restrict__ scale, float* __restrict__ unscale) {
@@ -876,6 +895,19 @@ int launch_sym_add(const float* S, int64_t d, int64_t lds, float* out, int64_t l
   if (d <= 0) return BVLM_OK;
   dim3 grid(static_cast<unsigned>((d + 255) / 256), static_cast<unsigned>(d));
   k_sym_add<<<grid, 256, 0, st>>>(S, d, lds, out, ldo, alpha, alpha_dev, accumulate);
+  count_launch();
+  BVLM_CUDA_TRY(cudaGetLastError());
+  return BVLM_OK;
+}
+
+int launch_scale_cols_f16(const float* x, int64_t n, int64_t d, int64_t ld, const float* scale, int append_one, __half* out,
+                          int64_t ldo, cudaStream_t st) {
+  if (n <= 0) return BVLM_OK;
+  if (ldo < d + (append_one ? 1 : 0) || (ldo & 1)) return BVLM_EINVAL;
+  unsigned gx = static_cast<unsigned>((ldo / 2 + 31) / 32);
+  if (gx > 16) gx = 16;
+  dim3 grid(gx, static_cast<unsigned>((n + 7) / 8));
+  k_scale_cols_f16<<<grid, dim3(32, 8), 0, st>>>(x, n, d, ld, scale, append_one, out, ldo);
   count_launch();
   BVLM_CUDA_TRY(cudaGetLastError());
   return BVLM_OK;

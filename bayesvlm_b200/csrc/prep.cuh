@@ -86,6 +86,10 @@ int launch_ggn_scalars(const float* q, int64_t C, float* scalars, float inv_coun
 int launch_sym_add(const float* S, int64_t d, int64_t lds, float* out, int64_t ldo, float alpha, const float* alpha_dev,
                    int accumulate, cudaStream_t st);
 
+// out[r, j] = fp16(x[r, j] * scale[j]) row-major with pitch ldo (ones column at j == d when append_one, zero padded)
+int launch_scale_cols_f16(const float* x, int64_t n, int64_t d, int64_t ld, const float* scale, int append_one, __half* out,
+                          int64_t ldo, cudaStream_t st);
+
 // per-feature power-of-two scale: scale[j] = 2^e_j with max_r |x_rj| 2^e_j in [512,1024); unscale[j] = 2^-e_j
 int launch_col_pow2_scale(const float* x, int64_t n, int64_t d, int64_t ld, int append_one, unsigned int* amax_bits,
                           float* scale, float* unscale, cudaStream_t st);
