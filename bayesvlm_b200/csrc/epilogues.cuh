@@ -175,7 +175,8 @@ struct EpiRowSumSq {
 // ---------------------------------------------------------------------------------------------
 template <int BN>
 struct EpiPredictive {
-  static constexpr size_t scratch_bytes(int warps) { return warps * 2 * SLAB_BYTES; }  // per warp: mean slab + var slab
+  // per warp: double-buffered mean + var slabs (the bulk store of chunk c is still reading while chunk c+1 is staged)
+  static constexpr size_t scratch_bytes(int warps) { return warps * 4 * SLAB_BYTES; }
   struct Params {
     CUtensorMap tm_mean, tm_var;  // [N, C] fp32, box {32 cols, 32 rows}, SWIZZLE_128B (used when use_tma)
     float* mean;
@@ -233,15 +234,14 @@ struct EpiPredictive {
     for (int j = 0; j < 32; ++j) v[j] *= st.rm;
     if (p.use_tma) {
       // rows beyond N and columns beyond C are clipped by the tensor map
-      const uint32_t slab_m = ctx.scratch_u32 + static_cast<uint32_t>(ctx.wid) * (2 * SLAB_BYTES);
+      const uint32_t slab_m = ctx.scratch_u32 + static_cast<uint32_t>(ctx.wid) * (4 * SLAB_BYTES) +
+                              static_cast<uint32_t>(c & 1) * (2 * SLAB_BYTES);
       const uint32_t slab_v = slab_m + SLAB_BYTES;
       const int row0 = tc.row0 + ctx.ew * 32;
-      slab_wait_free<1>(ctx.lane);  // pending: previous mean, previous var -> the mean slab is free again
+      slab_wait_free<1>(ctx.lane);  // one bulk group (mean + var) per chunk: only the previous chunk's may still be reading
       slab_write_f32(slab_m, ctx.lane, v);
-      slab_issue(&p.tm_mean, slab_m, ctx.lane, col0, row0);
-      slab_commit(ctx.lane);
-      slab_wait_free<1>(ctx.lane);  // pending: previous var, this mean -> the var slab is free again
       slab_write_f32(slab_v, ctx.lane, var);
+      slab_issue(&p.tm_mean, slab_m, ctx.lane, col0, row0);
       slab_issue(&p.tm_var, slab_v, ctx.lane, col0, row0);
       slab_commit(ctx.lane);
       return;

@@ -179,25 +179,16 @@ int bvlm_predictive(const float* E, int64_t N, int64_t D, int64_t lde, const flo
   Operand16 opA{E16, N, kp, FMT_F16, e_pitch};
   Operand16 opB{T16, C, kp, FMT_F16};
   if ((rc = operand_tmap<GEMM_BM>(&tmA, opA))) return rc;
-  if ((rc = operand_tmap<PRED_BN>(&tmB, opB))) return rc;
   static const int variant = [] {
-    const char* e = getenv("BVLM_PRED_VARIANT");  // 0: one-CTA engine, 1: CTA pairs + 4 epilogue warps, 2: pairs + 8 warps
+    const char* e = getenv("BVLM_PRED_VARIANT");  // 1: 4 epilogue warps + 5 stages (default), 2: 8 epilogue warps + 3 stages
     return e != nullptr ? atoi(e) : 1;
   }();
-  GemmPlan plan;
-  if (variant == 0) {
-    plan = precision == 3
-               ? make_split_plan<PRED_BN>(static_cast<int>(N), static_cast<int>(C), static_cast<int>(seg), SCHED_TILES, FMT_F16)
-               : make_plan<PRED_BN>(static_cast<int>(N), static_cast<int>(C), static_cast<int>(kp), SCHED_TILES, 1, FMT_F16, FMT_F16);
-  } else {
-    plan = precision == 3
-               ? make_split_plan2<PRED_BN>(static_cast<int>(N), static_cast<int>(C), static_cast<int>(seg), SCHED_TILES, FMT_F16)
-               : make_plan2<PRED_BN>(static_cast<int>(N), static_cast<int>(C), static_cast<int>(kp), SCHED_TILES, 1, FMT_F16);
-    if ((rc = operand_tmap<PRED_BN / 2>(&tmB, opB))) return rc;  // each CTA of a pair loads half of the B tile
-  }
+  GemmPlan plan = precision == 3
+                      ? make_split_plan2<PRED_BN>(static_cast<int>(N), static_cast<int>(C), static_cast<int>(seg), SCHED_TILES, FMT_F16)
+                      : make_plan2<PRED_BN>(static_cast<int>(N), static_cast<int>(C), static_cast<int>(kp), SCHED_TILES, 1, FMT_F16);
+  if ((rc = operand_tmap<PRED_BN / 2>(&tmB, opB))) return rc;  // each CTA of a pair loads half of the B tile
   CUtensorMap tmA8, tmB8;
   if (precision == BVLM_PREC_X2F8) {
-    if (variant == 0) return BVLM_ENOTSUP;  // the FP8 phase lives in the CTA-pair engine
     if ((rc = make_tmap_2d(&tmA8, A8, TM_U8, static_cast<uint64_t>(2 * seg8), static_cast<uint64_t>(N),
                            static_cast<uint64_t>(2 * seg8), 128, GEMM_BM, 1)))
       return rc;
@@ -234,11 +225,10 @@ int bvlm_predictive(const float* E, int64_t N, int64_t D, int64_t lde, const flo
                            static_cast<uint64_t>(ldo) * 4, 32, 32, 1)))
       return rc;
   }
-  if (variant == 0) rc = launch_gemm<PRED_BN, PRED_STAGES, EpiPredictive<PRED_BN>>(tmA, tmB, plan, ep, st, TAG_PREDICTIVE);
-  else if (variant == 1)
-    rc = launch_gemm2<PRED_BN, 6, 4, EpiPredictive<PRED_BN>>(tmA, tmB, plan, ep, st, TAG_PREDICTIVE, pA8, pB8);
+  if (variant == 1)
+    rc = launch_gemm2<PRED_BN, 5, 4, EpiPredictive<PRED_BN>>(tmA, tmB, plan, ep, st, TAG_PREDICTIVE, pA8, pB8);
   else
-    rc = launch_gemm2<PRED_BN, 5, 8, EpiPredictive<PRED_BN>>(tmA, tmB, plan, ep, st, TAG_PREDICTIVE, pA8, pB8);
+    rc = launch_gemm2<PRED_BN, 3, 8, EpiPredictive<PRED_BN>>(tmA, tmB, plan, ep, st, TAG_PREDICTIVE, pA8, pB8);
   if (rc) return rc;
   if (probs != nullptr) rc = launch_probit_softmax(mean, var, N, C, ldo, probs, st);
   return rc;

@@ -336,21 +336,6 @@ k_predictive_prep_vec(const float* __restrict__ x, int64_t R, int64_t D, int64_t
   }
 }
 
-// E_i = |e_i|^2 + alpha_i sum(beta);  u_i = s^2 (e_i^2 . delta) / E_i;  v_i = s^2 alpha_i / E_i;
-// rm_i = mean_scale * 2^-k_i / sqrt(E_i)   (per-row factor that turns the raw accumulator into the mean logit)
-__global__ void k_predictive_row_scalars(int64_t R, const float* __restrict__ alpha, const float* __restrict__ n2,
-                                         const float* __restrict__ pd, const float* __restrict__ unscale, float sum_beta,
-                                         float s2, float mean_scale, float* __restrict__ u, float* __restrict__ v,
-                                         float* __restrict__ rm) {
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= R) return;
-  const float a = alpha[i];
-  const float E = n2[i] + a * sum_beta;
-  u[i] = s2 * pd[i] / E;
-  v[i] = s2 * a / E;
-  rm[i] = mean_scale * unscale[i] / sqrtf(E);
-}
-
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(ROW_BLOCK)
 k_ggn_row_prep(const float* __restrict__ x, int64_t R, int64_t D, int64_t ld, float opscale, int nsplit, int side,
@@ -401,49 +386,6 @@ __global__ void k_normalize_weights(const float* __restrict__ w_raw, const float
                                     float* __restrict__ w) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < R) w[i] = w_raw[i] * (static_cast<float>(R) / *w_sum);
-}
-
-// ------------------------------------------------------------------------------------------------
-// 64 (r) x 32 (j) tile; block (32, 8)
-__global__ void __launch_bounds__(256)
-k_transpose_to_16(const float* __restrict__ src, int64_t R, int64_t d, int64_t ld, const float* __restrict__ mult,
-                  int sqrt_mult, const float* __restrict__ jmult, float gmult, int append_one, int fmt,
-                  uint16_t* __restrict__ dst, int64_t ldo, int64_t col_off, int64_t R_pad) {
-  __shared__ float tile[64][33];
-  const int tx = threadIdx.x, ty = threadIdx.y;
-  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * 64;
-  const int64_t j0 = static_cast<int64_t>(blockIdx.y) * 32;
-  const int64_t d_rows = d + (append_one ? 1 : 0);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int rr = ty + 8 * i;
-    const int64_t r = r0 + rr;
-    const int64_t j = j0 + tx;
-    float v = 0.f;
-    if (r < R) {
-      float m = gmult;
-      if (mult != nullptr) {
-        const float mv = mult[r];
-        m *= sqrt_mult ? sqrtf(fmaxf(mv, 0.f)) : mv;
-      }
-      if (jmult != nullptr && j < d + (append_one ? 1 : 0)) m *= jmult[j];
-      if (j < d) v = src[r * ld + j] * m;
-      else if (j == d && append_one) v = m;
-    }
-    tile[rr][tx] = v;
-  }
-  __syncthreads();
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int jj = ty + 8 * i;
-    const int64_t j = j0 + jj;
-    const int64_t r = r0 + 2 * tx;
-    if (j < d_rows && r < R_pad) {
-      const uint32_t pk = static_cast<uint32_t>(to_16(tile[2 * tx][jj], fmt)) |
-                          (static_cast<uint32_t>(to_16(tile[2 * tx + 1][jj], fmt)) << 16);
-      *reinterpret_cast<uint32_t*>(dst + j * ldo + col_off + r) = pk;
-    }
-  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -795,16 +737,6 @@ int launch_predictive_embed_prep(const float* x, int64_t R, int64_t D, int64_t l
   return BVLM_OK;
 }
 
-int launch_predictive_row_scalars(int64_t R, const float* alpha, const float* n2, const float* pd, const float* unscale,
-                                  float sum_beta, float s2, float mean_scale, float* u, float* v, float* rm, cudaStream_t st) {
-  if (R <= 0) return BVLM_OK;
-  k_predictive_row_scalars<<<static_cast<unsigned>((R + 255) / 256), 256, 0, st>>>(R, alpha, n2, pd, unscale, sum_beta, s2,
-                                                                                   mean_scale, u, v, rm);
-  count_launch();
-  BVLM_CUDA_TRY(cudaGetLastError());
-  return BVLM_OK;
-}
-
 int launch_ggn_row_prep(const float* x, int64_t R, int64_t D, int64_t ld, float opscale, int nsplit, int side, __half* xhat,
                         int64_t d_pad, float* inv_norm, float* w_raw, float* w_sum, cudaStream_t st) {
   if (R <= 0) return BVLM_OK;
@@ -818,21 +750,6 @@ int launch_ggn_row_prep(const float* x, int64_t R, int64_t D, int64_t ld, float 
 int launch_normalize_weights(const float* w_raw, const float* w_sum, int64_t R, float* w, cudaStream_t st) {
   if (R <= 0) return BVLM_OK;
   k_normalize_weights<<<static_cast<unsigned>((R + 255) / 256), 256, 0, st>>>(w_raw, w_sum, R, w);
-  count_launch();
-  BVLM_CUDA_TRY(cudaGetLastError());
-  return BVLM_OK;
-}
-
-int launch_transpose_to_16(const float* src, int64_t R, int64_t d, int64_t ld, const float* mult, int sqrt_mult,
-                           const float* jmult, float gmult, int append_one, int fmt, void* dst, int64_t ldo,
-                           int64_t col_off, int64_t R_pad, cudaStream_t st) {
-  if (R_pad <= 0) return BVLM_OK;
-  if ((R_pad & 1) || (col_off & 1) || (ldo & 1)) return BVLM_EINVAL;
-  const int64_t d_rows = d + (append_one ? 1 : 0);
-  dim3 grid(static_cast<unsigned>((R_pad + 63) / 64), static_cast<unsigned>((d_rows + 31) / 32));
-  dim3 block(32, 8);
-  k_transpose_to_16<<<grid, block, 0, st>>>(src, R, d, ld, mult, sqrt_mult, jmult, gmult, append_one, fmt,
-                                            static_cast<uint16_t*>(dst), ldo, col_off, R_pad);
   count_launch();
   BVLM_CUDA_TRY(cudaGetLastError());
   return BVLM_OK;

@@ -1,6 +1,6 @@
-// Operand preparation kernels: fp32 row-major activations / embeddings -> 16-bit K-major GEMM operands
-// (converted, normalised, optionally hi/lo split for ~fp32 accuracy, optionally transposed), plus the small
-// per-row statistics the epilogues need. All are HBM-bound, one warp per row or 32x32 smem-tiled transposes.
+// Operand preparation kernels: fp32 row-major activations / embeddings -> 16-bit (or FP8) GEMM operands (converted,
+// normalised / power-of-two scaled, optionally hi/lo split), plus the small per-row statistics the epilogues need.
+// All are HBM-bound, one warp per row. Nothing is transposed: products of the X^T X kind use MN-major operands.
 #pragma once
 #include "common.cuh"
 
@@ -31,10 +31,6 @@ int launch_predictive_embed_prep(const float* x, int64_t R, int64_t D, int64_t l
                                  __half* act16, int64_t act_kpad, float* act_unscale, cudaStream_t st);
 // (act != NULL additionally converts the row's activations: act16 [R, act_kpad] fp16 with an exact per-row power-of-two
 //  scale, act_unscale[r] = 2^(-2 e_r) -- the same operand launch_rows_to_16(row_pow2_scale = 1) produces.)
-// E = n2 + alpha sum_beta; u = s2 pd / E; v = s2 alpha / E; rm = mean_scale * unscale / sqrt(E)   (vlm.py:665-684)
-int launch_predictive_row_scalars(int64_t R, const float* alpha, const float* n2, const float* pd, const float* unscale,
-                                  float sum_beta, float s2, float mean_scale, float* u, float* v, float* rm, cudaStream_t st);
-
 // GGN row prep (hessians.py:15-21): xhat = x/|x| * opscale -> fp16 [R, d_pad] (nsplit 1) or [R, 2*d_pad] = [hi | lo]
 // (nsplit 3; `side` is ignored); inv_norm[r] = 1/|x_r|;
 // w_raw[r] = 1/|x_r|^2 ; *w_sum += sum_r w_raw[r] (atomic).
@@ -43,13 +39,6 @@ int launch_ggn_row_prep(const float* x, int64_t R, int64_t D, int64_t ld, float 
 
 // w[r] = w_raw[r] * R / *w_sum   (mean-one weights keep the fp16 operands of the final GEMM in range)
 int launch_normalize_weights(const float* w_raw, const float* w_sum, int64_t R, float* w, cudaStream_t st);
-
-// Transposing writer: dst[j * ldo + col_off + r] = fmt( src[r * ld + j] * mult[r] * jmult[j] * gmult ), r < R, j < d;
-// an optional ones row (j == d) is appended when append_one; columns r in [R, R_pad) are zero-filled.
-// mult / jmult may be null (1). sqrt_mult=1 uses sqrt(max(mult,0)).
-int launch_transpose_to_16(const float* src, int64_t R, int64_t d, int64_t ld, const float* mult, int sqrt_mult,
-                           const float* jmult, float gmult, int append_one, int fmt, void* dst, int64_t ldo,
-                           int64_t col_off, int64_t R_pad, cudaStream_t st);
 
 // Per-source finalisation of the pivot-centred GGN (collapsed form of hessians.py:30-46 / 103-113; see kfac.cu).
 // gamma = max_c q_c normalises the stacked operands of pass 4 into fp16's range whatever the curvature scale is.
