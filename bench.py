@@ -256,7 +256,7 @@ def run_b200(args, rank, world, local_rank):
     avg_ms = kern[dom][1] / kern[dom][0]
     ach = algo_flops[dom] / (avg_ms * 1e-3) / 1e12
     peak = peaks["bf16_tflops_sustained"]
-    roofline = {"bound": "tensor", "kernel": f"gemm_tn_kernel<{dom}>", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+    roofline = {"bound": "tensor", "kernel": f"gemm2_tn_kernel<{dom}> (CTA-pair tcgen05 engine)", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                 "frac": ach / peak, "traffic": None, "peak_source": peaks_src + ", sustained bf16",
                 "avg_launch_ms": avg_ms, "launches": kern[dom][0],
                 "kernels": {k: {"launches": v[0], "avg_ms": v[1] / v[0],
