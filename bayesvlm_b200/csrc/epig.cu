@@ -126,6 +126,7 @@ struct EpiEpigJoint {
   };
   static constexpr bool ALL_CHUNKS = false;
   static constexpr bool UNROLL_CHUNKS = false;
+  static constexpr bool DRAIN_FIRST = false;
   __device__ static void kernel_begin(State&, const Params&, const EpiCtx&) {}
   __device__ static void kernel_end(State&, const Params&, const EpiCtx&) {}
 

@@ -80,6 +80,7 @@ struct EpiStoreF32 {
   };
   static constexpr bool ALL_CHUNKS = false;
   static constexpr bool UNROLL_CHUNKS = true;
+  static constexpr bool DRAIN_FIRST = false;
   __device__ static void kernel_begin(State&, const Params&, const EpiCtx&) {}
   __device__ static void kernel_end(State&, const Params&, const EpiCtx&) {}
   __device__ static void item_begin(State& st, const Params& p, const EpiCtx&, const TileCoord&) {
@@ -135,6 +136,7 @@ struct EpiRowSumSq {
   };
   static constexpr bool ALL_CHUNKS = false;
   static constexpr bool UNROLL_CHUNKS = true;
+  static constexpr bool DRAIN_FIRST = false;
   __device__ static void kernel_begin(State&, const Params&, const EpiCtx&) {}
   __device__ static void kernel_end(State&, const Params&, const EpiCtx&) {}
   __device__ static void item_begin(State& st, const Params&, const EpiCtx&, const TileCoord&) { st.acc = 0.f; }
@@ -175,8 +177,8 @@ struct EpiRowSumSq {
 // ---------------------------------------------------------------------------------------------
 template <int BN>
 struct EpiPredictive {
-  // per warp: double-buffered mean + var slabs (the bulk store of chunk c is still reading while chunk c+1 is staged)
-  static constexpr size_t scratch_bytes(int warps) { return warps * 4 * SLAB_BYTES; }
+  // per warp: mean + var slabs, double-buffered with 4 epilogue warps (16 KB per warp), single with 8 (8 KB per warp)
+  static constexpr size_t scratch_bytes(int) { return 16 * SLAB_BYTES; }
   struct Params {
     CUtensorMap tm_mean, tm_var;  // [N, C] fp32, box {32 cols, 32 rows}, SWIZZLE_128B (used when use_tma)
     float* mean;
@@ -198,6 +200,7 @@ struct EpiPredictive {
   };
   static constexpr bool ALL_CHUNKS = false;
   static constexpr bool UNROLL_CHUNKS = true;
+  static constexpr bool DRAIN_FIRST = true;   // 8-warp configuration: free the TMEM buffer before the stores
   __device__ static void kernel_begin(State&, const Params&, const EpiCtx&) {}
   __device__ static void kernel_end(State&, const Params& p, const EpiCtx& ctx) {
     if (p.use_tma && ctx.lane == 0) tma_store_wait_all<0>();
@@ -232,13 +235,17 @@ struct EpiPredictive {
     }
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] *= st.rm;
+    if (p.use_tma == 2) return;  // (diagnostic: main loop without output traffic, BVLM_DEBUG_NOSTORE=1)
     if (p.use_tma) {
       // rows beyond N and columns beyond C are clipped by the tensor map
-      const uint32_t slab_m = ctx.scratch_u32 + static_cast<uint32_t>(ctx.wid) * (4 * SLAB_BYTES) +
-                              static_cast<uint32_t>(c & 1) * (2 * SLAB_BYTES);
+      const bool dbl = ctx.n_warps == 4;
+      const uint32_t slab_m = ctx.scratch_u32 + static_cast<uint32_t>(ctx.wid) * ((dbl ? 4 : 2) * SLAB_BYTES) +
+                              static_cast<uint32_t>(dbl ? (c & 1) : 0) * (2 * SLAB_BYTES);
       const uint32_t slab_v = slab_m + SLAB_BYTES;
       const int row0 = tc.row0 + ctx.ew * 32;
-      slab_wait_free<1>(ctx.lane);  // one bulk group (mean + var) per chunk: only the previous chunk's may still be reading
+      // one bulk group (mean + var) per chunk: double-buffered -> only the previous chunk's may still be reading
+      if (dbl) slab_wait_free<1>(ctx.lane);
+      else slab_wait_free<0>(ctx.lane);
       slab_write_f32(slab_m, ctx.lane, v);
       slab_write_f32(slab_v, ctx.lane, var);
       slab_issue(&p.tm_mean, slab_m, ctx.lane, col0, row0);
@@ -292,6 +299,7 @@ struct EpiRowLse {
   };
   static constexpr bool ALL_CHUNKS = false;
   static constexpr bool UNROLL_CHUNKS = false;
+  static constexpr bool DRAIN_FIRST = false;
   __device__ static void kernel_begin(State&, const Params&, const EpiCtx&) {}
   __device__ static void kernel_end(State&, const Params&, const EpiCtx&) {}
   __device__ static void item_begin(State& st, const Params&, const EpiCtx&, const TileCoord&) {
@@ -395,6 +403,7 @@ struct EpiGgnWeights {
   };
   static constexpr bool ALL_CHUNKS = true;      // slabs are issued per pair of 32-column chunks
   static constexpr bool UNROLL_CHUNKS = false;  // the body is large: keep one copy
+  static constexpr bool DRAIN_FIRST = false;
   __device__ static uint32_t qsum_addr(const EpiCtx& ctx) {
     return ctx.scratch_u32 + static_cast<uint32_t>(ctx.n_warps) * (3 * SLAB_BYTES);
   }

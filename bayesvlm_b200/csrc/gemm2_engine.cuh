@@ -295,6 +295,29 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ctx.ew * 32) << 16) + static_cast<uint32_t>(acc * BN);
         const int n_valid = plan.N - tc.n * BN;
+        if constexpr (Epi::DRAIN_FIRST && EPI_WARPS == 8) {
+          // Drain this warp's whole share of the accumulator into registers and hand the TMEM buffer back to the MMA
+          // issuer BEFORE the (store-latency bound) epilogue work: tensor memory is then occupied for ~1 us per tile,
+          // whatever the output path takes.
+          float vv[CH_PER_WARP][32];
+#pragma unroll
+          for (int i = 0; i < CH_PER_WARP; ++i)
+            tmem_ld_32x32(taddr + static_cast<uint32_t>((chalf * CH_PER_WARP + i) * 32), vv[i]);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
+#pragma unroll
+          for (int i = 0; i < CH_PER_WARP; ++i) {
+            const int c = chalf * CH_PER_WARP + i;
+            if (!Epi::ALL_CHUNKS && c * 32 >= n_valid) continue;
+            Epi::chunk(st, ep, ctx, tc, vv[i], c);
+          }
+          Epi::tile_end(st, ep, ctx, tc);
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1u;
+          continue;
+        }
         if constexpr (Epi::UNROLL_CHUNKS) {
 #pragma unroll
           for (int c = 0; c < CHUNKS; ++c) {

@@ -217,6 +217,7 @@ int bvlm_predictive(const float* E, int64_t N, int64_t D, int64_t lde, const flo
   // TMA stores need 16-byte aligned rows; tiny class counts (e.g. C = 10) fall back to direct stores
   ep.use_tma = ((ldo * 4) % 16 == 0 && (reinterpret_cast<uintptr_t>(mean) & 15) == 0 &&
                 (reinterpret_cast<uintptr_t>(var) & 15) == 0) ? 1 : 0;
+  static const bool nostore = getenv("BVLM_DEBUG_NOSTORE") != nullptr;  // diagnostic: main loop without output traffic
   if (ep.use_tma) {
     if ((rc = make_tmap_2d(&ep.tm_mean, mean, TM_F32, static_cast<uint64_t>(C), static_cast<uint64_t>(N),
                            static_cast<uint64_t>(ldo) * 4, 32, 32, 1)))
@@ -225,10 +226,16 @@ int bvlm_predictive(const float* E, int64_t N, int64_t D, int64_t lde, const flo
                            static_cast<uint64_t>(ldo) * 4, 32, 32, 1)))
       return rc;
   }
+  if (nostore) ep.use_tma = 2;
+  if (getenv("BVLM_DEBUG_SHORTK") != nullptr) {  // diagnostic: one K block per tile -> the kernel is its epilogue
+    plan.kb_total = 1;
+    plan.kb_alt = 0x7fffffff;
+    plan.seg_kb = 0;
+  }
   if (variant == 1)
     rc = launch_gemm2<PRED_BN, 5, 4, EpiPredictive<PRED_BN>>(tmA, tmB, plan, ep, st, TAG_PREDICTIVE, pA8, pB8);
   else
-    rc = launch_gemm2<PRED_BN, 3, 8, EpiPredictive<PRED_BN>>(tmA, tmB, plan, ep, st, TAG_PREDICTIVE, pA8, pB8);
+    rc = launch_gemm2<PRED_BN, 5, 8, EpiPredictive<PRED_BN>>(tmA, tmB, plan, ep, st, TAG_PREDICTIVE, pA8, pB8);
   if (rc) return rc;
   if (probs != nullptr) rc = launch_probit_softmax(mean, var, N, C, ldo, probs, st);
   return rc;
