@@ -256,8 +256,12 @@ def run_b200(args, rank, world, local_rank):
     avg_ms = kern[dom][1] / kern[dom][0]
     ach = algo_flops[dom] / (avg_ms * 1e-3) / 1e12
     peak = peaks["bf16_tflops_sustained"]
+    try:
+        traffic = json.loads((ROOT / "profiles" / "ncu_traffic.json").read_text()).get(dom)
+    except Exception:
+        traffic = None
     roofline = {"bound": "tensor", "kernel": f"gemm2_tn_kernel<{dom}> (CTA-pair tcgen05 engine)", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                "frac": ach / peak, "traffic": None, "peak_source": peaks_src + ", sustained bf16",
+                "frac": ach / peak, "traffic": traffic, "peak_source": peaks_src + ", sustained bf16",
                 "avg_launch_ms": avg_ms, "launches": kern[dom][0],
                 "kernels": {k: {"launches": v[0], "avg_ms": v[1] / v[0],
                                 "algo_tflops": algo_flops.get(k, 0.0) / (v[1] / v[0] * 1e-3) / 1e12} for k, v in kern.items()},
