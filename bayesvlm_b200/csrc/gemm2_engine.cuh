@@ -45,6 +45,18 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorM
       : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1)
       : "memory");
 }
+// same, multicast to every CTA of the cluster whose bit is set in cta_mask (same shared-memory offset in each; the
+// transaction bytes are credited to the leader CTA of each destination's pair)
+__device__ __forceinline__ void tma_load_2d_pair_mc(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int32_t c0,
+                                                    int32_t c1, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1),
+        "h"(cta_mask)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_3d_pair(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int32_t c0,
                                                  int32_t c1, int32_t c2) {
   asm volatile(
@@ -84,11 +96,11 @@ __device__ __forceinline__ void umma_f8_ss_pair(uint32_t tmem_d, uint64_t desc_a
       : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// arrive on the barrier at this offset in BOTH CTAs once all previously issued MMAs of the pair have completed
-__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+// arrive on the barrier at this offset in every CTA of `cta_mask` once all previously issued MMAs of the pair are done
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t cta_mask) {
   asm volatile(
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
-      "h"(static_cast<uint16_t>(3))
+      "h"(cta_mask)
       : "memory");
 }
 
@@ -101,8 +113,11 @@ constexpr size_t gemm2_smem_bytes() {
 // A_MN / B_MN: the operand is MN-major (its M / N index is contiguous in global memory, i.e. the tensor is stored
 // [K rows, M or N columns] row-major -- a plain row-major activation matrix is the "transposed" operand of X^T X without
 // any transposing pass). Such a tile is fetched as 64-column boxes of [64 K rows x 128 bytes].
-template <int BN, int STAGES, int EPI_WARPS, class Epi, bool A_MN = false, bool B_MN = false>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * EPI_WARPS, 1)
+// PAIRS = 2: clusters of FOUR CTAs = two MMA pairs working on two consecutive 256-row M tiles of the SAME N tile; the B
+// tile is fetched ONCE per cluster and multicast into both pairs (pair 0's producers issue it), which cuts the operand
+// traffic over the L2 fabric by a quarter -- the bound of the FP8-assisted predictive GEMM.
+template <int BN, int STAGES, int EPI_WARPS, class Epi, bool A_MN = false, bool B_MN = false, int PAIRS = 1>
+__global__ void __launch_bounds__(128 + 32 * EPI_WARPS, 1)
 gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmA8, const __grid_constant__ CUtensorMap tmB8, const GemmPlan plan,
                 const __grid_constant__ typename Epi::Params ep) {
@@ -129,8 +144,12 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
+  const uint32_t crank = cluster_ctarank();  // 0 .. 2 * PAIRS - 1
+  const uint32_t rank = crank & 1u;          // rank inside the MMA pair
+  const uint32_t pair = crank >> 1;
   const bool leader = rank == 0;
+  const uint16_t pair_mask = static_cast<uint16_t>(3u << (2 * pair));
+  const uint16_t all_mask = static_cast<uint16_t>((1u << (2 * PAIRS)) - 1u);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -139,7 +158,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 2);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], PAIRS);  // every pair's MMAs must be done with a stage before anybody refills it
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
@@ -157,8 +176,8 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
 
   const int n_items = plan_num_items<BN>(plan);
-  const int cluster_id = blockIdx.x >> 1;
-  const int n_clusters = gridDim.x >> 1;
+  const int cluster_id = blockIdx.x / (2 * PAIRS);
+  const int n_clusters = gridDim.x / (2 * PAIRS);
 
   if (warp == 0) {
     // ------------------------------------------------ TMA producer (one per CTA)
@@ -169,8 +188,10 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int n_inner = plan_inner<BN>(plan, item);
         for (int inner = 0; inner < n_inner; ++inner) {
           const TileCoord tc = plan_tile<BN>(plan, item, inner);
-          const int row_a = tc.m * GEMM2_BM + static_cast<int>(rank) * GEMM_BM;
+          const int row_a = (tc.m * PAIRS + static_cast<int>(pair)) * GEMM2_BM + static_cast<int>(rank) * GEMM_BM;
           const int row_b = tc.n * BN + static_cast<int>(rank) * (BN / 2);
+          const bool load_b = PAIRS == 1 || pair == 0;  // pair 0 multicasts the shared B tile to the other pair
+          const uint16_t b_mask = static_cast<uint16_t>(0x5u << rank);  // CTAs with the same in-pair rank
           int seg_v = 0, seg_off = tc.kb0;
           for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
             int col_a = kb * GEMM_BK, col_b = col_a;
@@ -187,7 +208,8 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (kb >= plan.kb_alt) {  // FP8 phase: same 128-byte K blocks, 128 elements each, second pair of tensor maps
               const int col8 = (kb - plan.kb_alt) * 128;
               tma_load_2d_pair(sA + stage * A_BYTES, &tmA8, &full_bar[stage], col8, row_a);
-              tma_load_2d_pair(sB + stage * B_BYTES, &tmB8, &full_bar[stage], col8, row_b);
+              if (PAIRS == 1) tma_load_2d_pair(sB + stage * B_BYTES, &tmB8, &full_bar[stage], col8, row_b);
+              else if (load_b) tma_load_2d_pair_mc(sB + stage * B_BYTES, &tmB8, &full_bar[stage], col8, row_b, b_mask);
             } else {
             if constexpr (A_MN) {  // [K, M] storage: two 64-column boxes of 64 K rows
 #pragma unroll
@@ -195,7 +217,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 tma_load_2d_pair(sA + stage * A_BYTES + blk * (GEMM_BK * 128), &tmA, &full_bar[stage], row_a + blk * 64, col_a);
             } else if (plan.a_is_3d) {  // a_outer_step outer items per CTA slab (EPIG: pool rows x classes x K)
               tma_load_3d_pair(sA + stage * A_BYTES, &tmA, &full_bar[stage], col_a, 0,
-                               (tc.m * 2 + static_cast<int>(rank)) * plan.a_outer_step);
+                               ((tc.m * PAIRS + static_cast<int>(pair)) * 2 + static_cast<int>(rank)) * plan.a_outer_step);
             } else {
               tma_load_2d_pair(sA + stage * A_BYTES, &tmA, &full_bar[stage], col_a, row_a);
             }
@@ -203,8 +225,10 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
               for (int blk = 0; blk < (BN / 2) / 64; ++blk)
                 tma_load_2d_pair(sB + stage * B_BYTES + blk * (GEMM_BK * 128), &tmB, &full_bar[stage], row_b + blk * 64, col_b);
-            } else {
+            } else if (PAIRS == 1) {
               tma_load_2d_pair(sB + stage * B_BYTES, &tmB, &full_bar[stage], col_b, row_b);
+            } else if (load_b) {
+              tma_load_2d_pair_mc(sB + stage * B_BYTES, &tmB, &full_bar[stage], col_b, row_b, b_mask);
             }
             }
             if (++stage == STAGES) {
@@ -252,13 +276,13 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                                  plan.idesc, (kb > tc.kb0 || k > 0) ? 1u : 0u);
               }
             }
-            umma_commit_pair(&empty_bar[stage]);
+            umma_commit_pair(&empty_bar[stage], all_mask);
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1u;
             }
           }
-          umma_commit_pair(&tfull_bar[acc]);
+          umma_commit_pair(&tfull_bar[acc], pair_mask);
           acc ^= 1;
           if (acc == 0) acc_phase ^= 1u;
         }
@@ -283,13 +307,13 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int item = cluster_id; item < n_items; item += n_clusters) {
       const int n_inner = plan_inner<BN>(plan, item);
       TileCoord t0 = plan_tile<BN>(plan, item, 0);
-      t0.row0 = t0.m * GEMM2_BM + static_cast<int>(rank) * GEMM_BM;
+      t0.row0 = (t0.m * PAIRS + static_cast<int>(pair)) * GEMM2_BM + static_cast<int>(rank) * GEMM_BM;
       t0.row0_next = -1;
       Epi::item_begin(st, ep, ctx, t0);
       for (int inner = 0; inner < n_inner; ++inner) {
         TileCoord tc = plan_tile<BN>(plan, item, inner);
-        tc.row0 = tc.m * GEMM2_BM + static_cast<int>(rank) * GEMM_BM;
-        tc.row0_next = (plan.mode == SCHED_COL_PANEL && inner + 1 < n_inner) ? tc.row0 + GEMM2_BM : -1;
+        tc.row0 = (tc.m * PAIRS + static_cast<int>(pair)) * GEMM2_BM + static_cast<int>(rank) * GEMM_BM;
+        tc.row0_next = (plan.mode == SCHED_COL_PANEL && inner + 1 < n_inner) ? tc.row0 + PAIRS * GEMM2_BM : -1;
         Epi::tile_begin(st, ep, ctx, tc);
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
@@ -382,27 +406,30 @@ inline GemmPlan make_split_plan2(int M, int N, int seg, int mode, int fmt) {
   return p;
 }
 
+// PAIRS = 2 clusters cover 512 rows per item
+inline void plan_use_pairs(GemmPlan& p, int pairs) { p.m_tiles = (p.M + pairs * GEMM2_BM - 1) / (pairs * GEMM2_BM); }
+
 // number of CTA pairs that can be co-resident for this instantiation (queried once)
-template <int BN, int STAGES, int EPI_WARPS, class Epi, bool A_MN = false, bool B_MN = false>
+template <int BN, int STAGES, int EPI_WARPS, class Epi, bool A_MN = false, bool B_MN = false, int PAIRS = 1>
 inline int gemm2_max_clusters(size_t smem) {
   static int cached = -1;
   if (cached >= 0) return cached;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(static_cast<unsigned>(device_sm_count() & ~1), 1, 1);
+  cfg.gridDim = dim3(static_cast<unsigned>(device_sm_count() / (2 * PAIRS) * (2 * PAIRS)), 1, 1);
   cfg.blockDim = dim3(128 + 32 * EPI_WARPS, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.x = 2 * PAIRS;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, gemm2_tn_kernel<BN, STAGES, EPI_WARPS, Epi, A_MN, B_MN>, &cfg) != cudaSuccess ||
+  if (cudaOccupancyMaxActiveClusters(&n, gemm2_tn_kernel<BN, STAGES, EPI_WARPS, Epi, A_MN, B_MN, PAIRS>, &cfg) != cudaSuccess ||
       n <= 0) {
     (void)cudaGetLastError();
-    n = device_sm_count() / 2;
+    n = device_sm_count() / (2 * PAIRS);
   }
   cached = n;
   return n;
@@ -410,26 +437,39 @@ inline int gemm2_max_clusters(size_t smem) {
 
 // K-major B operand: tensor map box rows = BN / 2 (each CTA of the pair loads half of the B tile).
 // MN-major operands: tensor map over the [K, M|N] storage with box {64 columns, 64 K rows} (operand_tmap_mn).
-template <int BN, int STAGES, int EPI_WARPS, class Epi, bool A_MN = false, bool B_MN = false>
+template <int BN, int STAGES, int EPI_WARPS, class Epi, bool A_MN = false, bool B_MN = false, int PAIRS = 1>
 inline int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmPlan& plan,
                         const typename Epi::Params& ep, cudaStream_t stream, int tag, const CUtensorMap* tmA8 = nullptr,
                         const CUtensorMap* tmB8 = nullptr) {
   if (plan.kb_total <= 0 || plan.M <= 0 || plan.N <= 0) return BVLM_EINVAL;
   constexpr size_t smem = gemm2_smem_bytes<BN, STAGES, EPI_WARPS, Epi>();
   static_assert(smem <= 232448, "shared memory budget exceeded");
-  auto kfn = gemm2_tn_kernel<BN, STAGES, EPI_WARPS, Epi, A_MN, B_MN>;
+  auto kfn = gemm2_tn_kernel<BN, STAGES, EPI_WARPS, Epi, A_MN, B_MN, PAIRS>;
   static bool configured = false;  // per instantiation
   if (!configured) {
     BVLM_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     configured = true;
   }
   const int items = plan_num_items<BN>(plan);
-  int clusters = gemm2_max_clusters<BN, STAGES, EPI_WARPS, Epi, A_MN, B_MN>(smem);
+  int clusters = gemm2_max_clusters<BN, STAGES, EPI_WARPS, Epi, A_MN, B_MN, PAIRS>(smem);
   if (items < clusters) clusters = items;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(2 * PAIRS * clusters), 1, 1);
+  cfg.blockDim = dim3(128 + 32 * EPI_WARPS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2 * PAIRS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
   timing_begin(tag, stream);
-  kfn<<<2 * clusters, 128 + 32 * EPI_WARPS, smem, stream>>>(tmA, tmB, tmA8 != nullptr ? *tmA8 : tmA,
-                                                            tmB8 != nullptr ? *tmB8 : tmB, plan, ep);
+  const cudaError_t le = cudaLaunchKernelEx(&cfg, kfn, tmA, tmB, tmA8 != nullptr ? *tmA8 : tmA, tmB8 != nullptr ? *tmB8 : tmB,
+                                            plan, ep);
   timing_end(tag, stream);
+  if (le != cudaSuccess) return static_cast<int>(le);
   count_launch();
   BVLM_CUDA_TRY(cudaGetLastError());
   return BVLM_OK;

@@ -180,7 +180,8 @@ int bvlm_predictive(const float* E, int64_t N, int64_t D, int64_t lde, const flo
   Operand16 opB{T16, C, kp, FMT_F16};
   if ((rc = operand_tmap<GEMM_BM>(&tmA, opA))) return rc;
   static const int variant = [] {
-    const char* e = getenv("BVLM_PRED_VARIANT");  // 1: 4 epilogue warps + 5 stages (default), 2: 8 epilogue warps + 3 stages
+    // 1: 4 epilogue warps + 5 stages (default), 2: 8 epilogue warps, 3: as 1 on 4-CTA clusters with the class tile multicast
+    const char* e = getenv("BVLM_PRED_VARIANT");
     return e != nullptr ? atoi(e) : 1;
   }();
   GemmPlan plan = precision == 3
@@ -232,7 +233,10 @@ int bvlm_predictive(const float* E, int64_t N, int64_t D, int64_t lde, const flo
     plan.kb_alt = 0x7fffffff;
     plan.seg_kb = 0;
   }
-  if (variant == 1)
+  if (variant == 3) {
+    plan_use_pairs(plan, 2);
+    rc = launch_gemm2<PRED_BN, 5, 4, EpiPredictive<PRED_BN>, false, false, 2>(tmA, tmB, plan, ep, st, TAG_PREDICTIVE, pA8, pB8);
+  } else if (variant == 1)
     rc = launch_gemm2<PRED_BN, 5, 4, EpiPredictive<PRED_BN>>(tmA, tmB, plan, ep, st, TAG_PREDICTIVE, pA8, pB8);
   else
     rc = launch_gemm2<PRED_BN, 5, 8, EpiPredictive<PRED_BN>>(tmA, tmB, plan, ep, st, TAG_PREDICTIVE, pA8, pB8);
