@@ -482,6 +482,105 @@ k_ggn_row_finalize(const float* __restrict__ x, int64_t B, int64_t D, int64_t Dp
   }
 }
 
+// 16-byte vectorised variant of k_ggn_row_finalize (D % 4 == 0, aligned rows): same math, a quarter of the load
+// instructions; the three sweeps over the row hit L1 after the first.
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void st4h(__half* dst, float a, float b, float c, float d) {
+  const __half2 h0 = __floats2half2_rn(a, b), h1 = __floats2half2_rn(c, d);
+  uint2 pk;
+  pk.x = *reinterpret_cast<const uint32_t*>(&h0);
+  pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+  *reinterpret_cast<uint2*>(dst) = pk;
+}
+__global__ void __launch_bounds__(ROW_BLOCK)
+k_ggn_row_finalize_vec(const float* __restrict__ x, int64_t B, int64_t D, int64_t Dp, int64_t ldx,
+                       const float* __restrict__ inv_norm, const float* __restrict__ w, const float* __restrict__ y,
+                       int64_t ldy, const float* __restrict__ inv_norm_y, const int* __restrict__ pivot,
+                       const float* __restrict__ rest, const float* __restrict__ inv_gamma, const float* __restrict__ Nraw,
+                       const float* __restrict__ Rraw, int64_t ldm, float unscale_n, float unscale_r, int siglip, float g,
+                       __half* __restrict__ LA, __half* __restrict__ RA, __half* __restrict__ LB, __half* __restrict__ RB,
+                       int64_t ldl, int64_t ldr) {
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= B) return;
+  const float inv = inv_norm[row];
+  const float* xr = x + row * ldx;
+  const float* rr = Rraw + row * ldm;
+  __half* lb = LB + row * ldl;
+  __half* rb = RB + row * ldr;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (siglip) {
+    const float kappa = g * sqrtf(fmaxf(w[row] * (*inv_gamma), 0.f));
+    float a = 0.f;
+    for (int64_t j = 4 * lane; j < D; j += 128) {
+      const float4 r4 = ld4(rr + j), x4 = ld4(xr + j);
+      a = fmaf(r4.x, x4.x, fmaf(r4.y, x4.y, fmaf(r4.z, x4.z, fmaf(r4.w, x4.w, a))));
+    }
+    a = warp_sum(a) * unscale_r * inv;
+    for (int64_t j = 4 * lane; j < Dp; j += 128) {
+      const bool ok = j < D;
+      const float4 r4 = ok ? ld4(rr + j) : z4, x4 = ok ? ld4(xr + j) : z4;
+      const float k2 = -2.f * kappa * inv, ha = -0.5f * a * inv;
+      st4h(lb + j, k2 * x4.x, k2 * x4.y, k2 * x4.z, k2 * x4.w);
+      st4h(rb + j, kappa * fmaf(ha, x4.x, r4.x * unscale_r), kappa * fmaf(ha, x4.y, r4.y * unscale_r),
+           kappa * fmaf(ha, x4.z, r4.z * unscale_r), kappa * fmaf(ha, x4.w, r4.w * unscale_r));
+    }
+    return;
+  }
+  const int pv = pivot[row];
+  const float* gr = y + static_cast<int64_t>(pv) * ldy;
+  const float ginv = inv_norm_y[pv];
+  const float rs = rest[row];
+  const float rho = rs / (1.f + rs);
+  const float sq = sqrtf(1.f / (1.f + rs));
+  const float c1 = 1.f / (1.f + sq), c2 = 1.f + sq;
+  const float kappa = g * sqrtf(fmaxf(w[row] * rho * (*inv_gamma), 0.f));
+  const float* nr = Nraw + row * ldm;
+  __half* la = LA + row * ldl;
+  __half* ra = RA + row * ldr;
+  float tau = 0.f;  // ebar . xh
+  for (int64_t j = 4 * lane; j < D; j += 128) {
+    const float4 n4 = ld4(nr + j), g4 = ld4(gr + j), x4 = ld4(xr + j);
+    tau = fmaf(fmaf(n4.x, unscale_n, -g4.x * ginv), x4.x, tau);
+    tau = fmaf(fmaf(n4.y, unscale_n, -g4.y * ginv), x4.y, tau);
+    tau = fmaf(fmaf(n4.z, unscale_n, -g4.z * ginv), x4.z, tau);
+    tau = fmaf(fmaf(n4.w, unscale_n, -g4.w * ginv), x4.w, tau);
+  }
+  tau = warp_sum(tau) * inv;
+  float a = 0.f;  // ubar . xh
+#define BVLM_U(nn, gg, rrv) fmaf(-tau, fmaf(rho, fmaf(nn, unscale_n, -(gg) * ginv), (gg) * ginv), (rrv) * unscale_r)
+  for (int64_t j = 4 * lane; j < D; j += 128) {
+    const float4 n4 = ld4(nr + j), g4 = ld4(gr + j), x4 = ld4(xr + j), r4 = ld4(rr + j);
+    a = fmaf(BVLM_U(n4.x, g4.x, r4.x), x4.x, a);
+    a = fmaf(BVLM_U(n4.y, g4.y, r4.y), x4.y, a);
+    a = fmaf(BVLM_U(n4.z, g4.z, r4.z), x4.z, a);
+    a = fmaf(BVLM_U(n4.w, g4.w, r4.w), x4.w, a);
+  }
+  a = warp_sum(a) * inv;
+  for (int64_t j = 4 * lane; j < Dp; j += 128) {
+    const bool ok = j < D;
+    const float4 n4 = ok ? ld4(nr + j) : z4, g4 = ok ? ld4(gr + j) : z4, x4 = ok ? ld4(xr + j) : z4, r4 = ok ? ld4(rr + j) : z4;
+    float vla[4], vra[4], vlb[4], vrb[4];
+    const float nn[4] = {n4.x, n4.y, n4.z, n4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w}, xx[4] = {x4.x, x4.y, x4.z, x4.w},
+                rv[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float gv = gg[t] * ginv, xh = xx[t] * inv;
+      const float e = ok ? fmaf(nn[t], unscale_n, -gv) : 0.f;
+      const float u = fmaf(-tau, fmaf(rho, e, gv), rv[t] * unscale_r);
+      vla[t] = -kappa * fmaf(c1, gv, e);
+      vra[t] = kappa * fmaf(rho, e, c2 * gv);
+      vlb[t] = -2.f * kappa * xh;
+      vrb[t] = kappa * fmaf(-0.5f * a, xh, u);
+    }
+    st4h(la + j, vla[0], vla[1], vla[2], vla[3]);
+    st4h(ra + j, vra[0], vra[1], vra[2], vra[3]);
+    st4h(lb + j, vlb[0], vlb[1], vlb[2], vlb[3]);
+    st4h(rb + j, vrb[0], vrb[1], vrb[2], vrb[3]);
+  }
+#undef BVLM_U
+}
+
 // out[c, :] = fp16( y_c / |y_c| * q_c * inv_gamma * mult ), zero padded to Dp columns: the scaled side of Yh^T diag(q) Yh
 __global__ void __launch_bounds__(ROW_BLOCK)
 k_ggn_scale_targets(const float* __restrict__ y, int64_t C, int64_t D, int64_t Dp, int64_t ldy,
@@ -582,21 +681,39 @@ __global__ void __launch_bounds__(256) k_col_absmax(const float* __restrict__ x,
 }
 
 // out[r, j] = fp16(x[r, j] * scale[j]) row-major [n, ldo] (a ones column at j == d when append_one, zeros up to ldo):
-// the MN-major SYRK operand -- no transpose
-__global__ void __launch_bounds__(256)
+// the MN-major SYRK operand -- no transpose. One warp per row, 16-byte loads when the rows are aligned.
+__global__ void __launch_bounds__(ROW_BLOCK)
 k_scale_cols_f16(const float* __restrict__ x, int64_t n, int64_t d, int64_t ld, const float* __restrict__ scale,
-                 int append_one, __half* __restrict__ out, int64_t ldo) {
-  const int64_t r = static_cast<int64_t>(blockIdx.y) * 8 + threadIdx.y;
+                 int append_one, __half* __restrict__ out, int64_t ldo, int vec_ok) {
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (r >= n) return;
   const float* xr = x + r * ld;
   __half* o = out + r * ldo;
-  for (int64_t j = 2 * (static_cast<int64_t>(blockIdx.x) * 32 + threadIdx.x); j < ldo; j += 64 * gridDim.x) {
-    float v0 = 0.f, v1 = 0.f;
-    if (j < d) v0 = xr[j] * scale[j];
-    else if (j == d && append_one) v0 = scale[j];
-    if (j + 1 < d) v1 = xr[j + 1] * scale[j + 1];
-    else if (j + 1 == d && append_one) v1 = scale[j + 1];
-    *reinterpret_cast<__half2*>(o + j) = __floats2half2_rn(v0, v1);
+  for (int64_t j = 4 * lane; j < ldo; j += 128) {
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (vec_ok && j + 3 < d) {
+      const float4 xv = __ldg(reinterpret_cast<const float4*>(xr + j));
+      const float4 sv = __ldg(reinterpret_cast<const float4*>(scale + j));
+      v[0] = xv.x * sv.x, v[1] = xv.y * sv.y, v[2] = xv.z * sv.z, v[3] = xv.w * sv.w;
+    } else {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int64_t jj = j + t;
+        if (jj < d) v[t] = xr[jj] * scale[jj];
+        else if (jj == d && append_one) v[t] = scale[jj];
+      }
+    }
+    const __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+    if (vec_ok && j + 3 < ldo) {
+      uint2 pk;
+      pk.x = *reinterpret_cast<const uint32_t*>(&h0);
+      pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+      *reinterpret_cast<uint2*>(o + j) = pk;
+    } else {  // ldo is even: at most one trailing pair
+      *reinterpret_cast<__half2*>(o + j) = h0;
+      if (j + 2 < ldo) *reinterpret_cast<__half2*>(o + j + 2) = h1;
+    }
   }
 }
 
@@ -762,9 +879,19 @@ int launch_ggn_row_finalize(const float* x, int64_t B, int64_t D, int64_t Dp, in
                             int64_t ldr, cudaStream_t st) {
   if (B <= 0) return BVLM_OK;
   if ((Dp & 1) || (ldl & 1) || (ldr & 1)) return BVLM_EINVAL;
-  k_ggn_row_finalize<<<row_grid(B), ROW_BLOCK, 0, st>>>(x, B, D, Dp, ldx, inv_norm, w, y, ldy, inv_norm_y, pivot, rest,
-                                                        inv_gamma, Nraw, Rraw, ldm, unscale_n, unscale_r, siglip, g, LA, RA,
-                                                        LB, RB, ldl, ldr);
+  const auto al = [](const void* p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; };
+  const bool vec = (D % 4) == 0 && (Dp % 4) == 0 && (ldx % 4) == 0 && (ldy % 4) == 0 && (ldm % 4) == 0 && (ldl % 4) == 0 &&
+                   (ldr % 4) == 0 && al(x, 16) && al(y, 16) && al(Nraw, 16) && al(Rraw, 16) && al(LB, 8) && al(RB, 8) &&
+                   (siglip || (al(LA, 8) && al(RA, 8)));
+  if (vec) {
+    k_ggn_row_finalize_vec<<<row_grid(B), ROW_BLOCK, 0, st>>>(x, B, D, Dp, ldx, inv_norm, w, y, ldy, inv_norm_y, pivot, rest,
+                                                              inv_gamma, Nraw, Rraw, ldm, unscale_n, unscale_r, siglip, g, LA,
+                                                              RA, LB, RB, ldl, ldr);
+  } else {
+    k_ggn_row_finalize<<<row_grid(B), ROW_BLOCK, 0, st>>>(x, B, D, Dp, ldx, inv_norm, w, y, ldy, inv_norm_y, pivot, rest,
+                                                          inv_gamma, Nraw, Rraw, ldm, unscale_n, unscale_r, siglip, g, LA, RA,
+                                                          LB, RB, ldl, ldr);
+  }
   count_launch();
   BVLM_CUDA_TRY(cudaGetLastError());
   return BVLM_OK;
@@ -821,10 +948,9 @@ int launch_scale_cols_f16(const float* x, int64_t n, int64_t d, int64_t ld, cons
                           int64_t ldo, cudaStream_t st) {
   if (n <= 0) return BVLM_OK;
   if (ldo < d + (append_one ? 1 : 0) || (ldo & 1)) return BVLM_EINVAL;
-  unsigned gx = static_cast<unsigned>((ldo / 2 + 31) / 32);
-  if (gx > 16) gx = 16;
-  dim3 grid(gx, static_cast<unsigned>((n + 7) / 8));
-  k_scale_cols_f16<<<grid, dim3(32, 8), 0, st>>>(x, n, d, ld, scale, append_one, out, ldo);
+  const int vec_ok = (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(scale) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(out) & 7) == 0 && (ld % 4) == 0 && (ldo % 4) == 0;
+  k_scale_cols_f16<<<row_grid(n), ROW_BLOCK, 0, st>>>(x, n, d, ld, scale, append_one, out, ldo, vec_ok);
   count_launch();
   BVLM_CUDA_TRY(cudaGetLastError());
   return BVLM_OK;
