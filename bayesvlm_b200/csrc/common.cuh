@@ -129,6 +129,12 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* t
         "r"(c2)
       : "memory");
 }
+// plain (non-tensor) bulk copy global -> shared of `bytes` (multiple of 16, both addresses 16-byte aligned), completing on `bar`
+__device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, const void* smem_src, int32_t c0, int32_t c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                :
@@ -157,6 +163,11 @@ __device__ __forceinline__ void sts_v4_u32(uint32_t addr, uint32_t a, uint32_t b
 }
 __device__ __forceinline__ void sts_f32(uint32_t addr, float a) {
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(a) : "memory");
+}
+__device__ __forceinline__ float4 lds_v4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
 }
 __device__ __forceinline__ float lds_f32(uint32_t addr) {
   float v;

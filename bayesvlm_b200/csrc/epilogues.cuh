@@ -2,6 +2,7 @@
 // 128-row tile (row = 128*m + 32*ew + lane) and receives it 32 columns at a time in registers.
 #pragma once
 #include "gemm_engine.cuh"
+#include "rowprep_device.cuh"
 
 namespace bvlm {
 
@@ -139,7 +140,9 @@ struct EpiRowSumSq {
   static constexpr bool DRAIN_FIRST = false;
   __device__ static void kernel_begin(State&, const Params&, const EpiCtx&) {}
   __device__ static void kernel_end(State&, const Params&, const EpiCtx&) {}
-  __device__ static void item_begin(State& st, const Params&, const EpiCtx&, const TileCoord&) { st.acc = 0.f; }
+  __device__ static void item_begin(State& st, const Params& p, const EpiCtx& ctx, const TileCoord& tc) {
+    st.acc = 0.f;
+  }
   __device__ static void tile_begin(State&, const Params&, const EpiCtx&, const TileCoord&) {}
   __device__ static void chunk(State& st, const Params&, const EpiCtx&, const TileCoord&, float (&v)[32], int) {
     float s0 = 0.f, s1 = 0.f;
@@ -166,6 +169,106 @@ struct EpiRowSumSq {
       if (p.row_scale != nullptr) r *= p.row_scale[row];
       p.out[row] = r;
     }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// EpiRowSumSq + a side job for its (nearly idle) epilogue warps: convert the EMBEDDING rows of the CTA's row panel (fp32 ->
+// fp16 / fp8 operands of the mean GEMM + row statistics, rowprep_device.cuh) while the tensor cores work on the activations,
+// so that the HBM-bound conversion overlaps the tensor-bound quadratic forms inside one kernel.
+// Each warp owns rows row0 + wid + n_warps * j and a private ring of shared-memory row slots fed by bulk copies
+// (cp.async.bulk + mbarrier): PREP_RING_BYTES per warp are in flight at all times, whatever the warp itself is doing --
+// ordinary loads (two rows per warp in flight) left the memory system half idle.
+constexpr int PREP_RING_BYTES = 12288;
+constexpr int PREP_MAX_SLOTS = 8;
+
+// EVX > 0: the embedding rows are exactly 128 * EVX floats wide and stored unpadded (no bounds checks); 0: generic, <= 1024.
+template <int BN, int EVX = 0>
+struct EpiQuadformPrep {
+  using Base = EpiRowSumSq<BN>;
+  static constexpr size_t scratch_bytes(int warps) { return 1024 + static_cast<size_t>(warps) * PREP_RING_BYTES; }
+  struct Params {
+    typename Base::Params base;
+    EmbedPrepArgs prep;
+    int row_bytes;  // D * 4 (multiple of 16)
+    int slots;      // largest power of two <= min(PREP_MAX_SLOTS, PREP_RING_BYTES / row_bytes)
+    int slot_shift; // log2(slots)
+  };
+  struct State {
+    typename Base::State base;
+    uint32_t issued, consumed;
+    uint32_t ring;
+    uint64_t* bars;
+  };
+  static constexpr bool ALL_CHUNKS = false;
+  static constexpr bool UNROLL_CHUNKS = true;
+  static constexpr bool DRAIN_FIRST = false;
+
+  __device__ static void issue(State& st, const Params& p, const EpiCtx& ctx, int64_t row) {
+    const uint32_t slot = st.issued & static_cast<uint32_t>(p.slots - 1);
+    if (ctx.lane == 0) {
+      mbar_arrive_expect_tx(&st.bars[slot], static_cast<uint32_t>(p.row_bytes));
+      bulk_load_1d(st.ring + slot * static_cast<uint32_t>(p.row_bytes), p.prep.x + row * p.prep.ld,
+                   static_cast<uint32_t>(p.row_bytes), &st.bars[slot]);
+    }
+    ++st.issued;
+  }
+  __device__ static void kernel_begin(State& st, const Params& p, const EpiCtx& ctx) {
+    st.issued = st.consumed = 0;
+    st.bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(ctx.scratch) + 512) + ctx.wid * PREP_MAX_SLOTS;
+    st.ring = ctx.scratch_u32 + 1024u + static_cast<uint32_t>(ctx.wid) * PREP_RING_BYTES;
+    if (ctx.lane == 0) {
+      for (int i = 0; i < p.slots; ++i) mbar_init(&st.bars[i], 1);
+      fence_barrier_init();
+      fence_proxy_async_smem();
+    }
+    __syncwarp();
+  }
+  __device__ static void kernel_end(State&, const Params&, const EpiCtx&) {}
+  __device__ static void item_begin(State& st, const Params& p, const EpiCtx& ctx, const TileCoord& tc) {
+    Base::item_begin(st.base, p.base, ctx, tc);
+    const int per_warp = GEMM_BM / ctx.n_warps;
+    for (int j = 0; j < p.slots && j < per_warp; ++j) {
+      const int64_t row = tc.row0 + ctx.wid + ctx.n_warps * j;
+      if (row >= p.prep.R) break;
+      issue(st, p, ctx, row);
+    }
+  }
+  __device__ static void tile_begin(State& st, const Params& p, const EpiCtx& ctx, const TileCoord& tc) {
+    // column tile n of T converts the j range proportional to its share (n + 1) / (T (T + 1) / 2) of the triangular K
+    // loop, BEFORE waiting for the tile's accumulator: the conversion is spread over the main loop of the row panel
+    const int T = (ctx.N + BN - 1) / BN, per_warp = GEMM_BM / ctx.n_warps;
+    const int j0 = per_warp * tc.n * (tc.n + 1) / (T * (T + 1)), j1 = per_warp * (tc.n + 1) * (tc.n + 2) / (T * (T + 1));
+    for (int j = j0; j < j1; ++j) {
+      const int64_t row = tc.row0 + ctx.wid + ctx.n_warps * j;
+      if (row >= p.prep.R) break;
+      const uint32_t slot = st.consumed & static_cast<uint32_t>(p.slots - 1);
+      mbar_wait(&st.bars[slot], (st.consumed >> p.slot_shift) & 1u);
+      ++st.consumed;
+      const uint32_t src = st.ring + slot * static_cast<uint32_t>(p.row_bytes);
+      constexpr int EV = EVX > 0 ? EVX : 8;
+      float4 e[EV];
+#pragma unroll
+      for (int i = 0; i < EV; ++i) {
+        const int c = (i * 32 + ctx.lane) * 4;
+        e[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (EVX > 0 || c < p.prep.D) e[i] = lds_v4(src + static_cast<uint32_t>(c) * 4u);
+      }
+      // pass 1 ends in warp reductions over values derived from every lane's e[]: all reads of the slot have completed,
+      // so it can be handed back to the copy engine (write-after-read needs no proxy fence, as in any TMA pipeline)
+      const EmbedRowStats rs = embed_row_stats<EV, (EVX > 0)>(p.prep, ctx.lane, e);
+      const int jn = j + p.slots;
+      const int64_t row_n = tc.row0 + ctx.wid + ctx.n_warps * jn;
+      if (jn < per_warp && row_n < p.prep.R) issue(st, p, ctx, row_n);
+      embed_row_store<EV, (EVX > 0)>(p.prep, row, ctx.lane, e, rs);
+    }
+  }
+  __device__ static void chunk(State& st, const Params& p, const EpiCtx& ctx, const TileCoord& tc, float (&v)[32], int c) {
+    Base::chunk(st.base, p.base, ctx, tc, v, c);
+  }
+  __device__ static void tile_end(State&, const Params&, const EpiCtx&, const TileCoord&) {}
+  __device__ static void item_end(State& st, const Params& p, const EpiCtx& ctx, const TileCoord& tc) {
+    Base::item_end(st.base, p.base, ctx, tc);
   }
 };
 

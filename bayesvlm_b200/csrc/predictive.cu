@@ -36,7 +36,7 @@ constexpr float PRED_OPSCALE_F8 = 128.f * 32.f;  // target side of the fp16 + fp
 // out[i] = | W16 act16_i |^2  through the row-panel GEMM with the sum-of-squares epilogue.
 int quadform_impl(const float* act, int64_t n, int64_t d, int64_t ld, int append_one, const void* W16, int64_t dA,
                   int64_t k_pad, float w_scale, float* out, void* ws, size_t ws_bytes, cudaStream_t st,
-                  bool converted = false) {
+                  bool converted = false, const EmbedPrepArgs* side = nullptr) {
   if (n <= 0) return BVLM_OK;
   if (dA != d + (append_one ? 1 : 0) || k_pad != pad64(dA)) return BVLM_EINVAL;
   if (ws_bytes < bvlm_quadform_workspace_bytes(n, d, append_one)) return BVLM_EWORKSPACE;
@@ -58,6 +58,23 @@ int quadform_impl(const float* act, int64_t n, int64_t d, int64_t ld, int append
                                       FMT_F16);
   plan.tri_k = 1;
   EpiRowSumSq<PRED_BN>::Params ep{out, row_unscale, 1.0f / (w_scale * w_scale)};
+  if (side != nullptr) {  // the epilogue warps also convert the embedding rows of their panel (EpiQuadformPrep)
+    const int row_bytes = static_cast<int>(side->D * 4);
+    int slot_shift = 0;
+    while ((2 << slot_shift) <= std::min(PREP_MAX_SLOTS, PREP_RING_BYTES / row_bytes)) ++slot_shift;
+    const int slots = 1 << slot_shift;
+    const bool exact = side->D % 128 == 0 && side->seg_pad == side->D && (side->nsplit != 2 || side->seg8 == side->D);
+#define BVLM_QPREP(EVX)                                                                                       \
+    do {                                                                                                      \
+      EpiQuadformPrep<PRED_BN, EVX>::Params ep2{ep, *side, row_bytes, slots, slot_shift};                     \
+      return launch_gemm2<PRED_BN, 4, 8, EpiQuadformPrep<PRED_BN, EVX>>(tmA, tmB, plan, ep2, st, TAG_QUADFORM); \
+    } while (0)
+    if (exact && side->D == 512) BVLM_QPREP(4);
+    if (exact && side->D == 768) BVLM_QPREP(6);
+    if (exact && side->D == 1024) BVLM_QPREP(8);
+    BVLM_QPREP(0);
+#undef BVLM_QPREP
+  }
   return launch_gemm2<PRED_BN, 6, 4, EpiRowSumSq<PRED_BN>>(tmA, tmB, plan, ep, st, TAG_QUADFORM);
 }
 
@@ -169,11 +186,21 @@ int bvlm_predictive(const float* E, int64_t N, int64_t D, int64_t lde, const flo
   Carver qcv(qws);  // same carve as quadform_impl
   __half* act16 = qcv.take<__half>(static_cast<size_t>(N) * k_pad);
   float* act_unscale = qcv.take<float>(static_cast<size_t>(N));
-  rc = launch_predictive_embed_prep(E, N, D, lde, delta, precision, E16, seg, e_pitch, A8, seg8, n2, pd, esc, Eact, d_act,
-                                    ldact, append_one, act16, k_pad, act_unscale, st);
+  // Embeddings: converted by the epilogue warps of the quadratic-form GEMM (tensor-bound, its epilogue nearly idle) when the
+  // rows are 16-byte aligned and fit its register-resident row routine; by the row-prep kernel otherwise.
+  static const bool fuse_env = [] {
+    const char* e = getenv("BVLM_PRED_FUSE_PREP");
+    return e == nullptr || atoi(e) != 0;
+  }();
+  const auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  const bool fuse = fuse_env && al16(E) && al16(delta) && (lde % 4) == 0 && (D % 4) == 0 && D * 4 <= PREP_RING_BYTES && (e_pitch % 4) == 0 && seg <= 1024 &&
+                    (precision != BVLM_PREC_X2F8 || seg8 <= 1024);
+  EmbedPrepArgs side{E, N, D, lde, delta, precision, E16, seg, e_pitch, A8, seg8, n2, pd, esc};
+  rc = launch_predictive_embed_prep(fuse ? nullptr : E, N, D, lde, delta, precision, E16, seg, e_pitch, A8, seg8, n2, pd, esc,
+                                    Eact, d_act, ldact, append_one, act16, k_pad, act_unscale, st);
   if (rc) return rc;
   rc = quadform_impl(Eact, N, d_act, ldact, append_one, Wi16, dA, k_pad, w_scale, alpha, qws, ws_bytes - used, st,
-                     /*converted=*/true);
+                     /*converted=*/true, fuse ? &side : nullptr);
   if (rc) return rc;
   CUtensorMap tmA, tmB;
   Operand16 opA{E16, N, kp, FMT_F16, e_pitch};

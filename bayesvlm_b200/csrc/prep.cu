@@ -2,6 +2,8 @@
 
 #include <cuda_fp8.h>
 
+#include "rowprep_device.cuh"
+
 namespace bvlm {
 
 namespace {
@@ -157,6 +159,7 @@ k_predictive_embed_prep(const float* __restrict__ x, int64_t R, int64_t D, int64
       *reinterpret_cast<__half2*>(oa + j) = __floats2half2_rn(v0, v1);
     }
   }
+  if (x == nullptr) return;  // embeddings converted elsewhere (epilogue warps of the quadratic-form GEMM)
   const float* xr = x + row * ld;
   float n2 = 0.f, pd = 0.f, amax = 0.f;
   for (int64_t j = lane; j < D; j += 32) {
@@ -264,76 +267,13 @@ k_predictive_prep_vec(const float* __restrict__ x, int64_t R, int64_t D, int64_t
     }
   }
   // ---------------- embeddings -> fp16 (+ lo fp16 | + fp8 compensation terms), row statistics
-  const float* xr = x + row * ld;
+  // (skipped when the quadratic-form GEMM converts them in its epilogue warps: x == nullptr)
+  if (x == nullptr) return;
+  EmbedPrepArgs ea{x, R, D, ld, diag_other, nsplit, packed, seg_pad, out_pitch > 0 ? out_pitch : seg_pad * (nsplit == 3 ? 2 : 1),
+                   packed8, seg8, n2_out, pd_out, unscale_out};
   float4 e[EV];
-  float n2 = 0.f, pd = 0.f, amax = 0.f;
-#pragma unroll
-  for (int i = 0; i < EV; ++i) {
-    const int64_t c = (static_cast<int64_t>(i) * 32 + lane) * 4;
-    e[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 dl = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (c + 3 < D) {
-      e[i] = __ldg(reinterpret_cast<const float4*>(xr + c));
-      dl = __ldg(reinterpret_cast<const float4*>(diag_other + c));
-    } else if (c < D) {
-      e[i].x = xr[c];
-      dl.x = diag_other[c];
-      if (c + 1 < D) e[i].y = xr[c + 1], dl.y = diag_other[c + 1];
-      if (c + 2 < D) e[i].z = xr[c + 2], dl.z = diag_other[c + 2];
-    }
-    const float4 q = make_float4(e[i].x * e[i].x, e[i].y * e[i].y, e[i].z * e[i].z, e[i].w * e[i].w);
-    n2 += (q.x + q.y) + (q.z + q.w);
-    pd = fmaf(q.x, dl.x, fmaf(q.y, dl.y, fmaf(q.z, dl.z, fmaf(q.w, dl.w, pd))));
-    amax = fmaxf(amax, fmaxf(fmaxf(fabsf(e[i].x), fabsf(e[i].y)), fmaxf(fabsf(e[i].z), fabsf(e[i].w))));
-  }
-  n2 = warp_sum(n2);
-  pd = warp_sum(pd);
-  amax = warp_max(amax);
-  int ee = 0;
-  if (amax > 0.f && isfinite(amax)) {
-    int ex;
-    frexpf(amax, &ex);
-    ee = (nsplit == 2 ? 8 : 9) - ex;
-    ee = ee < -60 ? -60 : (ee > 60 ? 60 : ee);
-  }
-  const float sc = ldexpf(1.f, ee) * (nsplit == 2 ? 32.f : 1.f);
-  const int64_t pitch = out_pitch > 0 ? out_pitch : seg_pad * (nsplit == 3 ? 2 : 1);
-  __half* o = packed + row * pitch;
-  uint8_t* o8 = nsplit == 2 ? packed8 + row * 2 * seg8 : nullptr;
-#pragma unroll
-  for (int i = 0; i < EV; ++i) {
-    const int64_t c = (static_cast<int64_t>(i) * 32 + lane) * 4;
-    const float v0 = e[i].x * sc, v1 = e[i].y * sc, v2 = e[i].z * sc, v3 = e[i].w * sc;
-    const __half2 h0 = __floats2half2_rn(v0, v1), h1 = __floats2half2_rn(v2, v3);
-    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
-    if (c < seg_pad) {
-      uint2 pk;
-      pk.x = *reinterpret_cast<const uint32_t*>(&h0);
-      pk.y = *reinterpret_cast<const uint32_t*>(&h1);
-      *reinterpret_cast<uint2*>(o + c) = pk;
-      if (nsplit == 3) {
-        const __half2 l0 = __floats2half2_rn(v0 - f0.x, v1 - f0.y), l1 = __floats2half2_rn(v2 - f1.x, v3 - f1.y);
-        pk.x = *reinterpret_cast<const uint32_t*>(&l0);
-        pk.y = *reinterpret_cast<const uint32_t*>(&l1);
-        *reinterpret_cast<uint2*>(o + seg_pad + c) = pk;
-      }
-    }
-    if (nsplit == 2 && c < seg8) {
-      const uint32_t lo8 =
-          static_cast<uint32_t>(__nv_cvt_float2_to_fp8x2(make_float2((v0 - f0.x) * 32.f, (v1 - f0.y) * 32.f), __NV_SATFINITE, __NV_E4M3)) |
-          (static_cast<uint32_t>(__nv_cvt_float2_to_fp8x2(make_float2((v2 - f1.x) * 32.f, (v3 - f1.y) * 32.f), __NV_SATFINITE, __NV_E4M3)) << 16);
-      const uint32_t x8 =
-          static_cast<uint32_t>(__nv_cvt_float2_to_fp8x2(make_float2(v0 * 0.03125f, v1 * 0.03125f), __NV_SATFINITE, __NV_E4M3)) |
-          (static_cast<uint32_t>(__nv_cvt_float2_to_fp8x2(make_float2(v2 * 0.03125f, v3 * 0.03125f), __NV_SATFINITE, __NV_E4M3)) << 16);
-      *reinterpret_cast<uint32_t*>(o8 + c) = lo8;
-      *reinterpret_cast<uint32_t*>(o8 + seg8 + c) = x8;
-    }
-  }
-  if (lane == 0) {
-    n2_out[row] = n2;
-    pd_out[row] = pd;
-    unscale_out[row] = ldexpf(1.f, -ee);
-  }
+  embed_row_load<EV>(ea, row, lane, e);
+  embed_row_finish<EV>(ea, row, lane, e);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -831,7 +771,7 @@ int launch_predictive_embed_prep(const float* x, int64_t R, int64_t D, int64_t l
   // fast path: 16-byte aligned rows that fit the register-resident kernel (covers every model of the reference)
   const auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   const int64_t ecols = seg_pad > seg8 && nsplit == 2 ? seg_pad : (nsplit == 2 ? seg8 : seg_pad);
-  const bool vec_ok = act != nullptr && al16(x) && al16(act) && al16(diag_other) && al16(packed) && al16(act16) &&
+  const bool vec_ok = act != nullptr && (x == nullptr || al16(x)) && al16(act) && al16(diag_other) && al16(packed) && al16(act16) &&
                       (ld % 4) == 0 && (ld_act % 4) == 0 && (seg_pad % 4) == 0 && (act_kpad % 4) == 0 &&
                       ((out_pitch > 0 ? out_pitch : seg_pad) % 4) == 0 && (nsplit != 2 || ((seg8 % 4) == 0 && al16(packed8))) &&
                       ecols <= 1024 && act_kpad <= 3200;
