@@ -119,12 +119,6 @@ def update_embeddings(projection: torch.nn.Module, outputs: EncoderResult, devic
     return new if keep_on_device else new.to("cpu")
 
 
-def _diag_embedding_cov(acts, cov, has_bias):
-    if has_bias:
-        acts = torch.cat([acts, torch.ones_like(acts[:, :1])], dim=1)
-    return ((acts @ cov.A_inv) * acts).sum(-1, keepdim=True) * cov.B_inv.diagonal()
-
-
 def select_epig_online(label_features: EncoderResult, pool_features: EncoderResult, target_features: EncoderResult,
                        pool_class_ids: torch.Tensor, image_projection: torch.nn.Linear, clip: CLIP, A_img: torch.Tensor,
                        A_txt: torch.Tensor, B_img: torch.Tensor, B_txt: torch.Tensor, cov_info: dict, budget: int,
@@ -164,16 +158,12 @@ def select_epig_online(label_features: EncoderResult, pool_features: EncoderResu
         else:
             idx_pool = torch.arange(n_pool_all)
     elif pool_subsampling in ("knn_cosine", "knn_wasserstein"):
-        mu_train, mu_test = pool_features.embeds, target_features.embeds[idx_targ]
-        cov_train = _diag_embedding_cov(pool_features.activations, cov_img, proj_has_bias)
-        cov_test = _diag_embedding_cov(target_features.activations[idx_targ], cov_img, proj_has_bias)
-        if pool_subsampling == "knn_cosine":
-            tr = mu_train / torch.sqrt((mu_train ** 2 + cov_train).sum(-1, keepdim=True))
-            te = mu_test / torch.sqrt((mu_test ** 2 + cov_test).sum(-1, keepdim=True))
-            sim = te @ tr.t()
-        else:  # negative diagonal 2-Wasserstein distance (reference knn.py:6-20)
-            sim = -(torch.cdist(mu_test, mu_train) ** 2 + cov_test.sum(-1)[:, None] + cov_train.sum(-1)[None, :]
-                    - 2 * cov_test.sqrt() @ cov_train.sqrt().t())
+        from .knn import expected_cosine_similarity, negative_wasserstein_similarity
+
+        test_sub = EncoderResult(embeds=target_features.embeds[idx_targ.to(device)],
+                                 activations=target_features.activations[idx_targ.to(device)])
+        similarity = expected_cosine_similarity if pool_subsampling == "knn_cosine" else negative_wasserstein_similarity
+        sim = similarity(test_sub, pool_features, cov_img, has_bias=proj_has_bias)  # [targets, pool] on the kernels
         nearest = torch.argsort(sim, descending=True, dim=1)
         idx_pool = nearest[:, :k_nearest_neighbors].flatten().unique().cpu()
         if len(idx_pool) < budget:

@@ -324,3 +324,67 @@ def epig_from_probs_f32(pool, targ):
         v = np.where(joint > 0, joint * np.log(joint), 0.0)
     h_joint = -v.sum(axis=(2, 3)).mean(axis=1)
     return h_pool + h_targ - h_joint
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Support-set search (reference bayesvlm/knn.py) -- SURVEY.md section 8(f) row 3
+# ---------------------------------------------------------------------------------------------------------------------
+def _knn_diag_cov(acts, A_inv, B_inv, dtype):
+    a = np.asarray(acts, dtype)
+    return ((a @ np.asarray(A_inv, dtype)) * a).sum(-1)[:, None] * np.asarray(B_inv, dtype).diagonal()   # knn.py:66-69
+
+
+def knn_expected_cosine(test_embeds, test_acts, train_embeds, train_acts, A_inv, B_inv, dtype=np.float32):
+    """[N_test, N_train] expected cosine similarity, operation by operation as knn.py:66-79."""
+    mu_te, mu_tr = np.asarray(test_embeds, dtype), np.asarray(train_embeds, dtype)
+    cov_te, cov_tr = _knn_diag_cov(test_acts, A_inv, B_inv, dtype), _knn_diag_cov(train_acts, A_inv, B_inv, dtype)
+    en_tr = (mu_tr * mu_tr + cov_tr).sum(-1, keepdims=True)          # :71-72
+    en_te = (mu_te * mu_te + cov_te).sum(-1, keepdims=True)          # :73-74
+    return (mu_te / np.sqrt(en_te)) @ (mu_tr / np.sqrt(en_tr)).T     # :77-80
+
+
+def knn_diagonal_wasserstein(mu1, mu2, cov1, cov2, dtype=np.float32):
+    """knn.py:6-17.  The pairwise squared distance is formed from differences (the quantity ``cdist(...)**2`` stands for;
+    torch's own evaluation goes through a matmul for large inputs and carries fp32 cancellation noise)."""
+    mu1, mu2 = np.asarray(mu1, dtype), np.asarray(mu2, dtype)
+    cov1, cov2 = np.asarray(cov1, dtype), np.asarray(cov2, dtype)
+    l2 = ((mu1[:, None, :] - mu2[None, :, :]) ** 2).sum(-1)          # :8
+    cross = 2 * (np.sqrt(cov1) @ np.sqrt(cov2).T)                    # :11
+    return l2 + cov1.sum(-1)[:, None] + cov2.sum(-1)[None, :] - cross   # :14
+
+
+def knn_neg_wasserstein(test_embeds, test_acts, train_embeds, train_acts, A_inv, B_inv, dtype=np.float32):
+    """[N_test, N_train] similarity of find_similar_samples_wasserstein (knn.py:163-169)."""
+    cov_te, cov_tr = _knn_diag_cov(test_acts, A_inv, B_inv, dtype), _knn_diag_cov(train_acts, A_inv, B_inv, dtype)
+    return -knn_diagonal_wasserstein(test_embeds, train_embeds, cov_te, cov_tr, dtype)
+
+
+def knn_support(sim, indices_test, values_test, k_nearest, buffersize=150):
+    """Support-set selection from a similarity matrix, loop by loop as knn.py:86-135 (also :171-218).
+    Returns {test_idx: dict(score, indices, similarities)} in insertion order."""
+    sim = np.asarray(sim)
+    n_test, n_train = sim.shape
+    width = min(k_nearest + buffersize, n_train)
+    order = np.argsort(-sim, axis=1, kind="stable")[:, :width]       # topk, sorted descending (:86)
+    vals = np.take_along_axis(sim, order, axis=1)
+    goal = k_nearest * n_test
+    k_ = k_nearest
+    while True:                                                      # :90-106
+        flat = order[:, :k_].T.flatten()                             # :92
+        if len(np.unique(flat)) >= goal:                             # :99
+            while len(np.unique(flat)) > goal:                       # :23-26
+                flat = flat[:-1]
+            break
+        if k_ >= width:
+            raise ValueError("not enough distinct neighbours")      # (the reference would loop forever here)
+        k_ += 1
+    kept = set(np.unique(flat).tolist())                             # :108
+    out = {}
+    for i in range(n_test):                                          # :114-133
+        ids, sims = [], []
+        for idx, val in zip(order[i, :k_], vals[i, :k_]):
+            if int(idx) in kept:
+                ids.append(int(idx))
+                sims.append(float(val))
+        out[int(indices_test[i])] = dict(score=float(values_test[i]), indices=ids, similarities=sims)
+    return out

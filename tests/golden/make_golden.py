@@ -166,10 +166,62 @@ def main():
 
     np.savez_compressed(OUT / "reference_small.npz", **out)
     meta = {"torch": torch.__version__, "reference": "MridulPandey17/BayesVLM @ /root/reference",
-            "files": ["reference_small.npz", "b32_config1.npz"], "keys": sorted(out)}
+            "files": ["reference_small.npz", "b32_config1.npz", "knn_small.npz"], "keys": sorted(out)}
     (OUT / "golden_meta.json").write_text(json.dumps(meta, indent=1))
+    make_knn()
     print("wrote", OUT)
 
 
+def make_knn():
+    """Support-set search (bayesvlm/knn.py) on a small clustered problem -> knn_small.npz.  `python make_golden.py knn`
+    regenerates only this file."""
+    import contextlib
+    import io
+
+    sys.path.insert(0, str(REF))
+    import bayesvlm.knn as r_knn
+    import bayesvlm.vlm as r_vlm
+    from bayesvlm.hessians import KroneckerFactorizedCovariance
+
+    g = torch.Generator().manual_seed(606)
+    D, d_act, n_train, n_test, n_centres = 24, 32, 300, 40, 12
+    centres, centres_a = randn(g, n_centres, D) * 2.0, randn(g, n_centres, d_act)
+    lab_tr, lab_te = torch.randint(0, n_centres, (n_train,), generator=g), torch.randint(0, n_centres, (n_test,), generator=g)
+    train = r_vlm.EncoderResult(embeds=centres[lab_tr] + 0.7 * randn(g, n_train, D),
+                                activations=centres_a[lab_tr] + 0.5 * randn(g, n_train, d_act))
+    test = r_vlm.EncoderResult(embeds=centres[lab_te] + 0.7 * randn(g, n_test, D),
+                               activations=centres_a[lab_te] + 0.5 * randn(g, n_test, d_act))
+    cov = KroneckerFactorizedCovariance(A_inv=spd(g, d_act, 2e-2), B_inv=spd(g, D, 0.4))
+    indices_test = torch.randperm(n_test, generator=g)[:9]
+    values_test = torch.rand(9, generator=g)
+    out = dict(train_e=train.embeds.numpy(), train_a=train.activations.numpy(), test_e=test.embeds.numpy(),
+               test_a=test.activations.numpy(), A_inv=cov.A_inv.numpy(), B_inv=cov.B_inv.numpy(),
+               indices_test=indices_test.numpy(), values_test=values_test.numpy())
+    for tag, fn, k_nearest, buf in (("cos", r_knn.find_similar_samples_cosine, 3, 10),
+                                    ("wass", r_knn.find_similar_samples_wasserstein, 3, 10),
+                                    ("cos_k5", r_knn.find_similar_samples_cosine, 5, 25)):
+        with contextlib.redirect_stdout(io.StringIO()):  # the reference prints its progress
+            res = fn(train, test, indices_test, values_test, k_nearest=k_nearest, source_covariance=cov, device="cpu",
+                     buffersize=buf)
+        width = max(len(v["indices"]) for v in res.values())
+        idx = np.full((len(res), width), -1, np.int64)
+        sim = np.full((len(res), width), np.nan, np.float32)
+        for r, v in enumerate(res.values()):
+            idx[r, :len(v["indices"])] = v["indices"]
+            sim[r, :len(v["similarities"])] = v["similarities"]
+        out.update({f"{tag}_keys": np.array(list(res.keys()), np.int64), f"{tag}_scores": np.array([v["score"] for v in res.values()]),
+                    f"{tag}_indices": idx, f"{tag}_sims": sim, f"{tag}_cfg": np.array([k_nearest, buf], np.int64)})
+        ex = r_knn.extract_test_train_indices(res)
+        out[f"{tag}_extract_train"] = np.array(sorted(ex["train"]), np.int64)
+    # the distance itself on explicit covariances (knn.py:6-20)
+    c1, c2 = torch.rand(9, D, generator=g) + 0.05, torch.rand(n_train, D, generator=g) + 0.05
+    out.update(w_cov1=c1.numpy(), w_cov2=c2.numpy(),
+               w_dist=r_knn.wdist2(test.embeds[indices_test], train.embeds, c1, c2).numpy())
+    np.savez_compressed(OUT / "knn_small.npz", **out)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "knn":
+        make_knn()
+    else:
+        main()
