@@ -306,6 +306,11 @@ __device__ __forceinline__ float fast_rcp(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// fp32 + fp16 -> fp32 in one instruction (sm_100 mixed-precision add, SASS FHADD): the half is converted exactly
+__device__ __forceinline__ float add_f32_f16(float acc, __half h) {
+  asm("add.rn.f32.f16 %0, %1, %0;" : "+f"(acc) : "h"(__half_as_ushort(h)));
+  return acc;
+}
 __device__ __forceinline__ void red_add_f32(float* addr, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
 }
