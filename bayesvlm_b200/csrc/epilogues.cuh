@@ -560,10 +560,17 @@ struct EpiGgnWeights {
       const int pj = st.piv - col0;  // pivot position inside this chunk (outside [0,32) if elsewhere)
       const float dsc = GGN_WDSCALE / GGN_WSCALE;
       const float o_off = -(st.m2 + st.lgw), s_d = p.s_log2e * dsc, d_off = -st.m2 * dsc;
+      const float2 se2 = make_float2(p.s_log2e, p.s_log2e), oo2 = make_float2(o_off, o_off), sd2 = make_float2(s_d, s_d),
+                   do2 = make_float2(d_off, d_off);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        om[j] = fast_exp2(fmaf(v[j], p.s_log2e, o_off));  // 2^(d - lgw), d = l - m <= 0 (exactly 0 at the pivot)
-        v[j] = fmaf(v[j], s_d, d_off);                    // d * WDSCALE / WSCALE
+      for (int j = 0; j < 32; j += 2) {  // packed fp32x2 FMAs: half the issue slots
+        const float2 vv = make_float2(v[j], v[j + 1]);
+        const float2 ex = __ffma2_rn(vv, se2, oo2);  // d - lgw, d = l - m <= 0 (exactly 0 at the pivot)
+        const float2 dd = __ffma2_rn(vv, sd2, do2);  // d * WDSCALE / WSCALE
+        om[j] = fast_exp2(ex.x);
+        om[j + 1] = fast_exp2(ex.y);
+        v[j] = dd.x;
+        v[j + 1] = dd.y;
       }
       if (pj >= 0 && pj < 32) {  // the pivot itself carries no conditional weight
 #pragma unroll
@@ -578,7 +585,11 @@ struct EpiGgnWeights {
     if (h == 0) slab_wait_free<1>(ctx.lane);  // every bulk store but the most recent one has finished reading
     if constexpr (!SIGLIP) slab_write_f16_half(wbase + static_cast<uint32_t>(b0) * SLAB_BYTES, ctx.lane, h, om);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] *= om[j];
+    for (int j = 0; j < 32; j += 2) {
+      const float2 pr = __fmul2_rn(make_float2(v[j], v[j + 1]), make_float2(om[j], om[j + 1]));
+      v[j] = pr.x;
+      v[j + 1] = pr.y;
+    }
     slab_write_f16_half(wbase + static_cast<uint32_t>(b1) * SLAB_BYTES, ctx.lane, h, v);
     if (h == 1) {
       const int row0 = tc.row0 + ctx.ew * 32;
@@ -592,8 +603,13 @@ struct EpiGgnWeights {
       if (st.sidx >= 3) st.sidx -= 3;
     }
     // ---- weighted column sums of this 32 x 32 block: butterfly over the rows, accumulated in shared memory
+    const float2 w2 = make_float2(st.w, st.w);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) om[j] *= st.w;
+    for (int j = 0; j < 32; j += 2) {
+      const float2 pr = __fmul2_rn(make_float2(om[j], om[j + 1]), w2);
+      om[j] = pr.x;
+      om[j + 1] = pr.y;
+    }
     const float qv = warp_transpose_reduce32(om, ctx.lane);
     const uint32_t qa = qsum_addr(ctx) + 4u * static_cast<uint32_t>(ctx.ew * BN + c * 32 + ctx.lane);
     sts_f32(qa, lds_f32(qa) + qv);
