@@ -166,9 +166,10 @@ def main():
 
     np.savez_compressed(OUT / "reference_small.npz", **out)
     meta = {"torch": torch.__version__, "reference": "MridulPandey17/BayesVLM @ /root/reference",
-            "files": ["reference_small.npz", "b32_config1.npz", "knn_small.npz"], "keys": sorted(out)}
+            "files": ["reference_small.npz", "b32_config1.npz", "knn_small.npz", "selection_small.npz"], "keys": sorted(out)}
     (OUT / "golden_meta.json").write_text(json.dumps(meta, indent=1))
     make_knn()
+    make_selection()
     print("wrote", OUT)
 
 
@@ -220,8 +221,45 @@ def make_knn():
     np.savez_compressed(OUT / "knn_small.npz", **out)
 
 
+def make_selection():
+    """Acquisition scores / subset selection (bayesvlm/selection.py) on CPU tensors -> selection_small.npz.
+    `python make_golden.py selection` regenerates only this file."""
+    sys.path.insert(0, str(REF))
+    import bayesvlm.selection as r_sel
+    import bayesvlm.vlm as r_vlm
+
+    g = torch.Generator().manual_seed(707)
+    n, c = 60, 7
+    mean, var = randn(g, n, c) * 3, torch.rand(n, c, generator=g) * 4 + 0.05
+    class_ids = torch.randint(0, 4, (n,), generator=g)
+    pl = r_vlm.ProbabilisticLogits(mean=mean, var=var)
+    out = dict(mean=mean.numpy(), var=var.numpy(), class_ids=class_ids.numpy())
+    for ev in ("map_alea", "comb", "comb_covar", "exp_alea"):
+        torch.manual_seed(11)  # exp_alea is not seeded by the reference: seed the global generator around the call
+        out[f"entropy_{ev}"] = r_sel._entropy(mean, var, ev, num_samples=25, seed=3).numpy()
+    out["score_var"] = r_sel.complexity_score(pl, "var").numpy()  # 2-D var: the diagonal of the N x C matrix -> a scalar
+    torch.manual_seed(12)
+    out["score_map_mi"] = r_sel.complexity_score(pl, "map_mutual_info", seed=5).numpy()
+    torch.manual_seed(13)
+    out["score_exp_mi"] = r_sel.complexity_score(pl, "exp_mutual_info", seed=5).numpy()
+    idx, val = r_sel.select_topk(pl, 9, "entropy", "map_alea", ignore_percentage=0.1, return_values=True)
+    out["topk_entropy_idx"], out["topk_entropy_val"] = idx.numpy(), val.numpy()
+    out["topk_cb_var"] = r_sel.select_topk_classbalanced(pl, class_ids, 10, "var").numpy()
+    out["topk_cb_entropy"] = r_sel.select_topk_classbalanced(pl, class_ids, 10, "entropy", "map_alea").numpy()
+    out["topk_rand"] = r_sel.select_topk_randomized(pl, 8, 1.5, "entropy", "comb", seed=4).numpy()
+    out["random_cb"] = r_sel.select_random_classbalanced(var, class_ids, 10, seed=6).numpy()
+    out["random"] = r_sel.select_random(pl, 12, seed=8).numpy()
+    cov = torch.stack([torch.diag(v) + 0.01 for v in var[:10]])
+    out["score_logdet"] = r_sel.complexity_score(r_vlm.ProbabilisticLogits(mean=mean[:10], var=cov), "logdet").numpy()
+    out["score_var3d"] = r_sel.complexity_score(r_vlm.ProbabilisticLogits(mean=mean[:10], var=cov), "var").numpy()
+    out["topk_var3d"] = r_sel.select_topk(r_vlm.ProbabilisticLogits(mean=mean[:10], var=cov), 4, "var").numpy()
+    np.savez_compressed(OUT / "selection_small.npz", **out)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "knn":
         make_knn()
+    elif len(sys.argv) > 1 and sys.argv[1] == "selection":
+        make_selection()
     else:
         main()
