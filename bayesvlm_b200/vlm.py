@@ -455,9 +455,11 @@ class CLIP(torch.nn.Module):
             if tuple(mean.shape) != (n, c) or tuple(var.shape) != (n, c):
                 raise ValueError("out buffers must be [N, C]")
         else:
-            mk = dict(dtype=torch.float32, pin_memory=out_pinned)
-            mean, var = torch.empty((n, c), **mk), torch.empty((n, c), **mk)
-            probs = torch.empty((n, c), **mk) if return_probs else None
+            from .hostmem import pinned_empty  # page-locked on the GPU's NUMA node
+
+            mk = (lambda: pinned_empty((n, c), device=dev)) if out_pinned else (lambda: torch.empty((n, c)))
+            mean, var = mk(), mk()
+            probs = mk() if return_probs else None
         bs = max(1, min(batch_size, n))
         key = (dev, bs, c, d, d_act, return_probs)
         pipe = getattr(self, "_host_pipe", None)

@@ -270,10 +270,12 @@ def run_b200(args, rank, world, local_rank):
                 "hbm_peak_gbs": peaks["hbm_gbs"]}
 
     # ------------------------------------------------------------------ end to end: host buffers through the public API
-    img_host = EncoderResult(t["img_e"].pin_memory(), t["img_a"].pin_memory())
-    txt_host = EncoderResult(t["txt_e"].pin_memory(), t["txt_a"].pin_memory())
+    from bayesvlm_b200.hostmem import pin, pinned_empty  # pinned staging buffers on the GPU's NUMA node
+
+    img_host = EncoderResult(pin(t["img_e"], dev), pin(t["img_a"], dev))
+    txt_host = EncoderResult(pin(t["txt_e"], dev), pin(t["txt_a"], dev))
     e2e_steps = max(1, min(K, 10))
-    host_out = (torch.empty((cfg["N"], cfg["C"]), pin_memory=True), torch.empty((cfg["N"], cfg["C"]), pin_memory=True))
+    host_out = (pinned_empty((cfg["N"], cfg["C"]), device=dev), pinned_empty((cfg["N"], cfg["C"]), device=dev))
     for _ in range(2):
         model.predict_host(img_host, txt_host, batch_size=args.e2e_batch, out=host_out)
     barrier_sync()
