@@ -435,7 +435,7 @@ class CLIP(torch.nn.Module):
 
     # ------------------------------------------------------------------------------------------------------------
     @torch.no_grad()
-    def predict_host(self, image_outputs: EncoderResult, text_outputs: EncoderResult, batch_size: int = 16384,
+    def predict_host(self, image_outputs: EncoderResult, text_outputs: EncoderResult, batch_size: int = 2048,
                      return_probs: bool = False, out_pinned: bool = True, out=None):
         """End-to-end predictive for HOST-resident features (the `make_predictions` data flow, precompute.py:18-65).
 

@@ -403,7 +403,8 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--e2e-batch", type=int, default=6250)
+    ap.add_argument("--e2e-batch", type=int, default=2048,
+                    help="image batch of the three-stream host pipeline (scripts/e2e_sweep.py: 2048 is the measured optimum)")
     ap.add_argument("--kfac-class-batches", type=int, default=2, help="class batches of 32768 per GPU per KFAC step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", default=None, help="mean-logit GEMM precision: fp16x3 | fp16+fp8 | fp16 (default: the library's)")

@@ -15,7 +15,7 @@ for bs in [int(a) for a in sys.argv[1:]] or [1563, 2048, 3125, 4167, 6250, 12500
     for _ in range(2):
         m.predict_host(img, txt, batch_size=bs, out=out)
     torch.cuda.synchronize(); t0 = time.perf_counter()
-    for _ in range(8):
+    for _ in range(24):
         m.predict_host(img, txt, batch_size=bs, out=out)
     torch.cuda.synchronize()
-    print(bs, round((time.perf_counter() - t0) / 8 * 1e3, 3), "ms", flush=True)
+    print(bs, round((time.perf_counter() - t0) / 24 * 1e3, 3), "ms", flush=True)
