@@ -113,3 +113,13 @@ def test_product_refuses_cpu(knn):
     with pytest.raises(RuntimeError):
         find_similar_samples_cosine(EncoderResult(t("train_e"), t("train_a")), EncoderResult(t("test_e"), t("test_a")),
                                     t("indices_test"), t("values_test"), 3, cov, device="cpu", buffersize=10)
+
+
+def test_hostmem_degrades_without_gpu():
+    """bayesvlm_b200.hostmem is best effort: without a CUDA device / NVML the placement helpers are no-ops."""
+    from bayesvlm_b200.hostmem import gpu_local_cpus, numa_local
+
+    if not torch.cuda.is_available():
+        assert gpu_local_cpus("cuda:0") is None
+    with numa_local("cpu") as bound:
+        assert bound is False
