@@ -193,8 +193,8 @@ int bvlm_predictive(const float* E, int64_t N, int64_t D, int64_t lde, const flo
     return e == nullptr || atoi(e) != 0;
   }();
   const auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-  const bool fuse = fuse_env && al16(E) && al16(delta) && (lde % 4) == 0 && (D % 4) == 0 && D * 4 <= PREP_RING_BYTES && (e_pitch % 4) == 0 && seg <= 1024 &&
-                    (precision != BVLM_PREC_X2F8 || seg8 <= 1024);
+  const bool fuse = fuse_env && al16(E) && al16(delta) && (lde % 4) == 0 && (D % 4) == 0 && D * 4 <= PREP_RING_BYTES &&
+                    (e_pitch % 4) == 0 && seg <= 1024 && (precision != BVLM_PREC_X2F8 || seg8 <= 1024);
   EmbedPrepArgs side{E, N, D, lde, delta, precision, E16, seg, e_pitch, A8, seg8, n2, pd, esc};
   rc = launch_predictive_embed_prep(fuse ? nullptr : E, N, D, lde, delta, precision, E16, seg, e_pitch, A8, seg8, n2, pd, esc,
                                     Eact, d_act, ldact, append_one, act16, k_pad, act_unscale, st);

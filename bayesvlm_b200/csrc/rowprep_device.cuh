@@ -141,22 +141,4 @@ __device__ __forceinline__ void embed_row_finish(const EmbedPrepArgs& a, int64_t
   embed_row_store<EV, EXACT>(a, row, lane, e, rs);
 }
 
-// rows row0, row0 + stride, ... (< row_end) of one warp, two rows in flight
-template <int EV>
-__device__ __forceinline__ void embed_rows_warp(const EmbedPrepArgs& a, int64_t row0, int64_t row_end, int64_t stride,
-                                                int lane) {
-  if (a.x == nullptr || row0 >= row_end) return;
-  float4 cur[EV], nxt[EV];
-  embed_row_load<EV>(a, row0, lane, cur);
-  for (int64_t r = row0; r < row_end; r += stride) {
-    const bool more = r + stride < row_end;
-    if (more) embed_row_load<EV>(a, r + stride, lane, nxt);
-    embed_row_finish<EV>(a, r, lane, cur);
-    if (more) {
-#pragma unroll
-      for (int i = 0; i < EV; ++i) cur[i] = nxt[i];
-    }
-  }
-}
-
 }  // namespace bvlm
