@@ -257,7 +257,7 @@ int bvlm_epig_joint_entropy_f16(const void* pool16, int64_t Np, const void* targ
   plan.a_tx_bytes = static_cast<uint32_t>(ppt * Cl * GEMM_BK * 2);
   EpiEpigJoint<EPIG_BN>::Params ep{Hjoint, Np, static_cast<int>(Cl), ppt, static_cast<int>(col_chunk / EPIG_BN),
                                    1.0f / static_cast<float>(K), static_cast<float>(Nt)};
-  return launch_gemm2<EPIG_BN, 6, 8, EpiEpigJoint<EPIG_BN>>(tmA, tmB, plan, ep, st, TAG_EPIG_JOINT);
+  return launch_gemm2<EPIG_BN, 6, 16, EpiEpigJoint<EPIG_BN>>(tmA, tmB, plan, ep, st, TAG_EPIG_JOINT);
 }
 
 }  // extern "C"

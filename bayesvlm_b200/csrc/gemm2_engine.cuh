@@ -122,7 +122,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const __grid_constant__ CUtensorMap tmA8, const __grid_constant__ CUtensorMap tmB8, const GemmPlan plan,
                 const __grid_constant__ typename Epi::Params ep) {
   static_assert(BN % 64 == 0 && BN >= 64 && BN <= 256, "BN must be a multiple of 64 in [64,256]");
-  static_assert(EPI_WARPS == 4 || EPI_WARPS == 8, "4 or 8 epilogue warps");
+  static_assert(EPI_WARPS == 4 || EPI_WARPS == 8 || EPI_WARPS == 16, "4, 8 or 16 epilogue warps");
   constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;    // this CTA's 128 rows of A
   constexpr int B_BYTES = (BN / 2) * GEMM_BK * 2;   // this CTA's half of the B tile
   constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
