@@ -388,7 +388,7 @@ __device__ __forceinline__ void merge_rowstats(float& m, float& rest, int& piv, 
 
 template <int BN>
 struct EpiRowLse {
-  static constexpr size_t scratch_bytes(int warps) { return warps == 8 ? 3 * 128 * sizeof(float) : 16; }
+  static constexpr size_t scratch_bytes(int warps) { return warps > 4 ? (warps / 4 - 1) * 3 * 128 * sizeof(float) : 16; }
   struct Params {
     float* rowmax2;  // [B, n_split] m   (log2 units)
     float* rest;     // [B, n_split]
@@ -446,20 +446,26 @@ struct EpiRowLse {
   __device__ static void tile_end(State&, const Params&, const EpiCtx&, const TileCoord&) {}
   __device__ static void item_end(State& st, const Params& p, const EpiCtx& ctx, const TileCoord& tc) {
     const int row = epi_row(ctx, tc);
-    if (ctx.n_warps == 8) {  // the warp of the upper column half hands its partial to the lower one
-      const uint32_t slot = ctx.scratch_u32 + 12u * static_cast<uint32_t>(ctx.ew * 32 + ctx.lane);
-      st.m *= p.s_log2e;  // raw accumulator units -> log2 units
-      if (ctx.wid >= 4) {
+    st.m *= p.s_log2e;  // raw accumulator units -> log2 units
+    const int groups = ctx.n_warps / 4;  // column groups per accumulator row (one warp each)
+    if (groups > 1) {  // the warps of the upper column groups hand their partials to the first one
+      const int g = ctx.wid >> 2;
+      const uint32_t base = ctx.scratch_u32 + 12u * static_cast<uint32_t>(ctx.ew * 32 + ctx.lane);
+      if (g > 0) {
+        const uint32_t slot = base + static_cast<uint32_t>(g - 1) * (12u * 128u);
         sts_f32(slot, st.m);
         sts_f32(slot + 4, st.rest);
         sts_f32(slot + 8, __int_as_float(st.piv));
       }
       epi_bar_sync(ctx);
-      if (ctx.wid < 4) merge_rowstats(st.m, st.rest, st.piv, lds_f32(slot), lds_f32(slot + 4), __float_as_int(lds_f32(slot + 8)));
+      if (g == 0) {
+        for (int k = 0; k + 1 < groups; ++k) {
+          const uint32_t slot = base + static_cast<uint32_t>(k) * (12u * 128u);
+          merge_rowstats(st.m, st.rest, st.piv, lds_f32(slot), lds_f32(slot + 4), __float_as_int(lds_f32(slot + 8)));
+        }
+      }
       epi_bar_sync(ctx);
-      if (ctx.wid >= 4) return;
-    } else {
-      st.m *= p.s_log2e;
+      if (g > 0) return;
     }
     if (row < ctx.M) {
       const int64_t o = static_cast<int64_t>(row) * p.n_split + tc.split;
