@@ -161,6 +161,36 @@ def cpu_kfac_rate(cfg, data_batches):
     return data_batches * cfg["batch_size"] / dt, dt
 
 
+def gpu_eager_rates(cfg, kc, dev):
+    """The reference algorithm in stock torch eager ON THE SAME B200 (true fp32, no TF32): the tougher, informational baseline
+    SURVEY.md section 8(d) asks for next to the host-core one.  Predictive: the full 50k x 1000 step; KFAC: the reference's
+    double loop over 8 data batches of 5 sources against one class batch of 32768 targets."""
+    from oracle import torch_port as T
+
+    t = predictive_inputs(cfg, 0)
+    Ai, Bi, At, Bt = covariances(t, cfg, dev)
+    a = tuple(t[k].to(dev) for k in ("img_e", "img_a", "txt_e", "txt_a")) + (Ai, Bi, At, Bt, LS)
+    for _ in range(2):
+        T.predictive(*a)
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        T.predictive(*a)
+    torch.cuda.synchronize(dev)
+    pdt = (time.perf_counter() - t0) / 5
+    n = kc["num_classes"]
+    e_img, e_txt, a_img = kfac_inputs(kc, n, kc["seed"], device=dev)
+    T.kfac_ggn(e_img, a_img, e_txt, n, kc["batch_size"], LS, max_data_batches=1)
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    T.kfac_ggn(e_img, a_img, e_txt, n, kc["batch_size"], LS, max_data_batches=8)
+    torch.cuda.synchronize(dev)
+    kdt = time.perf_counter() - t0
+    return {"predictive_pairs_per_s": cfg["N"] * cfg["C"] / pdt, "predictive_ms_per_step": pdt * 1e3,
+            "kfac_samples_per_s": 8 * kc["batch_size"] / kdt,
+            "what": "oracle/torch_port (the reference's ATen operation sequence) in torch eager fp32 on the same GPU, inputs resident"}
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -371,6 +401,11 @@ def run_b200(args, rank, world, local_rank):
                         "kfac": {"value": krate, "unit": "samples/s",
                                  "sample": f"reference double loop, 1 class batch of 32768 targets x 8 data batches of 5 ({kdt:.1f} s)"}}
         kfac["vs_cpu_port"] = kfac["value"] / krate
+        try:
+            cpu_baseline["same_gpu_torch_eager"] = gpu_eager_rates(cfg, kc, dev)
+        except Exception as exc:  # informational leg: never fail the bench line on it
+            cpu_baseline["same_gpu_torch_eager"] = {"unavailable": repr(exc)[:200]}
+        torch.cuda.empty_cache()
 
     if rank == 0:
         line = {

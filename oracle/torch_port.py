@@ -34,7 +34,7 @@ def infonce_ggn(source, target, logit_scale):
     mean = (yh.T @ p.unsqueeze(-1))                                            # [B,D,1], :33
     cov = second - mean @ mean.transpose(1, 2)                                 # :36,:46
     d = source.shape[-1]
-    jac = torch.eye(d, dtype=source.dtype) / nx.unsqueeze(-1) \
+    jac = torch.eye(d, dtype=source.dtype, device=source.device) / nx.unsqueeze(-1) \
         - source.unsqueeze(2) * source.unsqueeze(1) / (nx ** 3).unsqueeze(-1)  # :39-43
     return (jac @ cov @ jac.transpose(1, 2) * s ** 2).sum(dim=0)               # :46-48
 
@@ -50,11 +50,11 @@ def siglip_ggn(x, indices, y, logit_scale, logit_bias, chunk_size_j=None):
     yh, _ = _unit(y)
     s = math.exp(float(logit_scale))
     z = xh @ yh.T * s + float(logit_bias)                                      # :88
-    sign = (2 * torch.eye(n_y, dtype=x.dtype) - 1)[indices]                    # :89-90
+    sign = (2 * torch.eye(n_y, dtype=x.dtype, device=x.device) - 1)[indices]                    # :89-90
     sg = torch.sigmoid(z * sign)                                               # :93
     lam = s * s * sg * (1 - sg)                                                # :94
     d = x.shape[1]
-    jac = torch.eye(d, dtype=x.dtype).unsqueeze(0) / nx.unsqueeze(-1) \
+    jac = torch.eye(d, dtype=x.dtype, device=x.device).unsqueeze(0) / nx.unsqueeze(-1) \
         - x.unsqueeze(2) * x.unsqueeze(1) / (nx.unsqueeze(-1) ** 3)            # :109-111
     total = 0
     for lo in range(0, n_y, chunk):                                            # :98
