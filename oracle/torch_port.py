@@ -149,7 +149,7 @@ def epig_from_probs(probs_pool, probs_targ, chunk_size=8192):
     h_targ = _entropy(probs_targ.mean(dim=1)).mean()                           # :372
     pool = probs_pool.permute(0, 2, 1)                                         # [N_p, Cl, K]
     targ = probs_targ.permute(1, 0, 2).reshape(k, n_t * cl)                    # [K, N_t * Cl]
-    h_joint = torch.zeros(pool.shape[0])                                       # :381
+    h_joint = torch.zeros(pool.shape[0], device=pool.device)                   # :381
     for lo in range(0, n_t * cl, chunk_size):                                  # :383
         joint = pool @ targ[:, lo:lo + chunk_size] / k                         # :387-388
         h_joint += -torch.sum(torch.xlogy(joint, joint), dim=(-2, -1)) / n_t   # :390-393

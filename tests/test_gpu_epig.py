@@ -103,6 +103,33 @@ def test_epig_fused_vs_oracle(cfg):
     _topk_identical_modulo_ties(s, ref, k, ulp * n_chunks + 2.0 ** -10 * h_max)
 
 
+@pytest.mark.parametrize("cfg", [dict(Np=300, Nt=200, K=100, Cl=10, chunk=512), dict(Np=1000, Nt=700, K=100, Cl=10, chunk=4096),
+                                 dict(Np=257, Nt=129, K=64, Cl=65, chunk=4096)])
+def test_epig_fused_vs_reference_ops_on_same_gpu(cfg):
+    """Parity protocol (1) of SURVEY.md section 8(d): identical fp16 probabilities go to the reference's operation sequence
+    executed by torch ON THE SAME GPU (oracle/torch_port.epig_from_probs: fp16 matmul, `/K`, xlogy, sums -- torch's own CUDA
+    kernels and their rounding) and to the fused kernel; scores agree to per-chunk fp16 ulps, top-k identical modulo ties."""
+    from oracle import torch_port as T
+
+    from bayesvlm_b200.epig import epig_from_probs_using_matmul
+    from bayesvlm_b200.vlm import sample_probas_from_noise
+
+    gen = torch.Generator().manual_seed(cfg["Np"] + 13 * cfg["Cl"])
+    mp, vp, ep = _probs(gen, cfg["Np"], cfg["K"], cfg["Cl"])
+    mt, vt, et = _probs(gen, cfg["Nt"], cfg["K"], cfg["Cl"])
+    p16 = sample_probas_from_noise(mp.cuda(), vp.cuda(), ep.cuda())
+    t16 = sample_probas_from_noise(mt.cuda(), vt.cuda(), et.cuda())
+    s = epig_from_probs_using_matmul(p16, t16, chunk_size=cfg["chunk"]).float().cpu().numpy()
+    ref = T.epig_from_probs(p16, t16, chunk_size=cfg["chunk"]).float().cpu().numpy()
+    n_chunks = math.ceil(cfg["Nt"] * cfg["Cl"] / cfg["chunk"])
+    h_max = 2 * math.log(cfg["Cl"])
+    tol = 2.0 ** -10 * max(h_max / n_chunks, 2.0 ** -14) * 2 * n_chunks + 2.0 ** -10 * h_max
+    d = np.abs(s - ref)
+    assert d.max() <= tol, (d.max(), tol)
+    assert (d == 0).mean() >= 0.4, (d == 0).mean()
+    _topk_identical_modulo_ties(s, ref, min(50, cfg["Np"] // 2), tol)
+
+
 def test_epig_from_logits_shared_rng():
     """E3: per-pool-chunk re-seeding (seed + row offset) with torch's own generator on the device."""
     from bayesvlm_b200.epig import epig_from_logits_using_matmul, epig_from_probs_using_matmul
