@@ -296,8 +296,8 @@ def run_b200(args, rank, world, local_rank):
                 "kernels": {k: {"launches": v[0], "avg_ms": v[1] / v[0],
                                 "algo_tflops": algo_flops.get(k, 0.0) / (v[1] / v[0] * 1e-3) / 1e12} for k, v in kern.items()},
                 # the predictive sits on the ridge (report both): the same launch against the HBM roof, algorithmic
-                # bytes = mean + var written (8 B per pair) + the 16-bit / 8-bit operands read once
-                "hbm": {"achieved": (8.0 * pairs + 3.0 * (cfg["N"] + cfg["C"]) * cfg["D"]) / (kern["predictive"][1] / kern["predictive"][0] * 1e-3) / 1e9
+                # bytes = mean + var written (8 B per pair) + the operands read once (fp16 + fp8 pair or fp16 hi|lo: 4 B per element)
+                "hbm": {"achieved": (8.0 * pairs + (2.0 if model.precision == "fp16" else 4.0) * (cfg["N"] + cfg["C"]) * cfg["D"]) / (kern["predictive"][1] / kern["predictive"][0] * 1e-3) / 1e9
                         if "predictive" in kern else None, "peak": peaks["hbm_gbs"], "unit": "GB/s"},
                 "step_algo_tflops": (algo_flops["predictive"] + algo_flops["quadform"]) / (ms_step * 1e-3) / 1e12,
                 "step_hbm_gbs": (8.0 * pairs + 4.0 * cfg["N"] * (cfg["D"] + cfg["d_img"])) / (ms_step * 1e-3) / 1e9,
