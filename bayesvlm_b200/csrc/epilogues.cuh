@@ -199,6 +199,7 @@ struct EpiQuadformPrep {
     uint32_t issued, consumed;
     uint32_t ring;
     uint64_t* bars;
+    float4 dl[EVX > 0 ? EVX : 1];  // this lane's slices of diag_other (exact-width instantiations)
   };
   static constexpr bool ALL_CHUNKS = false;
   static constexpr bool UNROLL_CHUNKS = true;
@@ -217,6 +218,10 @@ struct EpiQuadformPrep {
     st.issued = st.consumed = 0;
     st.bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(ctx.scratch) + 512) + ctx.wid * PREP_MAX_SLOTS;
     st.ring = ctx.scratch_u32 + 1024u + static_cast<uint32_t>(ctx.wid) * PREP_RING_BYTES;
+    if constexpr (EVX > 0) {
+#pragma unroll
+      for (int i = 0; i < EVX; ++i) st.dl[i] = __ldg(reinterpret_cast<const float4*>(p.prep.diag_other + (i * 32 + ctx.lane) * 4));
+    }
     if (ctx.lane == 0) {
       for (int i = 0; i < p.slots; ++i) mbar_init(&st.bars[i], 1);
       fence_barrier_init();
@@ -256,7 +261,7 @@ struct EpiQuadformPrep {
       }
       // pass 1 ends in warp reductions over values derived from every lane's e[]: all reads of the slot have completed,
       // so it can be handed back to the copy engine (write-after-read needs no proxy fence, as in any TMA pipeline)
-      const EmbedRowStats rs = embed_row_stats<EV, (EVX > 0)>(p.prep, ctx.lane, e);
+      const EmbedRowStats rs = embed_row_stats<EV, (EVX > 0)>(p.prep, ctx.lane, e, EVX > 0 ? st.dl : nullptr);
       const int jn = j + p.slots;
       const int64_t row_n = tc.row0 + ctx.wid + ctx.n_warps * jn;
       if (jn < per_warp && row_n < p.prep.R) issue(st, p, ctx, row_n);

@@ -53,8 +53,11 @@ struct EmbedRowStats {
 };
 
 // pass 1: |x|^2, sum_d x_d^2 diag_other_d, row scale (ends in warp reductions: every lane's e[] has been consumed on return)
+// `dl_cached` (optional): the lane's float4 slices of diag_other kept in registers by the caller -- in the GEMM epilogue a
+// per-row reload misses L1 (bulk copies and stores stream through it) and stalls the FMAs on the long scoreboard.
 template <int EV, bool EXACT = false>
-__device__ __forceinline__ EmbedRowStats embed_row_stats(const EmbedPrepArgs& a, int lane, const float4 (&e)[EV]) {
+__device__ __forceinline__ EmbedRowStats embed_row_stats(const EmbedPrepArgs& a, int lane, const float4 (&e)[EV],
+                                                         const float4* dl_cached = nullptr) {
   // packed fp32x2 arithmetic (sm_100 FFMA2 / FMUL2 / FADD2): half the issue slots of the scalar form
   float2 n2v = make_float2(0.f, 0.f), pdv = make_float2(0.f, 0.f);
   float amax = 0.f;
@@ -62,7 +65,8 @@ __device__ __forceinline__ EmbedRowStats embed_row_stats(const EmbedPrepArgs& a,
   for (int i = 0; i < EV; ++i) {
     const int c = (i * 32 + lane) * 4;
     float4 dl = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (EXACT || c + 3 < a.D) dl = __ldg(reinterpret_cast<const float4*>(a.diag_other + c));
+    if (dl_cached != nullptr) dl = dl_cached[i];
+    else if (EXACT || c + 3 < a.D) dl = __ldg(reinterpret_cast<const float4*>(a.diag_other + c));
     else if (c < a.D) {
       dl.x = a.diag_other[c];
       if (c + 1 < a.D) dl.y = a.diag_other[c + 1];
