@@ -187,3 +187,21 @@ def test_kfac_ggn_medium_vs_oracle():
     Ar, Br = O.kfac_ggn(src_e.numpy(), src_a.numpy(), tgt_e.numpy(), ncls, bs, LS)
     _check_factor(A, Ar)
     _check_factor(B, Br)
+
+
+def test_kfac_ggn_input_placement_is_irrelevant():
+    """Pageable host, pinned host (staged one class batch ahead on a copy stream) and device-resident inputs run the same
+    kernels on the same data: the same factors (up to the summation order of the split-K atomics)."""
+    from bayesvlm_b200.hessians import kfac_ggn
+    from bayesvlm_b200.vlm import CLIP
+
+    gen = torch.Generator().manual_seed(2003)
+    n, ncls, bs, D, d_in = 5 * 512 + 37, 512, 5, 128, 160
+    src_e, tgt_e = _paired(gen, n, D)
+    src_a = torch.randn(n, d_in, generator=gen)
+    vlm = CLIP(logit_scale=LS, device="cuda")
+    ref = kfac_ggn(vlm, ncls, bs, src_e.cuda(), src_a.cuda(), tgt_e.cuda(), "cuda", "info_nce")
+    for place in (lambda t: t, lambda t: t.pin_memory()):
+        A, B = kfac_ggn(vlm, ncls, bs, place(src_e), place(src_a), place(tgt_e), "cuda", "info_nce")
+        assert torch.allclose(A, ref[0], rtol=1e-5, atol=1e-6 * float(ref[0].abs().max()))
+        assert torch.allclose(B, ref[1], rtol=1e-5, atol=1e-6 * float(ref[1].abs().max()))
