@@ -163,30 +163,49 @@ def kfac_ggn(vlm, num_classes: int, batch_size: int, source_embeds: torch.Tensor
     B = torch.zeros((d_emb, d_emb), dtype=torch.float32, device=dev)
 
     # Host-resident inputs (the reference's calling convention) are staged one class batch AHEAD on a copy stream, so that
-    # the PCIe transfer of batch i+1 (235 MB at config 2, ~4.3 ms) overlaps the kernels of batch i (~4.6 ms); this needs
-    # pinned host tensors -- pageable ones are copied synchronously by the driver and serialise anyway.
+    # the PCIe transfer of batch i+1 (235 MB at config 2, ~4.3 ms) overlaps the kernels of batch i (~4.6 ms).
     inputs = (target_embeds, source_embeds, source_activations)
     staged = any(t.device.type == "cpu" for t in inputs)
     copy_stream = torch.cuda.Stream(dev) if staged else None
     main_stream = torch.cuda.current_stream(dev)
 
-    def fetch(i):
+    # Pageable host tensors go through two sets of pinned bounce buffers filled by torch's (multi-threaded) host copy while
+    # the GPU works on the previous batch -- the driver's own pageable path is a synchronous, single-threaded staging copy.
+    bounce = None
+    if staged and any(t.device.type == "cpu" and not t.is_pinned() for t in inputs):
+        from .hostmem import pinned_empty
+
+        bounce = [[pinned_empty((num_classes, t.shape[1]), torch.float32, dev)
+                   if t.device.type == "cpu" and not t.is_pinned() else None for t in inputs] for _ in range(2)]
+    bounce_free = [None, None]  # event: the host->device copies out of this set have completed
+
+    def fetch(i, slot):
         lo, hi = i * num_classes, (i + 1) * num_classes
         if not staged:
             return tuple(t[lo:hi].to(dev, dtype=torch.float32) for t in inputs) + (None,)
+        sources = []
+        for k, t in enumerate(inputs):
+            if bounce is not None and bounce[slot][k] is not None:
+                if bounce_free[slot] is not None:
+                    bounce_free[slot].synchronize()
+                bounce[slot][k].copy_(t[lo:hi])
+                sources.append(bounce[slot][k])
+            else:
+                sources.append(t[lo:hi])
         with torch.cuda.stream(copy_stream):
-            parts = tuple(t[lo:hi].to(dev, dtype=torch.float32, non_blocking=True) for t in inputs)
+            parts = tuple(t.to(dev, dtype=torch.float32, non_blocking=True) for t in sources)
             ready = torch.cuda.Event()
             ready.record(copy_stream)
+        bounce_free[slot] = ready
         return parts + (ready,)
 
     schedule = list(class_batch_schedule(num_class_batches, rank, world))
     if staged:
         copy_stream.wait_stream(main_stream)
-    pending = fetch(schedule[0]) if schedule else None
+    pending = fetch(schedule[0], 0) if schedule else None
     for k, _ in enumerate(schedule):
         tgt, src, act, ready = pending
-        pending = fetch(schedule[k + 1]) if k + 1 < len(schedule) else None
+        pending = fetch(schedule[k + 1], (k + 1) % 2) if k + 1 < len(schedule) else None
         if ready is not None:
             main_stream.wait_event(ready)
             for t in (tgt, src, act):

@@ -203,5 +203,6 @@ def test_kfac_ggn_input_placement_is_irrelevant():
     ref = kfac_ggn(vlm, ncls, bs, src_e.cuda(), src_a.cuda(), tgt_e.cuda(), "cuda", "info_nce")
     for place in (lambda t: t, lambda t: t.pin_memory()):
         A, B = kfac_ggn(vlm, ncls, bs, place(src_e), place(src_a), place(tgt_e), "cuda", "info_nce")
-        assert torch.allclose(A, ref[0], rtol=1e-5, atol=1e-6 * float(ref[0].abs().max()))
-        assert torch.allclose(B, ref[1], rtol=1e-5, atol=1e-6 * float(ref[1].abs().max()))
+        # run-to-run differences of the split-K / column-sum atomics reach 3e-6 of the largest entry
+        assert float((A - ref[0]).abs().max()) <= 2e-5 * float(ref[0].abs().max())
+        assert float((B - ref[1]).abs().max()) <= 2e-5 * float(ref[1].abs().max())
