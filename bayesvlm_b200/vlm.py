@@ -444,6 +444,8 @@ class CLIP(torch.nn.Module):
         the tensor cores and PCIe out overlap.  Text-side quantities are computed once, not per batch as the reference
         does (vlm.py:663).  `out=(mean, var[, probs])` lets a serving loop reuse its own (pinned) host buffers; otherwise
         fresh host tensors are allocated (pinned when `out_pinned`)."""
+        from .hostmem import pinned_empty  # page-locked on the GPU's NUMA node
+
         dev = self.device
         if dev.type != "cuda":
             raise RuntimeError("predict_host needs the module on a CUDA device")
@@ -455,13 +457,12 @@ class CLIP(torch.nn.Module):
             if tuple(mean.shape) != (n, c) or tuple(var.shape) != (n, c):
                 raise ValueError("out buffers must be [N, C]")
         else:
-            from .hostmem import pinned_empty  # page-locked on the GPU's NUMA node
-
             mk = (lambda: pinned_empty((n, c), device=dev)) if out_pinned else (lambda: torch.empty((n, c)))
             mean, var = mk(), mk()
             probs = mk() if return_probs else None
         bs = max(1, min(batch_size, n))
-        key = (dev, bs, c, d, d_act, return_probs)
+        bounce = any(t.device.type == "cpu" and not t.is_pinned() for t in (image_outputs.embeds, image_outputs.activations))
+        key = (dev, bs, c, d, d_act, return_probs, bounce)
         pipe = getattr(self, "_host_pipe", None)
         if pipe is None or pipe["key"] != key:
             f32 = dict(dtype=torch.float32, device=dev)
@@ -469,7 +470,9 @@ class CLIP(torch.nn.Module):
                     "bufs": [dict(emb=torch.empty((bs, d), **f32), act=torch.empty((bs, d_act), **f32),
                                   mean=torch.empty((bs, c), **f32), var=torch.empty((bs, c), **f32),
                                   probs=torch.empty((bs, c), **f32) if return_probs else None,
-                                  computed=None, drained=None) for _ in range(2)]}
+                                  h_emb=pinned_empty((bs, d), device=dev) if bounce else None,
+                                  h_act=pinned_empty((bs, d_act), device=dev) if bounce else None,
+                                  computed=None, drained=None, loaded=None) for _ in range(2)]}
             self._host_pipe = pipe
         s_in, s_cmp, s_out = pipe["s_in"], pipe["s_cmp"], pipe["s_out"]
         cur = torch.cuda.current_stream(dev)
@@ -482,13 +485,21 @@ class CLIP(torch.nn.Module):
             hi = min(n, lo + bs)
             m = hi - lo
             b = pipe["bufs"][i % 2]
+            src_emb, src_act = image_outputs.embeds[lo:hi], image_outputs.activations[lo:hi]
+            if bounce:  # pageable inputs: torch's host copy into a pinned bounce buffer, then a truly asynchronous transfer
+                if b["loaded"] is not None:
+                    b["loaded"].synchronize()  # the transfer of two batches ago has left the bounce buffer
+                b["h_emb"][:m].copy_(src_emb)
+                b["h_act"][:m].copy_(src_act)
+                src_emb, src_act = b["h_emb"][:m], b["h_act"][:m]
             with torch.cuda.stream(s_in):
                 if b["computed"] is not None:
                     s_in.wait_event(b["computed"])  # the kernels of two batches ago have consumed this staging buffer
-                b["emb"][:m].copy_(image_outputs.embeds[lo:hi], non_blocking=True)
-                b["act"][:m].copy_(image_outputs.activations[lo:hi], non_blocking=True)
+                b["emb"][:m].copy_(src_emb, non_blocking=True)
+                b["act"][:m].copy_(src_act, non_blocking=True)
                 loaded = torch.cuda.Event()
                 loaded.record(s_in)
+                b["loaded"] = loaded
             with torch.cuda.stream(s_cmp):
                 s_cmp.wait_event(loaded)
                 if b["drained"] is not None:
@@ -508,7 +519,7 @@ class CLIP(torch.nn.Module):
         s_out.synchronize()
         cur.wait_stream(s_cmp)
         for b in pipe["bufs"]:
-            b["computed"] = b["drained"] = None
+            b["computed"] = b["drained"] = b["loaded"] = None
         res = ProbabilisticLogits(mean=mean, var=var)
         return (res, probs) if return_probs else res
 
