@@ -123,6 +123,30 @@ def reduce_factors(A: torch.Tensor, B: torch.Tensor, group=None) -> Tuple[torch.
     return flat[: A.numel()].view_as(A), flat[A.numel():].view_as(B)
 
 
+_KFAC_STAGING = {}
+
+
+def _kfac_staging(dev: torch.device, num_classes: int, inputs):
+    """Two sets of device staging buffers (+ pinned bounce buffers for pageable inputs) per (device, shapes), a copy stream,
+    and the events that order their reuse; kept across calls."""
+    from .hostmem import pinned_empty
+
+    need_bounce = tuple(t.device.type == "cpu" and not t.is_pinned() for t in inputs)
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), num_classes,
+           tuple(t.shape[1] for t in inputs), need_bounce)
+    st = _KFAC_STAGING.get(key)
+    if st is None:
+        _KFAC_STAGING.clear()  # one configuration at a time: the buffers are hundreds of MB
+        st = {"stream": torch.cuda.Stream(dev),
+              "device": [[torch.empty((num_classes, t.shape[1]), dtype=torch.float32, device=dev) for t in inputs]
+                         for _ in range(2)],
+              "bounce": [[pinned_empty((num_classes, t.shape[1]), torch.float32, dev) if nb else None
+                          for t, nb in zip(inputs, need_bounce)] for _ in range(2)]}
+        _KFAC_STAGING[key] = st
+    st["loaded"], st["consumed"] = [None, None], [None, None]
+    return st
+
+
 @torch.no_grad()
 def kfac_ggn(vlm, num_classes: int, batch_size: int, source_embeds: torch.Tensor, source_activations: torch.Tensor,
              target_embeds: torch.Tensor, device: str, likelihood: Literal["info_nce", "siglip"],
@@ -163,21 +187,15 @@ def kfac_ggn(vlm, num_classes: int, batch_size: int, source_embeds: torch.Tensor
     B = torch.zeros((d_emb, d_emb), dtype=torch.float32, device=dev)
 
     # Host-resident inputs (the reference's calling convention) are staged one class batch AHEAD on a copy stream, so that
-    # the PCIe transfer of batch i+1 (235 MB at config 2, ~4.3 ms) overlaps the kernels of batch i (~4.6 ms).
+    # the PCIe transfer of batch i+1 (235 MB at config 2, ~4.3 ms) overlaps the kernels of batch i (~4.6 ms).  Two sets of
+    # persistent device staging buffers are reused across calls (fresh per-batch allocations on the copy stream make the
+    # caching allocator fall back to cudaMalloc while their cross-stream frees are pending: measured 4x slower).
+    # Pageable host tensors additionally go through pinned bounce buffers filled by torch's (multi-threaded) host copy
+    # while the GPU works on the previous batch -- the driver's own pageable path is a synchronous, single-threaded copy.
     inputs = (target_embeds, source_embeds, source_activations)
     staged = any(t.device.type == "cpu" for t in inputs)
-    copy_stream = torch.cuda.Stream(dev) if staged else None
     main_stream = torch.cuda.current_stream(dev)
-
-    # Pageable host tensors go through two sets of pinned bounce buffers filled by torch's (multi-threaded) host copy while
-    # the GPU works on the previous batch -- the driver's own pageable path is a synchronous, single-threaded staging copy.
-    bounce = None
-    if staged and any(t.device.type == "cpu" and not t.is_pinned() for t in inputs):
-        from .hostmem import pinned_empty
-
-        bounce = [[pinned_empty((num_classes, t.shape[1]), torch.float32, dev)
-                   if t.device.type == "cpu" and not t.is_pinned() else None for t in inputs] for _ in range(2)]
-    bounce_free = [None, None]  # event: the host->device copies out of this set have completed
+    stage = _kfac_staging(dev, num_classes, inputs) if staged else None
 
     def fetch(i, slot):
         lo, hi = i * num_classes, (i + 1) * num_classes
@@ -185,35 +203,41 @@ def kfac_ggn(vlm, num_classes: int, batch_size: int, source_embeds: torch.Tensor
             return tuple(t[lo:hi].to(dev, dtype=torch.float32) for t in inputs) + (None,)
         sources = []
         for k, t in enumerate(inputs):
-            if bounce is not None and bounce[slot][k] is not None:
-                if bounce_free[slot] is not None:
-                    bounce_free[slot].synchronize()
-                bounce[slot][k].copy_(t[lo:hi])
-                sources.append(bounce[slot][k])
+            host = stage["bounce"][slot][k]
+            if t.device.type == "cpu" and not t.is_pinned():
+                if stage["loaded"][slot] is not None:
+                    stage["loaded"][slot].synchronize()  # the previous transfer out of this bounce buffer has finished
+                host.copy_(t[lo:hi])
+                sources.append(host)
             else:
                 sources.append(t[lo:hi])
-        with torch.cuda.stream(copy_stream):
-            parts = tuple(t.to(dev, dtype=torch.float32, non_blocking=True) for t in sources)
+        with torch.cuda.stream(stage["stream"]):
+            if stage["consumed"][slot] is not None:
+                stage["stream"].wait_event(stage["consumed"][slot])  # the kernels of two batches ago are done with this set
+            for dst, src_t in zip(stage["device"][slot], sources):
+                dst.copy_(src_t, non_blocking=True)
             ready = torch.cuda.Event()
-            ready.record(copy_stream)
-        bounce_free[slot] = ready
-        return parts + (ready,)
+            ready.record(stage["stream"])
+        stage["loaded"][slot] = ready
+        return tuple(stage["device"][slot]) + (ready,)
 
     schedule = list(class_batch_schedule(num_class_batches, rank, world))
     if staged:
-        copy_stream.wait_stream(main_stream)
+        stage["stream"].wait_stream(main_stream)
     pending = fetch(schedule[0], 0) if schedule else None
     for k, _ in enumerate(schedule):
         tgt, src, act, ready = pending
         pending = fetch(schedule[k + 1], (k + 1) % 2) if k + 1 < len(schedule) else None
         if ready is not None:
             main_stream.wait_event(ready)
-            for t in (tgt, src, act):
-                t.record_stream(main_stream)  # allocated on the copy stream, consumed here
         used = (num_classes // batch_size) * batch_size  # data-batch remainder never reaches B
         if used > 0:
             _ggn(src[:used], tgt, logit_scale, logit_bias, siglip=siglip, out=B, accumulate=True)
         syrk_accumulate(act, out=A, append_one=siglip, accumulate=True)
+        if staged:
+            done = torch.cuda.Event()
+            done.record(main_stream)
+            stage["consumed"][k % 2] = done
 
     if use_dist and world > 1:
         A, B = reduce_factors(A, B, group)

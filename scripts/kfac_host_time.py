@@ -5,7 +5,7 @@ import bench
 from bayesvlm_b200.hessians import kfac_ggn
 from bayesvlm_b200.vlm import CLIP
 kc = bench.KFAC
-n = 8 * kc["num_classes"]
+n = (int(sys.argv[1]) if len(sys.argv) > 1 else 8) * kc["num_classes"]
 e_img, e_txt, a_img = bench.kfac_inputs(kc, n, kc["seed"])
 vlm = CLIP(logit_scale=bench.LS, device="cuda")
 kw = dict(num_classes=kc["num_classes"], batch_size=kc["batch_size"], device="cuda", likelihood="info_nce")
