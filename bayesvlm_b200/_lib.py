@@ -63,10 +63,14 @@ SIGNATURES = {
     "bvlm_predictive_workspace_bytes": (c_size_t, [_I, _I, _I, c_int, c_int]),
     "bvlm_predictive": (
         c_int,
-        [_P, _I, _I, _I, _P, _I, _I, c_int, _P, _I, _I, c_float, _P, c_float, c_float, _P, _P, _P, _P, _I, c_int, _P, _P, _P,
-         _I, _P, c_size_t, _P],
+        [_P, _I, _I, _I, _P, _I, _I, c_int, _P, _I, _I, c_float, _P, c_float, c_float, _P, _P, _P, _P, _P, _I, c_int, _P, _P,
+         _P, _I, _P, c_size_t, _P],
     ),
     "bvlm_probit_softmax": (c_int, [_P, _P, _I, _I, _I, _P, _P]),
+    "bvlm_epig_operand_k": (c_int, [_I]),
+    "bvlm_epig_prepare_from_noise": (c_int, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
+    "bvlm_epig_prepare_from_probs": (c_int, [_P, _I, _I, _I, _P, _P, _P]),
+    "bvlm_epig_joint_entropy_operands": (c_int, [_P, _I, _P, _I, _I, _I, _I, _P, _P]),
     "bvlm_epig_sample_probs": (c_int, [_P, _P, _P, _I, _I, _I, _P, _P]),
     "bvlm_epig_marginal_entropy_f16": (c_int, [_P, _I, _I, _I, _P, _P]),
     "bvlm_epig_joint_workspace_bytes": (c_size_t, [_I, _I, _I, _I]),
@@ -150,18 +154,31 @@ def stream_ptr(device: torch.device) -> c_void_p:
     return c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+def run(device: torch.device, name: str, *args) -> None:
+    """Call the entry point `name` with `device` as the CUDA current device (the library launches kernels, memsets and
+    encodes tensor maps on the current device; the reference API takes a device argument instead) and raise on a
+    non-zero status."""
+    with torch.cuda.device(device):
+        rc = getattr(lib, name)(*args)
+    check(rc, name)
+
+
 _WORKSPACES: dict = {}
 
 
 def workspace(device: torch.device, nbytes: int, tag: str = "default") -> torch.Tensor:
-    """Grow-only per-device scratch buffer (uint8, 256-byte aligned by the caching allocator)."""
-    key = (device.index if device.index is not None else torch.cuda.current_device(), tag)
+    """Grow-only scratch buffer (uint8, 256-byte aligned by the caching allocator) per (device, stream, tag): kernels on
+    different streams never share scratch, and a buffer is only ever reused in the order of the stream it was allocated on,
+    so regrowing it (the old block returns to the allocator, which is stream-ordered) is safe."""
+    index = device.index if device.index is not None else torch.cuda.current_device()
+    key = (index, torch.cuda.current_stream(device).cuda_stream, tag)
     buf = _WORKSPACES.get(key)
     if buf is None or buf.numel() < nbytes:
         if buf is not None:
             del _WORKSPACES[key]
             del buf
-        buf = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=device)
+        with torch.cuda.device(device):
+            buf = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=device)
         _WORKSPACES[key] = buf
     return buf
 

@@ -39,7 +39,11 @@ enum KernelTag : int {
   TAG_QUADFORM = 6,
   TAG_PREDICTIVE = 7,
   TAG_EPIG_JOINT = 8,
-  TAG_COUNT = 9
+  TAG_EPIG_PREPARE = 9,
+  TAG_PRED_PREP = 10,
+  TAG_PROBIT = 11,
+  TAG_SYRK_PREP = 12,
+  TAG_COUNT = 13
 };
 void timing_begin(int tag, cudaStream_t st);
 void timing_end(int tag, cudaStream_t st);

@@ -22,87 +22,231 @@ inline int64_t pad64(int64_t k) { return round_up_i64(k, 64); }
 
 __device__ __forceinline__ float round_f16(float v) { return __half2float(__float2half_rn(v)); }
 
-// x * log(x) with torch's Half semantics (both the log and the product are rounded to fp16); 0 at x == 0.
+// x * log(x) on a Half tensor AS TORCH'S CUDA KERNEL EVALUATES IT (xlogy_kernel_cuda: `x * std::log(y)` in device code --
+// the operands are widened to float, logf and the product stay fp32, ONE rounding to fp16 at the end); 0 at x == 0.
+// (torch's CPU kernel rounds log() to Half before the product -- measured on B200 with torch 2.11: the CUDA result equals
+//  the single-rounding form for 15359 of the 15360 fp16 values in (0, 1], the CPU form for 11360; scripts/probe_epig_parity.py.)
 __device__ __forceinline__ float xlogx_f16(float x) {
   if (x == 0.f) return 0.f;
-  const float l = round_f16(logf(x));
-  return round_f16(x * l);
+  return round_f16(x * logf(x));
 }
 
+__device__ __forceinline__ void cp_async_4(uint32_t smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // ---------------------------------------------------------------------------------------------------------------
-// E0: probs[n,k,:] = softmax(mean[n,:] + eps[k,n,:] * sqrt(var[n,:]))  -> fp16           (vlm.py:116-123)
-// one thread per (n,k); consecutive threads walk k so the [N,K,Cl] writes are contiguous.
+// E0 + E1 + operand layout in ONE pass over a block of R sample rows                 (vlm.py:116-123, epig.py:294-311, 374-376)
+//   FROM_NOISE : eps [K, N, Cl] fp32 (torch.randn order), mean / var [N, Cl]  ->  probs = softmax(eps * sqrt(var) + mean) -> fp16
+//   !FROM_NOISE: probs_in [N, K, Cl] fp16
+// outputs (each optional): probs_out [N, K, Cl] fp16, oper [N, Cl, Kp] fp16 (the K-major operand of the joint-entropy GEMM,
+// zero padded along K), marg [N] fp16 marginal entropies with torch's CUDA rounding points (mean over K = fp32 sum times
+// 1/K -> fp16; xlogy -> fp16; sum over Cl in fp32 -> fp16; negate).
+// Data movement: the noise of a row block is one contiguous R*Cl run per MC sample, fetched with cp.async straight into
+// shared memory (odd row stride: the per-sample reads below are conflict free); results are staged in shared memory in
+// their GLOBAL layouts and leave with 128-bit stores; the reduction over K is a warp-shuffle sum with lanes along K.
+// The softmax follows torch's softmax_warp_forward for rows of <= 16 classes (sum in the 16-lane butterfly order, expf,
+// true division), so the fp16 probabilities are bit-identical to the reference's on the same device.
 // ---------------------------------------------------------------------------------------------------------------
+struct PrepLayout {
+  int R, estride;
+  size_t off_nk, off_eps, off_ms, bytes;
+};
+
+inline PrepLayout prep_layout(int64_t K, int64_t Cl, int64_t Kp, bool from_noise, bool need_nk, size_t budget) {
+  PrepLayout L{};
+  const size_t per_row = static_cast<size_t>(Cl * Kp * 2) + (need_nk ? static_cast<size_t>(K * Cl * 2) : 0) +
+                         (from_noise ? static_cast<size_t>(K * Cl * 4 + 8 * Cl) : 0);
+  const size_t fixed = from_noise ? static_cast<size_t>(K) * 4 + 64 : 64;
+  int R = budget > fixed ? static_cast<int>((budget - fixed) / per_row) : 0;
+  if (R > 32) R = 32;
+  L.R = R;
+  if (R <= 0) return L;
+  L.estride = static_cast<int>(R * Cl) | 1;
+  size_t off = static_cast<size_t>(R) * Cl * Kp * 2;
+  L.off_nk = off;
+  if (need_nk) off += (static_cast<size_t>(R) * K * Cl * 2 + 15) & ~static_cast<size_t>(15);
+  L.off_eps = off;
+  if (from_noise) off += static_cast<size_t>(K) * L.estride * 4;
+  L.off_ms = off;
+  if (from_noise) off += static_cast<size_t>(2 * R * Cl) * 4;
+  L.bytes = off;
+  return L;
+}
+
+template <bool FROM_NOISE, bool CL16>
 __global__ void __launch_bounds__(256)
-k_epig_sample(const float* __restrict__ mean, const float* __restrict__ var, const float* __restrict__ eps, int64_t N,
-              int64_t K, int64_t Cl, __half* __restrict__ probs) {
-  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= N * K) return;
-  const int64_t n = idx / K;
-  const int64_t k = idx - n * K;
-  const float* m = mean + n * Cl;
-  const float* v = var + n * Cl;
-  const float* e = eps + (k * N + n) * Cl;
-  float zmax = -INFINITY, zsum = 0.f;
-  for (int64_t c = 0; c < Cl; ++c) {
-    const float z = fmaf(e[c], sqrtf(v[c]), m[c]);
-    if (z > zmax) {
-      zsum = zsum * expf(zmax - z);
-      zmax = z;
+k_epig_prepare(const float* __restrict__ mean, const float* __restrict__ var, const float* __restrict__ eps,
+               const __half* __restrict__ probs_in, int64_t N, int K, int Cl, int Kp, const PrepLayout L,
+               __half* __restrict__ probs_out, __half* __restrict__ oper, __half* __restrict__ marg) {
+  extern __shared__ __align__(16) uint8_t ps[];
+  __half* s_op = reinterpret_cast<__half*>(ps);               // [R][Cl][Kp]
+  __half* s_nk = reinterpret_cast<__half*>(ps + L.off_nk);    // [R][K][Cl]
+  float* s_eps = reinterpret_cast<float*>(ps + L.off_eps);    // [K][estride]
+  float* s_mean = reinterpret_cast<float*>(ps + L.off_ms);    // [R*Cl]
+  float* s_std = s_mean + L.R * Cl;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t n0 = static_cast<int64_t>(blockIdx.x) * L.R;
+  const int rows = static_cast<int>(N - n0 < L.R ? N - n0 : L.R);
+  const int seg = rows * Cl;
+  const bool need_nk = !FROM_NOISE || probs_out != nullptr;
+
+  // ---- phase 1: fetch the block's inputs
+  if constexpr (FROM_NOISE) {
+    for (int k = warp; k < K; k += 8) {
+      const float* src = eps + (static_cast<int64_t>(k) * N + n0) * Cl;
+      const uint32_t dst = smem_u32(s_eps + k * L.estride);
+      for (int j = lane; j < seg; j += 32) cp_async_4(dst + 4u * j, src + j);
     }
-    zsum += expf(z - zmax);
+    for (int j = tid; j < seg; j += 256) {
+      s_mean[j] = mean[n0 * Cl + j];
+      s_std[j] = sqrtf(var[n0 * Cl + j]);
+    }
+  } else {
+    const __half* src = probs_in + n0 * K * Cl;
+    const int total = rows * K * Cl;
+    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+      for (int i = tid; i < total / 8; i += 256) cp_async_16(smem_u32(s_nk) + 16u * i, src + 8 * i);
+      for (int i = (total / 8) * 8 + tid; i < total; i += 256) s_nk[i] = src[i];
+    } else {
+      for (int i = tid; i < total; i += 256) s_nk[i] = src[i];
+    }
   }
-  __half* o = probs + idx * Cl;
-  for (int64_t c = 0; c < Cl; ++c) {
-    const float z = fmaf(e[c], sqrtf(v[c]), m[c]);
-    o[c] = __float2half_rn(expf(z - zmax) / zsum);
+  // zero the K padding of the operand tile
+  if (Kp > K) {
+    const int padw = Kp - K;
+    for (int i = tid; i < seg * padw; i += 256) {
+      const int r = i / padw;
+      s_op[r * Kp + K + (i - r * padw)] = __float2half_rn(0.f);
+    }
   }
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// E1: marginal entropy of fp16 probabilities, one warp per sample                      (epig.py:294-311, 275-292)
-// ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_epig_marginal(const __half* __restrict__ probs, int64_t N, int64_t K, int64_t Cl, __half* __restrict__ out) {
-  const int64_t n = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (n >= N) return;
-  const __half* p = probs + n * K * Cl;
-  float ent = 0.f;
-  for (int64_t c = lane; c < Cl; c += 32) {
-    float s = 0.f;
-    for (int64_t k = 0; k < K; ++k) s += __half2float(p[k * Cl + c]);
-    const float pbar = round_f16(s / static_cast<float>(K));  // torch.mean on Half: fp32 sum, divide, round
-    ent += xlogx_f16(pbar);
-  }
-  ent = warp_sum(ent);
-  if (lane == 0) out[n] = __float2half_rn(-round_f16(ent));
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// [N, K, Cl] fp16 -> [N, Cl, Kp] fp16 (K-major GEMM operand, zero padded along K)     (epig.py:374-376 permutes)
-// ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_epig_permute(const __half* __restrict__ in, int64_t N, int64_t K, int64_t Cl, int64_t Kp, __half* __restrict__ out) {
-  extern __shared__ __half s_tile[];  // [K][Cl]
-  const int64_t n = blockIdx.x;
-  if (n >= N) return;
-  const __half* src = in + n * K * Cl;
-  for (int64_t i = threadIdx.x; i < K * Cl; i += blockDim.x) s_tile[i] = src[i];
+  cp_async_wait_all();
   __syncthreads();
-  __half* dst = out + n * Cl * Kp;
-  for (int64_t i = threadIdx.x; i < Cl * Kp; i += blockDim.x) {
-    const int64_t c = i / Kp;
-    const int64_t k = i - c * Kp;
-    dst[i] = k < K ? s_tile[k * Cl + c] : __float2half_rn(0.f);
+
+  // ---- phase 2: one (row, MC sample) per thread, lanes along k
+  for (int i = tid; i < rows * K; i += 256) {
+    const int n = i / K, k = i - n * K;
+    if constexpr (FROM_NOISE) {
+      const float* e = s_eps + k * L.estride + n * Cl;
+      const float* m = s_mean + n * Cl;
+      const float* sd = s_std + n * Cl;
+      if constexpr (CL16) {
+        float z[16];
+        float zmax = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          z[c] = c < Cl ? __fadd_rn(__fmul_rn(e[c], sd[c]), m[c]) : -INFINITY;  // torch: randn * std + mean, two roundings
+          zmax = fmaxf(zmax, z[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < 16; ++c) z[c] = c < Cl ? expf(z[c] - zmax) : 0.f;
+        // torch softmax_warp_forward: butterfly sum over the 16 lanes of a row (xor 8, 4, 2, 1)
+        const float t0 = z[0] + z[8], t1 = z[1] + z[9], t2 = z[2] + z[10], t3 = z[3] + z[11], t4 = z[4] + z[12],
+                    t5 = z[5] + z[13], t6 = z[6] + z[14], t7 = z[7] + z[15];
+        const float u0 = t0 + t4, u1 = t1 + t5, u2 = t2 + t6, u3 = t3 + t7;
+        const float zsum = (u0 + u2) + (u1 + u3);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          if (c < Cl) {
+            const __half h = __float2half_rn(z[c] / zsum);
+            s_op[(n * Cl + c) * Kp + k] = h;
+            if (need_nk) s_nk[(n * K + k) * Cl + c] = h;
+          }
+        }
+      } else {
+        float zmax = -INFINITY;
+        for (int c = 0; c < Cl; ++c) zmax = fmaxf(zmax, __fadd_rn(__fmul_rn(e[c], sd[c]), m[c]));
+        float zsum = 0.f;
+        for (int c = 0; c < Cl; ++c) zsum += expf(__fadd_rn(__fmul_rn(e[c], sd[c]), m[c]) - zmax);
+        for (int c = 0; c < Cl; ++c) {
+          const __half h = __float2half_rn(expf(__fadd_rn(__fmul_rn(e[c], sd[c]), m[c]) - zmax) / zsum);
+          s_op[(n * Cl + c) * Kp + k] = h;
+          if (need_nk) s_nk[(n * K + k) * Cl + c] = h;
+        }
+      }
+    } else {
+      for (int c = 0; c < Cl; ++c) s_op[(n * Cl + c) * Kp + k] = s_nk[(n * K + k) * Cl + c];
+    }
   }
+  __syncthreads();
+
+  // ---- phase 3: marginal entropies, one warp per row, shuffle reduction over K
+  if (marg != nullptr) {
+    const float inv_k = static_cast<float>(1.0 / static_cast<double>(K));  // torch multiplies by the fp32 reciprocal
+    for (int n = warp; n < rows; n += 8) {
+      float ent = 0.f;
+      for (int c = 0; c < Cl; ++c) {
+        const __half* row = s_op + (n * Cl + c) * Kp;
+        float s = 0.f;
+        for (int k = lane; k < K; k += 32) s += __half2float(row[k]);
+        s = warp_sum(s);
+        ent += xlogx_f16(round_f16(s * inv_k));
+      }
+      if (lane == 0) marg[n0 + n] = __float2half_rn(-round_f16(ent));
+    }
+  }
+
+  // ---- phase 4: results leave in their global layouts, 128 bits at a time
+  if (oper != nullptr) {
+    uint4* dst = reinterpret_cast<uint4*>(oper + n0 * Cl * Kp);  // Kp is a multiple of 64 halves: always 16-byte aligned
+    const uint4* src = reinterpret_cast<const uint4*>(s_op);
+    for (int i = tid; i < seg * Kp / 8; i += 256) dst[i] = src[i];
+  }
+  if (FROM_NOISE && probs_out != nullptr) {
+    __half* dst = probs_out + n0 * K * Cl;
+    const int total = rows * K * Cl;
+    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+      for (int i = tid; i < total / 8; i += 256) reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(s_nk)[i];
+      for (int i = (total / 8) * 8 + tid; i < total; i += 256) dst[i] = s_nk[i];
+    } else {
+      for (int i = tid; i < total; i += 256) dst[i] = s_nk[i];
+    }
+  }
+}
+
+constexpr size_t PREP_SMEM_BUDGET = 100 * 1024;  // two blocks per SM
+
+int launch_epig_prepare(const float* mean, const float* var, const float* eps, const __half* probs_in, int64_t N, int64_t K,
+                        int64_t Cl, __half* probs_out, __half* oper, __half* marg, cudaStream_t st) {
+  if (N <= 0) return BVLM_OK;
+  if (K <= 0 || Cl <= 0 || K > 4096 || Cl > 4096) return BVLM_EINVAL;
+  const bool from_noise = eps != nullptr;
+  const int64_t Kp = pad64(K);
+  const bool need_nk = !from_noise || probs_out != nullptr;
+  const PrepLayout L = prep_layout(K, Cl, Kp, from_noise, need_nk, PREP_SMEM_BUDGET);
+  if (L.R <= 0) return BVLM_ENOTSUP;  // one row's K x Cl block does not fit shared memory
+  const unsigned grid = static_cast<unsigned>(ceil_div_i64(N, L.R));
+  const bool cl16 = Cl <= 16;
+#define BVLM_PREP_LAUNCH(FN, C16)                                                                                       \
+  do {                                                                                                                  \
+    auto kfn = k_epig_prepare<FN, C16>;                                                                                 \
+    BVLM_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(PREP_SMEM_BUDGET))); \
+    kfn<<<grid, 256, L.bytes, st>>>(mean, var, eps, probs_in, N, static_cast<int>(K), static_cast<int>(Cl),             \
+                                    static_cast<int>(Kp), L, probs_out, oper, marg);                                    \
+  } while (0)
+  timing_begin(TAG_EPIG_PREPARE, st);
+  if (from_noise) {
+    if (cl16) BVLM_PREP_LAUNCH(true, true);
+    else BVLM_PREP_LAUNCH(true, false);
+  } else {
+    BVLM_PREP_LAUNCH(false, false);
+  }
+#undef BVLM_PREP_LAUNCH
+  timing_end(TAG_EPIG_PREPARE, st);
+  count_launch();
+  BVLM_CUDA_TRY(cudaGetLastError());
+  return BVLM_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // E2 epilogue. Tile rows are (pool row, class) pairs packed ppt = floor(128/Cl) pool rows per 128-row CTA slab; tile
 // columns are the flattened (target, class) axis. Row panels: each CTA pair walks all column tiles of its pool rows.
-// Per element (two at a time in half2 registers where the arithmetic is fp16 anyway):
-//   h = fp16(acc); j = fp16(h / K); l = fp16(log j); t = fp16(j * l)  [= HMUL2, exact product rounded once]; sum += t
+// Per element (torch's CUDA rounding points; two elements at a time):
+//   h = fp16(acc); j = fp16(h * (1/K)); t = fp16(j * log j)  [fp32 log and product, one rounding]; sum += t  (fp32)
 // ---------------------------------------------------------------------------------------------------------------
 template <int BN>
 struct EpiEpigJoint {
@@ -113,8 +257,8 @@ struct EpiEpigJoint {
     int Cl;
     int ppt;            // pool rows per 128-row slab
     int tiles_per_chunk;  // col_chunk / BN
-    float inv_K;        // 1 / number of MC samples
-    float Nt;           // number of target points (divisor)
+    float inv_K;        // fp32(1 / K): torch's CUDA `tensor / python_scalar` multiplies by the fp32 reciprocal
+    float inv_Nt;       // fp32(1 / N_t), same rule
   };
   struct State {
     float chunk_acc;  // running fp32 sum of fp16(xlogy) over the current column chunk (this thread's row, its column half)
@@ -141,7 +285,7 @@ struct EpiEpigJoint {
       for (int h = 0; h < ctx.n_warps / 4; ++h)
         for (int c = 0; c < p.Cl; ++c) sum += lds_f32(s + 4u * static_cast<uint32_t>(h * 128 + r + c));
       const float neg = -round_f16(sum);               // fp16(sum) then negate
-      st.hj += round_f16(neg / p.Nt);                  // "/ N_t" on a Half tensor
+      st.hj += round_f16(neg * p.inv_Nt);              // "/ N_t" on a Half tensor
     }
     st.chunk_acc = 0.f;
   }
@@ -164,19 +308,18 @@ struct EpiEpigJoint {
     }
   }
   __device__ static void chunk(State& st, const Params& p, const EpiCtx&, const TileCoord&, float (&v)[32], int) {
-    // columns beyond N are TMA zero fill: joint = 0 -> 0 * max(log 0, -65504) = -0, no masking needed
-    const __half2 lo_clamp = __floats2half2_rn(-65504.f, -65504.f);
+    // columns beyond N are TMA zero fill: j = 0 -> 0 * log 0 = NaN, which the NaN-suppressing min below turns into 0
+    const __half2 zero2 = __float2half2_rn(0.f);
     const float2 inv_k2 = make_float2(p.inv_K, p.inv_K), ln2 = make_float2(0.6931471805599453f, 0.6931471805599453f);
     float s0 = 0.f, s1 = 0.f;
 #pragma unroll
     for (int j = 0; j < 32; j += 2) {
       // packed fp32x2 multiplies (FMUL2) and mixed-precision adds (fp32 += fp16, FHADD): same roundings, fewer issue slots
       const float2 h = __half22float2(__floats2half2_rn(v[j], v[j + 1]));            // matmul output rounded to fp16
-      const __half2 jt = __float22half2_rn(__fmul2_rn(h, inv_k2));                    // "/ K" on a Half tensor
-      const float2 jf = __half22float2(jt);
-      __half2 lg = __float22half2_rn(__fmul2_rn(make_float2(fast_log2(jf.x), fast_log2(jf.y)), ln2));
-      lg = __hmax2(lg, lo_clamp);                                                     // log 0 = -inf would make 0 * inf
-      const __half2 t = __hmul2(jt, lg);                                              // fp16(j * fp16(log j))
+      const float2 jf = __half22float2(__float22half2_rn(__fmul2_rn(h, inv_k2)));    // "/ K" on a Half tensor
+      const float2 lg = __fmul2_rn(make_float2(fast_log2(jf.x), fast_log2(jf.y)), ln2);  // log j in fp32
+      __half2 t = __float22half2_rn(__fmul2_rn(jf, lg));                              // fp16(j * log j): ONE rounding
+      t = __hmin2(t, zero2);                                                          // j log j <= 0; NaN (j = 0) -> 0
       s0 = add_f32_f16(s0, __low2half(t));
       s1 = add_f32_f16(s1, __high2half(t));
     }
@@ -193,53 +336,43 @@ struct EpiEpigJoint {
 
 extern "C" {
 
+int bvlm_epig_operand_k(int64_t K) { return static_cast<int>(pad64(K)); }
+
+int bvlm_epig_prepare_from_noise(const float* mean, const float* var, const float* eps, int64_t N, int64_t K, int64_t Cl,
+                                 void* probs16, void* oper16, void* marg16, void* stream) {
+  if (mean == nullptr || var == nullptr || eps == nullptr) return BVLM_EINVAL;
+  if (probs16 == nullptr && oper16 == nullptr && marg16 == nullptr) return BVLM_EINVAL;
+  return launch_epig_prepare(mean, var, eps, nullptr, N, K, Cl, static_cast<__half*>(probs16), static_cast<__half*>(oper16),
+                             static_cast<__half*>(marg16), static_cast<cudaStream_t>(stream));
+}
+
+int bvlm_epig_prepare_from_probs(const void* probs16, int64_t N, int64_t K, int64_t Cl, void* oper16, void* marg16,
+                                 void* stream) {
+  if (probs16 == nullptr || (oper16 == nullptr && marg16 == nullptr)) return BVLM_EINVAL;
+  return launch_epig_prepare(nullptr, nullptr, nullptr, static_cast<const __half*>(probs16), N, K, Cl, nullptr,
+                             static_cast<__half*>(oper16), static_cast<__half*>(marg16), static_cast<cudaStream_t>(stream));
+}
+
 int bvlm_epig_sample_probs(const float* mean, const float* var, const float* eps, int64_t N, int64_t K, int64_t Cl,
                            void* probs16, void* stream) {
-  if (mean == nullptr || var == nullptr || eps == nullptr || probs16 == nullptr) return BVLM_EINVAL;
-  if (N <= 0 || K <= 0 || Cl <= 0) return BVLM_OK;
-  const int64_t total = N * K;
-  k_epig_sample<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      mean, var, eps, N, K, Cl, static_cast<__half*>(probs16));
-  count_launch();
-  BVLM_CUDA_TRY(cudaGetLastError());
-  return BVLM_OK;
+  if (probs16 == nullptr) return BVLM_EINVAL;
+  return bvlm_epig_prepare_from_noise(mean, var, eps, N, K, Cl, probs16, nullptr, nullptr, stream);
 }
 
 int bvlm_epig_marginal_entropy_f16(const void* probs16, int64_t N, int64_t K, int64_t Cl, void* out16, void* stream) {
-  if (probs16 == nullptr || out16 == nullptr) return BVLM_EINVAL;
-  if (N <= 0) return BVLM_OK;
-  k_epig_marginal<<<static_cast<unsigned>((N + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __half*>(probs16), N, K, Cl, static_cast<__half*>(out16));
-  count_launch();
-  BVLM_CUDA_TRY(cudaGetLastError());
-  return BVLM_OK;
+  if (out16 == nullptr) return BVLM_EINVAL;
+  return bvlm_epig_prepare_from_probs(probs16, N, K, Cl, nullptr, out16, stream);
 }
 
-size_t bvlm_epig_joint_workspace_bytes(int64_t Np, int64_t Nt, int64_t K, int64_t Cl) {
-  const int64_t Kp = pad64(K);
-  return static_cast<size_t>(round_up_i64(Np * Cl * Kp * 2, 256) + round_up_i64(Nt * Cl * Kp * 2, 256) + 1024);
-}
-
-int bvlm_epig_joint_entropy_f16(const void* pool16, int64_t Np, const void* targ16, int64_t Nt, int64_t K, int64_t Cl,
-                                int64_t col_chunk, float* Hjoint, void* ws, size_t ws_bytes, void* stream) {
-  if (pool16 == nullptr || targ16 == nullptr || Hjoint == nullptr || ws == nullptr) return BVLM_EINVAL;
+int bvlm_epig_joint_entropy_operands(const void* poolP, int64_t Np, const void* targP, int64_t Nt, int64_t K, int64_t Cl,
+                                     int64_t col_chunk, float* Hjoint, void* stream) {
+  if (poolP == nullptr || targP == nullptr || Hjoint == nullptr) return BVLM_EINVAL;
   if (Np <= 0 || Nt <= 0 || K <= 0 || Cl <= 0) return BVLM_EINVAL;
   if (Cl > 128 || col_chunk <= 0 || (col_chunk % EPIG_BN) != 0) return BVLM_ENOTSUP;
-  if (K * Cl * 2 > 48 * 1024) return BVLM_ENOTSUP;
   if (Nt * Cl > 0x7fffffff || Np > 0x7fffffff) return BVLM_EINVAL;
-  if (ws_bytes < bvlm_epig_joint_workspace_bytes(Np, Nt, K, Cl)) return BVLM_EWORKSPACE;
-  if ((reinterpret_cast<uintptr_t>(ws) & 255) != 0) return BVLM_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(poolP) & 15) != 0 || (reinterpret_cast<uintptr_t>(targP) & 15) != 0) return BVLM_EINVAL;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t Kp = pad64(K);
-  __half* poolP = static_cast<__half*>(ws);
-  __half* targP = reinterpret_cast<__half*>(static_cast<uint8_t*>(ws) + round_up_i64(Np * Cl * Kp * 2, 256));
-  const size_t sh = static_cast<size_t>(K * Cl * 2);
-  k_epig_permute<<<static_cast<unsigned>(Np), 256, sh, st>>>(static_cast<const __half*>(pool16), Np, K, Cl, Kp, poolP);
-  count_launch();
-  k_epig_permute<<<static_cast<unsigned>(Nt), 256, sh, st>>>(static_cast<const __half*>(targ16), Nt, K, Cl, Kp, targP);
-  count_launch();
-  BVLM_CUDA_TRY(cudaGetLastError());
-
   const int ppt = static_cast<int>(128 / Cl);
   CUtensorMap tmA, tmB;
   int rc = make_tmap_3d(&tmA, poolP, TM_F16, static_cast<uint64_t>(Kp), static_cast<uint64_t>(Cl),
@@ -256,8 +389,29 @@ int bvlm_epig_joint_entropy_f16(const void* pool16, int64_t Np, const void* targ
   plan.a_outer_step = ppt;
   plan.a_tx_bytes = static_cast<uint32_t>(ppt * Cl * GEMM_BK * 2);
   EpiEpigJoint<EPIG_BN>::Params ep{Hjoint, Np, static_cast<int>(Cl), ppt, static_cast<int>(col_chunk / EPIG_BN),
-                                   1.0f / static_cast<float>(K), static_cast<float>(Nt)};
+                                   static_cast<float>(1.0 / static_cast<double>(K)),
+                                   static_cast<float>(1.0 / static_cast<double>(Nt))};
   return launch_gemm2<EPIG_BN, 6, 16, EpiEpigJoint<EPIG_BN>>(tmA, tmB, plan, ep, st, TAG_EPIG_JOINT);
+}
+
+size_t bvlm_epig_joint_workspace_bytes(int64_t Np, int64_t Nt, int64_t K, int64_t Cl) {
+  const int64_t Kp = pad64(K);
+  return static_cast<size_t>(round_up_i64(Np * Cl * Kp * 2, 256) + round_up_i64(Nt * Cl * Kp * 2, 256) + 1024);
+}
+
+int bvlm_epig_joint_entropy_f16(const void* pool16, int64_t Np, const void* targ16, int64_t Nt, int64_t K, int64_t Cl,
+                                int64_t col_chunk, float* Hjoint, void* ws, size_t ws_bytes, void* stream) {
+  if (pool16 == nullptr || targ16 == nullptr || Hjoint == nullptr || ws == nullptr) return BVLM_EINVAL;
+  if (Np <= 0 || Nt <= 0 || K <= 0 || Cl <= 0) return BVLM_EINVAL;
+  if (ws_bytes < bvlm_epig_joint_workspace_bytes(Np, Nt, K, Cl)) return BVLM_EWORKSPACE;
+  if ((reinterpret_cast<uintptr_t>(ws) & 255) != 0) return BVLM_EINVAL;
+  const int64_t Kp = pad64(K);
+  void* poolP = ws;
+  void* targP = static_cast<uint8_t*>(ws) + round_up_i64(Np * Cl * Kp * 2, 256);
+  int rc = bvlm_epig_prepare_from_probs(pool16, Np, K, Cl, poolP, nullptr, stream);
+  if (rc) return rc;
+  if ((rc = bvlm_epig_prepare_from_probs(targ16, Nt, K, Cl, targP, nullptr, stream))) return rc;
+  return bvlm_epig_joint_entropy_operands(poolP, Np, targP, Nt, K, Cl, col_chunk, Hjoint, stream);
 }
 
 }  // extern "C"

@@ -298,7 +298,11 @@ struct EpiPredictive {
     const float* n2;
     const float* pd;
     const float* esc;
-    float sum_beta, s2, mean_scale;
+    float sum_beta;
+    float ls;             // log-space logit scale (host copy), used when ls_dev == nullptr
+    const float* ls_dev;  // optional DEVICE scalar holding the log-space logit scale: read per tile, so a parameter updated
+                          // in place (the `.data` idiom of reference epig.py:230) is always current and the host never syncs
+    float mean_unscale;   // 1 / (operand scaling of the two unit-energy embeddings)
     const float* a;   // padded to a multiple of BN entries (zeros beyond C)
     const float* b;
     int use_tma;      // 0: row pitch not a multiple of 16 bytes -> direct stores
@@ -321,9 +325,10 @@ struct EpiPredictive {
       const float al = p.alpha[row];
       const float E = fmaf(al, p.sum_beta, p.n2[row]);
       const float rE = 1.0f / E;
-      st.u = p.s2 * p.pd[row] * rE;
-      st.v = p.s2 * al * rE;
-      st.rm = p.mean_scale * p.esc[row] * rsqrtf(E);
+      const float s = expf(p.ls_dev != nullptr ? __ldg(p.ls_dev) : p.ls);
+      st.u = s * s * p.pd[row] * rE;
+      st.v = s * s * al * rE;
+      st.rm = s * p.mean_unscale * p.esc[row] * rsqrtf(E);
     }
   }
   __device__ static void chunk(State& st, const Params& p, const EpiCtx& ctx, const TileCoord& tc, float (&v)[32], int c) {
@@ -343,7 +348,9 @@ struct EpiPredictive {
     }
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] *= st.rm;
-    if (p.use_tma == 2) return;  // (diagnostic: main loop without output traffic, BVLM_DEBUG_NOSTORE=1)
+#ifdef BVLM_DIAG
+    if (p.use_tma == 2) return;  // (diagnostic build only: main loop without output traffic, BVLM_DEBUG_NOSTORE=1)
+#endif
     if (p.use_tma) {
       // rows beyond N and columns beyond C are clipped by the tensor map
       const bool dbl = ctx.n_warps == 4;

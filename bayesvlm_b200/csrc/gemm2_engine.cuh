@@ -412,8 +412,9 @@ inline void plan_use_pairs(GemmPlan& p, int pairs) { p.m_tiles = (p.M + pairs * 
 // number of CTA pairs that can be co-resident for this instantiation (queried once)
 template <int BN, int STAGES, int EPI_WARPS, class Epi, bool A_MN = false, bool B_MN = false, int PAIRS = 1>
 inline int gemm2_max_clusters(size_t smem) {
-  static int cached = -1;
-  if (cached >= 0) return cached;
+  static std::atomic<int> cached_dev[BVLM_MAX_DEVICES];  // per device (zero = not queried yet)
+  std::atomic<int>& cached = cached_dev[current_device_slot()];
+  if (const int c = cached.load(std::memory_order_relaxed); c > 0) return c;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(static_cast<unsigned>(device_sm_count() / (2 * PAIRS) * (2 * PAIRS)), 1, 1);
   cfg.blockDim = dim3(128 + 32 * EPI_WARPS, 1, 1);
@@ -431,7 +432,7 @@ inline int gemm2_max_clusters(size_t smem) {
     (void)cudaGetLastError();
     n = device_sm_count() / (2 * PAIRS);
   }
-  cached = n;
+  cached.store(n, std::memory_order_relaxed);
   return n;
 }
 
@@ -445,10 +446,11 @@ inline int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ge
   constexpr size_t smem = gemm2_smem_bytes<BN, STAGES, EPI_WARPS, Epi>();
   static_assert(smem <= 232448, "shared memory budget exceeded");
   auto kfn = gemm2_tn_kernel<BN, STAGES, EPI_WARPS, Epi, A_MN, B_MN, PAIRS>;
-  static bool configured = false;  // per instantiation
-  if (!configured) {
+  static std::atomic<int> configured_dev[BVLM_MAX_DEVICES];  // per instantiation AND per device (the attribute is per device)
+  std::atomic<int>& configured = configured_dev[current_device_slot()];
+  if (!configured.load(std::memory_order_acquire)) {
     BVLM_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    configured = true;
+    configured.store(1, std::memory_order_release);
   }
   const int items = plan_num_items<BN>(plan);
   int clusters = gemm2_max_clusters<BN, STAGES, EPI_WARPS, Epi, A_MN, B_MN, PAIRS>(smem);

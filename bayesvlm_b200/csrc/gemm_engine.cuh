@@ -11,6 +11,8 @@
 // lower triangle for SYRK), row panels (one M-tile, all N-tiles: row reductions keep state in registers) or
 // column panels (one N-tile, all M-tiles: column reductions keep state in registers).
 #pragma once
+#include <atomic>
+
 #include "common.cuh"
 #include "tmap.cuh"
 
@@ -433,10 +435,11 @@ inline int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   constexpr size_t smem = gemm_smem_bytes<BN, STAGES, Epi>();
   static_assert(smem <= 232448, "shared memory budget exceeded");
   auto kfn = gemm_tn_kernel<BN, STAGES, Epi>;
-  static bool configured = false;  // per instantiation
-  if (!configured) {
+  static std::atomic<int> configured_dev[BVLM_MAX_DEVICES];  // per instantiation AND per device
+  std::atomic<int>& configured = configured_dev[current_device_slot()];
+  if (!configured.load(std::memory_order_acquire)) {
     BVLM_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    configured = true;
+    configured.store(1, std::memory_order_release);
   }
   const int items = plan_num_items<BN>(plan);
   int grid = device_sm_count();

@@ -152,9 +152,9 @@ size_t bvlm_predictive_workspace_bytes(int64_t N, int64_t D, int64_t d_act, int 
 
 int bvlm_predictive(const float* E, int64_t N, int64_t D, int64_t lde, const float* Eact, int64_t d_act, int64_t ldact,
                     int append_one, const void* Wi16, int64_t dA, int64_t k_pad, float w_scale, const float* delta,
-                    float sum_beta, float logit_scale, const void* T16, const void* T8, const float* colA, const float* colB,
-                    int64_t C, int precision, float* mean, float* var, float* probs, int64_t ldo, void* ws, size_t ws_bytes,
-                    void* stream) {
+                    float sum_beta, float logit_scale, const float* logit_scale_dev, const void* T16, const void* T8,
+                    const float* colA, const float* colB, int64_t C, int precision, float* mean, float* var, float* probs,
+                    int64_t ldo, void* ws, size_t ws_bytes, void* stream) {
   if (E == nullptr || Eact == nullptr || Wi16 == nullptr || delta == nullptr || T16 == nullptr || colA == nullptr ||
       colB == nullptr || mean == nullptr || var == nullptr || ws == nullptr)
     return BVLM_EINVAL;
@@ -176,7 +176,6 @@ int bvlm_predictive(const float* E, int64_t N, int64_t D, int64_t lde, const flo
   const int64_t seg8 = pad128(D);
   uint8_t* A8 = precision == BVLM_PREC_X2F8 ? cv.take<uint8_t>(static_cast<size_t>(N) * 2 * seg8) : nullptr;
   const size_t used = cv.used();
-  const float s = expf(logit_scale);
   // One HBM-bound pass over the image rows converts BOTH operands (activations -> fp16 for the quadratic forms,
   // embeddings -> fp16 [+ fp16 lo | + fp8 compensation terms]); neither depends on the quadratic forms, whose 1/sqrt(E_i)
   // normalisation is applied by the epilogue of the mean GEMM.
@@ -238,14 +237,14 @@ int bvlm_predictive(const float* E, int64_t N, int64_t D, int64_t lde, const flo
   ep.pd = pd;
   ep.esc = esc;
   ep.sum_beta = sum_beta;
-  ep.s2 = s * s;
-  ep.mean_scale = precision == BVLM_PREC_X2F8 ? s / (128.f * 1024.f) : s / PRED_OPSCALE;
+  ep.ls = logit_scale;
+  ep.ls_dev = logit_scale_dev;
+  ep.mean_unscale = precision == BVLM_PREC_X2F8 ? 1.0f / (128.f * 1024.f) : 1.0f / PRED_OPSCALE;
   ep.a = colA;
   ep.b = colB;
   // TMA stores need 16-byte aligned rows; tiny class counts (e.g. C = 10) fall back to direct stores
   ep.use_tma = ((ldo * 4) % 16 == 0 && (reinterpret_cast<uintptr_t>(mean) & 15) == 0 &&
                 (reinterpret_cast<uintptr_t>(var) & 15) == 0) ? 1 : 0;
-  static const bool nostore = getenv("BVLM_DEBUG_NOSTORE") != nullptr;  // diagnostic: main loop without output traffic
   if (ep.use_tma) {
     if ((rc = make_tmap_2d(&ep.tm_mean, mean, TM_F32, static_cast<uint64_t>(C), static_cast<uint64_t>(N),
                            static_cast<uint64_t>(ldo) * 4, 32, 32, 1)))
@@ -254,12 +253,14 @@ int bvlm_predictive(const float* E, int64_t N, int64_t D, int64_t lde, const flo
                            static_cast<uint64_t>(ldo) * 4, 32, 32, 1)))
       return rc;
   }
-  if (nostore) ep.use_tma = 2;
-  if (getenv("BVLM_DEBUG_SHORTK") != nullptr) {  // diagnostic: one K block per tile -> the kernel is its epilogue
+#ifdef BVLM_DIAG  // diagnostic builds only (python -m bayesvlm_b200.build --diag): never in the shipped library
+  if (getenv("BVLM_DEBUG_NOSTORE") != nullptr) ep.use_tma = 2;  // main loop without output traffic
+  if (getenv("BVLM_DEBUG_SHORTK") != nullptr) {                 // one K block per tile -> the kernel is its epilogue
     plan.kb_total = 1;
     plan.kb_alt = 0x7fffffff;
     plan.seg_kb = 0;
   }
+#endif
   if (variant == 3) {
     plan_use_pairs(plan, 2);
     rc = launch_gemm2<PRED_BN, 5, 4, EpiPredictive<PRED_BN>, false, false, 2>(tmA, tmB, plan, ep, st, TAG_PREDICTIVE, pA8, pB8);

@@ -1,5 +1,6 @@
 #include "tmap.cuh"
 
+#include <atomic>
 #include <cstdlib>
 #include <mutex>
 
@@ -77,14 +78,21 @@ int64_t operand_pitch(int64_t k_elems) {
   return ((k_elems * 2) % 1024 == 0) ? k_elems + pad : k_elems;
 }
 
+int current_device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) return 0;
+  return dev < BVLM_MAX_DEVICES ? dev : BVLM_MAX_DEVICES - 1;
+}
+
 int device_sm_count() {
-  static int cached = 0;
-  if (cached > 0) return cached;
+  static std::atomic<int> cached[BVLM_MAX_DEVICES];
+  const int slot = current_device_slot();
+  if (const int c = cached[slot].load(std::memory_order_relaxed); c > 0) return c;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 148;
   int n = 0;
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
-  cached = n;
+  cached[slot].store(n, std::memory_order_relaxed);
   return n;
 }
 

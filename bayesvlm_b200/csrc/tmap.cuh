@@ -16,6 +16,10 @@ int make_tmap_2d(CUtensorMap* out, const void* base, int dtype, uint64_t inner, 
 int make_tmap_3d(CUtensorMap* out, const void* base, int dtype, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1_bytes,
                  uint64_t s2_bytes, uint32_t b0, uint32_t b1, uint32_t b2, int swizzle128);
 
-int device_sm_count();
+// Per-device caches (SM count, occupancy, function attributes) are indexed by the CUDA current device: the library may be
+// driven on several GPUs of one process (the Python mirror makes the tensors' device current around every call).
+constexpr int BVLM_MAX_DEVICES = 64;
+int current_device_slot();  // CUDA current device ordinal, clamped to [0, BVLM_MAX_DEVICES)
+int device_sm_count();      // SM count of the current device
 
 }  // namespace bvlm

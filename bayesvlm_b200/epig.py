@@ -18,10 +18,52 @@ from .hessians import compute_covariances, compute_hessian_analytic_InfoNCE, opt
 from .vlm import CLIP, EncoderResult, ProbabilisticLogits
 
 _JOINT_TILE_N = 256  # column tile of the joint-entropy kernel; chunk_size must be a multiple of it
+_PREP_SMEM = 100 * 1024  # shared-memory budget of the fused sample / permute / marginal-entropy kernel (csrc/epig.cu)
 
 
 def _kernel_path_ok(probs: torch.Tensor) -> bool:
     return probs.is_cuda and probs.dtype == torch.float16
+
+
+def _prepare_fits(k: int, cl: int, from_noise: bool) -> bool:
+    """One sample row (K x Cl) of the fused kernel's staging must fit its shared-memory budget."""
+    kp = int(lib.bvlm_epig_operand_k(k))
+    per_row = cl * kp * 2 + (k * cl * 4 + 8 * cl if from_noise else k * cl * 2)
+    return per_row + 4 * k + 64 <= _PREP_SMEM
+
+
+def _joint_fused_ok(k: int, cl: int, chunk_size: int) -> bool:
+    return cl <= 128 and chunk_size % _JOINT_TILE_N == 0 and chunk_size > 0
+
+
+def prepare_from_probs(probs: torch.Tensor, want_operand: bool = True, want_entropy: bool = True):
+    """fp16 CUDA probabilities [N, K, Cl] -> (operand [N, Cl, Kp] fp16 for the joint-entropy GEMM, marginal entropies [N]
+    fp16) in one pass (the permute of reference epig.py:374-376 + marginal_entropy_from_probs :294-311)."""
+    n, k, cl = probs.shape
+    probs = probs.contiguous()
+    dev = probs.device
+    oper = torch.empty((n, cl, int(lib.bvlm_epig_operand_k(k))), dtype=torch.float16, device=dev) if want_operand else None
+    marg = torch.empty(n, dtype=torch.float16, device=dev) if want_entropy else None
+    _lib.run(dev, "bvlm_epig_prepare_from_probs", _lib.ptr(probs), n, k, cl, _lib.ptr(oper), _lib.ptr(marg),
+             _lib.stream_ptr(dev))
+    return oper, marg
+
+
+def prepare_from_noise(mean: torch.Tensor, var: torch.Tensor, eps: torch.Tensor, want_probs: bool = False,
+                       want_operand: bool = True, want_entropy: bool = True):
+    """E0 + E1 + operand layout fused: noise eps [K, N, Cl] (torch.randn order, reference vlm.py:121) and logits
+    mean / var [N, Cl] -> (probs [N, K, Cl] fp16 | None, operand [N, Cl, Kp] fp16 | None, marginal entropies [N] fp16 | None)."""
+    from .vlm import _check_noise_shapes
+
+    k, n, cl = _check_noise_shapes(mean, var, eps)
+    dev = mean.device
+    f16 = dict(dtype=torch.float16, device=dev)
+    probs = torch.empty((n, k, cl), **f16) if want_probs else None
+    oper = torch.empty((n, cl, int(lib.bvlm_epig_operand_k(k))), **f16) if want_operand else None
+    marg = torch.empty(n, **f16) if want_entropy else None
+    _lib.run(dev, "bvlm_epig_prepare_from_noise", _lib.ptr(mean.contiguous()), _lib.ptr(var.contiguous()),
+             _lib.ptr(eps.contiguous()), n, k, cl, _lib.ptr(probs), _lib.ptr(oper), _lib.ptr(marg), _lib.stream_ptr(dev))
+    return probs, oper, marg
 
 
 def entropy_from_probs(probs: torch.Tensor) -> torch.Tensor:
@@ -32,31 +74,33 @@ def entropy_from_probs(probs: torch.Tensor) -> torch.Tensor:
 def marginal_entropy_from_probs(probs: torch.Tensor) -> torch.Tensor:
     """H[E_theta p(y|x,theta)] for probs [N, K, Cl] -> [N] (reference epig.py:294-311)."""
     assert probs.ndim == 3
-    if _kernel_path_ok(probs):
-        n, k, cl = probs.shape
-        out = torch.empty(n, dtype=torch.float16, device=probs.device)
-        rc = lib.bvlm_epig_marginal_entropy_f16(_lib.ptr(probs.contiguous()), n, k, cl, _lib.ptr(out),
-                                                _lib.stream_ptr(probs.device))
-        _lib.check(rc, "bvlm_epig_marginal_entropy_f16")
-        return out
     if not probs.is_cuda:
         raise RuntimeError("bayesvlm_b200.epig runs on CUDA tensors only (no CPU fallback)")
+    if _kernel_path_ok(probs) and _prepare_fits(probs.shape[1], probs.shape[2], False):
+        return prepare_from_probs(probs, want_operand=False)[1]
     return entropy_from_probs(torch.mean(probs, dim=1))
 
 
+def joint_entropy_from_operands(oper_pool: torch.Tensor, oper_targ: torch.Tensor, k: int, chunk_size: int) -> torch.Tensor:
+    """E_t H[p(y, y_t | x, x_t)] from the permuted operands [N, Cl, Kp]: fp32 accumulation over column chunks of the
+    flattened (t, c) axis with the reference's fp16 rounding points inside a chunk (epig.py:376-393)."""
+    n_p, cl, _ = oper_pool.shape
+    n_t = oper_targ.shape[0]
+    dev = oper_pool.device
+    out = torch.empty(n_p, dtype=torch.float32, device=dev)
+    _lib.run(dev, "bvlm_epig_joint_entropy_operands", _lib.ptr(oper_pool), n_p, _lib.ptr(oper_targ), n_t, k, cl,
+             int(chunk_size), _lib.ptr(out), _lib.stream_ptr(dev))
+    return out
+
+
 def joint_entropy_from_probs(probs_pool: torch.Tensor, probs_targ: torch.Tensor, chunk_size: int) -> torch.Tensor:
-    """E_t H[p(y, y_t | x, x_t)] accumulated in fp32 over column chunks of the flattened (t, c) axis (epig.py:376-393)."""
+    """Same term from fp16 probabilities [N, K, Cl] (permutes internally)."""
     n_p, k, cl = probs_pool.shape
-    n_t = probs_targ.shape[0]
     if probs_targ.shape[1] != k or probs_targ.shape[2] != cl:
         raise ValueError("pool and target probabilities must share [K, Cl]")
-    out = torch.empty(n_p, dtype=torch.float32, device=probs_pool.device)
-    ws = _lib.workspace(probs_pool.device, lib.bvlm_epig_joint_workspace_bytes(n_p, n_t, k, cl), tag="epig")
-    rc = lib.bvlm_epig_joint_entropy_f16(_lib.ptr(probs_pool.contiguous()), n_p, _lib.ptr(probs_targ.contiguous()), n_t, k,
-                                         cl, int(chunk_size), _lib.ptr(out), _lib.ptr(ws), ws.numel(),
-                                         _lib.stream_ptr(probs_pool.device))
-    _lib.check(rc, "bvlm_epig_joint_entropy_f16")
-    return out
+    oper_p, _ = prepare_from_probs(probs_pool, want_entropy=False)
+    oper_t, _ = prepare_from_probs(probs_targ, want_entropy=False)
+    return joint_entropy_from_operands(oper_p, oper_t, k, chunk_size)
 
 
 def _joint_entropy_torch(probs_pool, probs_targ, chunk_size):
@@ -80,30 +124,53 @@ def epig_from_probs_using_matmul(probs_pool: torch.Tensor, probs_targ: torch.Ten
     assert probs_pool.ndim == probs_targ.ndim == 3
     if not (probs_pool.is_cuda and probs_targ.is_cuda):
         raise RuntimeError("bayesvlm_b200.epig runs on CUDA tensors only (no CPU fallback)")
-    cl = probs_targ.shape[2]
+    k, cl = probs_targ.shape[1], probs_targ.shape[2]
+    if probs_pool.shape[1] != k or probs_pool.shape[2] != cl:
+        raise ValueError("pool and target probabilities must share [K, Cl]")
+    fused = (_kernel_path_ok(probs_pool) and _kernel_path_ok(probs_targ) and _joint_fused_ok(k, cl, chunk_size) and
+             _prepare_fits(k, cl, False))
+    if fused:
+        oper_p, entropy_pool = prepare_from_probs(probs_pool)
+        oper_t, entropy_targ = prepare_from_probs(probs_targ)
+        entropy_joint = joint_entropy_from_operands(oper_p, oper_t, k, chunk_size)
+        return entropy_pool + torch.mean(entropy_targ) - entropy_joint
     entropy_pool = marginal_entropy_from_probs(probs_pool)
     entropy_targ_mean = torch.mean(marginal_entropy_from_probs(probs_targ))
-    fused = (_kernel_path_ok(probs_pool) and _kernel_path_ok(probs_targ) and cl <= 128 and
-             chunk_size % _JOINT_TILE_N == 0 and probs_pool.shape[1] * cl * 2 <= 48 * 1024)
-    if fused:
-        entropy_joint = joint_entropy_from_probs(probs_pool, probs_targ, chunk_size)
-    else:
-        entropy_joint = _joint_entropy_torch(probs_pool, probs_targ, chunk_size)
-    return entropy_pool + entropy_targ_mean - entropy_joint
+    return entropy_pool + entropy_targ_mean - _joint_entropy_torch(probs_pool, probs_targ, chunk_size)
 
 
 @torch.no_grad()
 def epig_from_logits_using_matmul(logits_pool: ProbabilisticLogits, logits_targ: ProbabilisticLogits, seed: int,
                                   num_samples: int, chunk_size: int = 4096) -> torch.Tensor:
     """Pool rows in chunks of ``chunk_size``; each chunk re-draws target AND pool samples under ``seed + row_offset``
-    (both calls re-seed torch's generator with the same value), casts to fp16 and scores (reference epig.py:313-340)."""
+    (both calls re-seed torch's generator with the same value), casts to fp16 and scores (reference epig.py:313-340).
+
+    The noise comes from ``torch.randn`` on the logits' device exactly as in the reference (``vlm.py:121``); sampling,
+    fp16 cast, the permutes and the marginal entropies are one kernel per side, the joint term one tcgen05 GEMM."""
     pieces = []
     n_pool = logits_pool.mean.shape[0]
+    cl = logits_pool.mean.shape[-1]
+    fused = (logits_pool.var.ndim == 2 and logits_targ.var.ndim == 2 and logits_pool.mean.is_cuda and
+             logits_pool.mean.dtype == torch.float32 and logits_targ.mean.dtype == torch.float32 and
+             _joint_fused_ok(num_samples, cl, chunk_size) and _prepare_fits(num_samples, cl, True))
     for lo in range(0, n_pool, chunk_size):
-        probs_targ = logits_targ.sample_probas_f16(num_samples, seed=seed + lo)
-        chunk = ProbabilisticLogits(mean=logits_pool.mean[lo:lo + chunk_size], var=logits_pool.var[lo:lo + chunk_size])
-        probs_pool = chunk.sample_probas_f16(num_samples, seed=seed + lo)
-        pieces.append(epig_from_probs_using_matmul(probs_pool, probs_targ, chunk_size=chunk_size).to(torch.float32))
+        if not fused:
+            probs_targ = logits_targ.sample_probas_f16(num_samples, seed=seed + lo)
+            chunk = ProbabilisticLogits(mean=logits_pool.mean[lo:lo + chunk_size], var=logits_pool.var[lo:lo + chunk_size])
+            probs_pool = chunk.sample_probas_f16(num_samples, seed=seed + lo)
+            pieces.append(epig_from_probs_using_matmul(probs_pool, probs_targ, chunk_size=chunk_size).to(torch.float32))
+            continue
+        dev = logits_targ.mean.device
+        torch.manual_seed(seed + lo)
+        eps = torch.randn((num_samples,) + tuple(logits_targ.mean.shape), device=dev)
+        _, oper_t, ent_t = prepare_from_noise(logits_targ.mean, logits_targ.var, eps)
+        mean_p, var_p = logits_pool.mean[lo:lo + chunk_size], logits_pool.var[lo:lo + chunk_size]
+        torch.manual_seed(seed + lo)
+        eps = torch.randn((num_samples,) + tuple(mean_p.shape), device=mean_p.device)
+        _, oper_p, ent_p = prepare_from_noise(mean_p, var_p, eps)
+        del eps
+        joint = joint_entropy_from_operands(oper_p, oper_t, num_samples, chunk_size)
+        pieces.append((ent_p + torch.mean(ent_t) - joint).to(torch.float32))
     return torch.cat(pieces, dim=0)
 
 

@@ -50,15 +50,12 @@ def _ggn(source: torch.Tensor, target: torch.Tensor, logit_scale, logit_bias, si
     ws = _lib.workspace(dev, lib.bvlm_ggn_workspace_bytes(b, c, d, prec), tag="ggn")
     ls = float(logit_scale)
     if siglip:
-        rc = lib.bvlm_ggn_siglip(_lib.ptr(source), b, source.stride(0), _lib.ptr(target), c, target.stride(0), d, ls,
-                                 float(logit_bias), prec, _lib.ptr(out), out.stride(0), int(accumulate), _lib.ptr(ws), ws.numel(),
-                                 _lib.stream_ptr(dev))
-        _lib.check(rc, "bvlm_ggn_siglip")
+        _lib.run(dev, "bvlm_ggn_siglip", _lib.ptr(source), b, source.stride(0), _lib.ptr(target), c, target.stride(0), d, ls,
+                 float(logit_bias), prec, _lib.ptr(out), out.stride(0), int(accumulate), _lib.ptr(ws), ws.numel(),
+                 _lib.stream_ptr(dev))
     else:
-        rc = lib.bvlm_ggn_infonce(_lib.ptr(source), b, source.stride(0), _lib.ptr(target), c, target.stride(0), d, ls,
-                                  prec, _lib.ptr(out), out.stride(0), int(accumulate), _lib.ptr(ws), ws.numel(),
-                                  _lib.stream_ptr(dev))
-        _lib.check(rc, "bvlm_ggn_infonce")
+        _lib.run(dev, "bvlm_ggn_infonce", _lib.ptr(source), b, source.stride(0), _lib.ptr(target), c, target.stride(0), d, ls,
+                 prec, _lib.ptr(out), out.stride(0), int(accumulate), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev))
     return out
 
 
@@ -84,7 +81,8 @@ def compute_hessian_analytic_SigLIP(x_batch: torch.Tensor, indices_batch: torch.
 
 def syrk_accumulate(acts: torch.Tensor, out: Optional[torch.Tensor] = None, append_one: bool = False,
                     alpha: float = 1.0, accumulate: bool = False) -> torch.Tensor:
-    """K1: ``out (+)= alpha * [acts 1?]^T [acts 1?]`` (scripts/hessian_estimation.py:99-104), bf16 operands, fp32 acc."""
+    """K1: ``out (+)= alpha * [acts 1?]^T [acts 1?]`` (scripts/hessian_estimation.py:99-104); fp16 operands with exact per-feature
+    power-of-two scaling, fp32 accumulation."""
     acts = _lib.rowmajor(_lib.require_cuda(acts, "activations"))
     n, d = acts.shape
     d_a = d + (1 if append_one else 0)
@@ -96,10 +94,9 @@ def syrk_accumulate(acts: torch.Tensor, out: Optional[torch.Tensor] = None, appe
             out.zero_()
         return out
     ws = _lib.workspace(acts.device, lib.bvlm_syrk_workspace_bytes(n, d, int(append_one), _lib.PREC_X1), tag="syrk")
-    rc = lib.bvlm_syrk_f32acc(_lib.ptr(acts), n, d, acts.stride(0), int(append_one), _lib.PREC_X1, _lib.ptr(out),
-                              out.stride(0), float(alpha), int(accumulate), _lib.ptr(ws), ws.numel(),
-                              _lib.stream_ptr(acts.device))
-    _lib.check(rc, "bvlm_syrk_f32acc")
+    _lib.run(acts.device, "bvlm_syrk_f32acc", _lib.ptr(acts), n, d, acts.stride(0), int(append_one), _lib.PREC_X1,
+             _lib.ptr(out), out.stride(0), float(alpha), int(accumulate), _lib.ptr(ws), ws.numel(),
+             _lib.stream_ptr(acts.device))
     return out
 
 

@@ -67,9 +67,8 @@ def _quadform(act: torch.Tensor, factor: _FactorOperand, has_bias: bool) -> torc
     if d + bias != factor.dA:
         raise ValueError(f"activations have {d}(+{bias}) features but A_inv is {factor.dA}^2")
     ws = _lib.workspace(act.device, lib.bvlm_quadform_workspace_bytes(n, d, bias))
-    rc = lib.bvlm_quadform(_lib.ptr(act), n, d, act.stride(0), bias, _lib.ptr(factor.w16), factor.dA, factor.k_pad,
-                           factor.scale, _lib.ptr(out), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(act.device))
-    _lib.check(rc, "bvlm_quadform")
+    _lib.run(act.device, "bvlm_quadform", _lib.ptr(act), n, d, act.stride(0), bias, _lib.ptr(factor.w16), factor.dA,
+             factor.k_pad, factor.scale, _lib.ptr(out), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(act.device))
     return out
 
 

@@ -64,21 +64,32 @@ def probit_softmax(mean: torch.Tensor, var: torch.Tensor) -> torch.Tensor:
     var = var.contiguous()
     out = torch.empty_like(mean)
     n, c = mean.shape
-    rc = lib.bvlm_probit_softmax(_lib.ptr(mean), _lib.ptr(var), n, c, c, _lib.ptr(out), _lib.stream_ptr(mean.device))
-    _lib.check(rc, "bvlm_probit_softmax")
+    _lib.run(mean.device, "bvlm_probit_softmax", _lib.ptr(mean), _lib.ptr(var), n, c, c, _lib.ptr(out),
+             _lib.stream_ptr(mean.device))
     return out
+
+
+def _check_noise_shapes(mean: torch.Tensor, var: torch.Tensor, eps: torch.Tensor):
+    """Validate the operands of the sampling kernel (it indexes raw pointers): fp32 CUDA tensors on one device with
+    mean / var [N, Cl] and eps [K, N, Cl]; returns (K, N, Cl)."""
+    _lib.require_cuda(mean, "mean")
+    _lib.require_cuda(var, "var")
+    _lib.require_cuda(eps, "eps")
+    if eps.dim() != 3 or mean.dim() != 2 or tuple(mean.shape) != tuple(var.shape) or tuple(eps.shape[1:]) != tuple(mean.shape):
+        raise ValueError(f"expected mean/var [N, Cl] and eps [K, N, Cl]; got {tuple(mean.shape)}, {tuple(var.shape)}, "
+                         f"{tuple(eps.shape)}")
+    if not (mean.device == var.device == eps.device):
+        raise ValueError("mean, var and eps must live on the same device")
+    k, n, cl = eps.shape
+    return k, n, cl
 
 
 def sample_probas_from_noise(mean: torch.Tensor, var: torch.Tensor, eps: torch.Tensor) -> torch.Tensor:
     """E0: fp16 ``softmax(mean + eps * sqrt(var))`` in the [N, K, Cl] layout from noise eps [K, N, Cl]."""
-    _lib.require_cuda(mean, "mean")
-    _lib.require_cuda(var, "var")
-    _lib.require_cuda(eps, "eps")
-    k, n, cl = eps.shape
+    k, n, cl = _check_noise_shapes(mean, var, eps)
     out = torch.empty((n, k, cl), dtype=torch.float16, device=mean.device)
-    rc = lib.bvlm_epig_sample_probs(_lib.ptr(mean.contiguous()), _lib.ptr(var.contiguous()), _lib.ptr(eps.contiguous()),
-                                    n, k, cl, _lib.ptr(out), _lib.stream_ptr(mean.device))
-    _lib.check(rc, "bvlm_epig_sample_probs")
+    _lib.run(mean.device, "bvlm_epig_sample_probs", _lib.ptr(mean.contiguous()), _lib.ptr(var.contiguous()),
+             _lib.ptr(eps.contiguous()), n, k, cl, _lib.ptr(out), _lib.stream_ptr(mean.device))
     return out
 
 
@@ -222,9 +233,8 @@ class _FactorOperand:
         self.dA = d
         self.k_pad = int(lib.bvlm_padded_k(d))
         self.w16 = torch.empty((d, self.k_pad), dtype=torch.float16, device=a_inv.device)
-        rc = lib.bvlm_factor_prepare(_lib.ptr(w), d, d, self.scale, _lib.ptr(self.w16), self.k_pad,
-                                     _lib.stream_ptr(a_inv.device))
-        _lib.check(rc, "bvlm_factor_prepare")
+        _lib.run(a_inv.device, "bvlm_factor_prepare", _lib.ptr(w), d, d, self.scale, _lib.ptr(self.w16), self.k_pad,
+                 _lib.stream_ptr(a_inv.device))
         self._keep = w  # the conversion is asynchronous: keep the source alive with the operand
 
 
@@ -258,16 +268,14 @@ class CLIP(torch.nn.Module):
     def device(self):
         return self.logit_scale.data.device
 
-    def _logit_scale_value(self) -> float:
-        """Host copy of the (log-space) logit scale, refreshed only when the parameter is modified: reading a CUDA
-        scalar synchronises the stream, which would serialise every kernel call behind the previous one."""
-        p = self.logit_scale
-        key = (p._version, p.data_ptr())
-        cached = getattr(self, "_ls_cache", None)
-        if cached is None or cached[0] != key:
-            cached = (key, float(p.detach()))
-            self._ls_cache = cached
-        return cached[1]
+    def _logit_scale_args(self, dev: torch.device):
+        """(host value, device pointer) of the log-space logit scale for the kernels.  When the parameter lives on the
+        kernels' device the kernel reads it there (no host sync per call, and in-place `.data` updates -- the idiom of
+        reference epig.py:230 -- are always seen); otherwise the host value is read now."""
+        p = self.logit_scale.data
+        if p.is_cuda and p.device == dev and p.dtype == torch.float32:
+            return 0.0, _lib.ptr(p)
+        return float(p), _lib.ptr(None)
 
     def set_covariances(self, source_covariance=None, target_covariance=None):
         def _own(cov):
@@ -337,12 +345,11 @@ class CLIP(torch.nn.Module):
         col_b = torch.empty(c_pad, dtype=torch.float32, device=emb.device)
         ws_bytes = lib.bvlm_predictive_target_workspace_bytes(c, d, d_act, bias)
         ws = _lib.workspace(emb.device, ws_bytes)
-        rc = lib.bvlm_predictive_target_prepare(
-            _lib.ptr(emb), c, d, emb.stride(0), _lib.ptr(act), d_act, act.stride(0), bias, _lib.ptr(tgt.factor.w16),
+        _lib.run(
+            emb.device, "bvlm_predictive_target_prepare", _lib.ptr(emb), c, d, emb.stride(0), _lib.ptr(act), d_act, act.stride(0), bias, _lib.ptr(tgt.factor.w16),
             tgt.factor.dA, tgt.factor.k_pad, tgt.factor.scale, _lib.ptr(src.diag_b), sum_delta, kappa, prec,
             _lib.ptr(t16), _lib.ptr(t8), _lib.ptr(col_a), _lib.ptr(col_b), _lib.ptr(ws), ws.numel(),
             _lib.stream_ptr(emb.device))
-        _lib.check(rc, "bvlm_predictive_target_prepare")
         self._target_cache = (key, target.embeds, target.activations, t16, t8, col_a, col_b)
         return t16, t8, col_a, col_b
 
@@ -415,13 +422,14 @@ class CLIP(torch.nn.Module):
             raise ValueError("mean / var / probs must share their row pitch")
         ws_bytes = lib.bvlm_predictive_workspace_bytes(n, d, d_act, bias, prec)
         ws = _lib.workspace(emb.device, ws_bytes)
-        rc = lib.bvlm_predictive(
+        ls_host, ls_dev = self._logit_scale_args(emb.device)
+        _lib.run(
+            emb.device, "bvlm_predictive",
             _lib.ptr(emb), n, d, emb.stride(0), _lib.ptr(act), d_act, act.stride(0), bias, _lib.ptr(src.factor.w16),
             src.factor.dA, src.factor.k_pad, src.factor.scale, _lib.ptr(tgt.diag_b), sum_beta,
-            self._logit_scale_value(), _lib.ptr(t16), _lib.ptr(t8), _lib.ptr(col_a), _lib.ptr(col_b), c, prec,
+            ls_host, ls_dev, _lib.ptr(t16), _lib.ptr(t8), _lib.ptr(col_a), _lib.ptr(col_b), c, prec,
             _lib.ptr(mean), _lib.ptr(var), _lib.ptr(probs), mean.stride(0), _lib.ptr(ws), ws.numel(),
             _lib.stream_ptr(emb.device))
-        _lib.check(rc, "bvlm_predictive")
 
     def forward(self, source_embeds: Union[torch.Tensor, EncoderResult], target_embeds: Union[torch.Tensor, EncoderResult],
                 map_estimate: bool = False):

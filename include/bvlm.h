@@ -97,6 +97,8 @@ int bvlm_quadform(const float* act, int64_t n, int64_t d, int64_t ld, int append
  *   var  [N, C] = exp(2 logit_scale) * [ (e_i^2 + alpha_i beta) . (gamma_j delta) + alpha_i beta . t_j^2 ] / (E_i E_j)
  *   probs [N, C] (optional, may be NULL) = softmax_j( mean / sqrt(1 + pi/8 var) )   scripts/zeroshot.py:119-120
  * (logit_bias is NOT added to the probabilistic mean -- vlm.py:681-684.)
+ * logit_scale is in log space; when logit_scale_dev (a DEVICE fp32 scalar, e.g. the module parameter itself) is not NULL it
+ * is read by the kernel instead of the host value, so in-place parameter updates are always seen and no host sync is needed.
  * --------------------------------------------------------------------------------------------------------- */
 size_t bvlm_predictive_target_workspace_bytes(int64_t C, int64_t D, int64_t d_act, int append_one);
 /* T8: [C, bvlm_predictive_t8_cols(D)] bytes of E4M3 operands, only for BVLM_PREC_X2F8 (NULL otherwise). */
@@ -108,9 +110,9 @@ int bvlm_predictive_target_prepare(const float* T, int64_t C, int64_t D, int64_t
 size_t bvlm_predictive_workspace_bytes(int64_t N, int64_t D, int64_t d_act, int append_one, int precision);
 int bvlm_predictive(const float* E, int64_t N, int64_t D, int64_t lde, const float* Eact, int64_t d_act, int64_t ldact,
                     int append_one, const void* Wi16, int64_t dA, int64_t k_pad, float w_scale, const float* delta,
-                    float sum_beta, float logit_scale, const void* T16, const void* T8, const float* colA, const float* colB,
-                    int64_t C, int precision, float* mean, float* var, float* probs, int64_t ldo, void* ws, size_t ws_bytes,
-                    void* stream);
+                    float sum_beta, float logit_scale, const float* logit_scale_dev, const void* T16, const void* T8,
+                    const float* colA, const float* colB, int64_t C, int precision, float* mean, float* var, float* probs,
+                    int64_t ldo, void* ws, size_t ws_bytes, void* stream);
 
 /* P3 -- standalone canonical probit softmax (scripts/zeroshot.py:119-120). */
 int bvlm_probit_softmax(const float* mean, const float* var, int64_t N, int64_t C, int64_t ld, float* probs,
@@ -120,12 +122,25 @@ int bvlm_probit_softmax(const float* mean, const float* var, int64_t N, int64_t 
  * E0 -- MC class probabilities  (bayesvlm/vlm.py:116-123):  probs[n,k,:] = softmax(mean[n,:] + eps[k,n,:] sqrt(var[n,:]))
  * eps [K, N, Cl] fp32 comes from torch.randn under the caller's torch.manual_seed (RNG parity with the reference);
  * probs [N, K, Cl] fp16.
- * E1 -- marginal entropy  (bayesvlm/epig.py:294-311, 275-292) on fp16 probabilities with the reference's fp16
- * rounding points (mean over K -> fp16, xlogy -> fp16, sum -> fp16); out [N] fp16.
+ * E1 -- marginal entropy  (bayesvlm/epig.py:294-311, 275-292) on fp16 probabilities with the rounding points of torch's
+ * CUDA kernels (mean over K = fp32 sum * fp32(1/K) -> fp16; xlogy = fp16(x * logf(x)), one rounding; sum -> fp16); out [N] fp16.
  * E2 -- joint-entropy term of EPIG (bayesvlm/epig.py:376-393):
- *   Hjoint[p] = sum_chunks fp16( fp16(-sum_{c,col in chunk} fp16(xlogy(j,j))) / N_t ),  j = fp16(fp16(pool @ targ) / K)
+ *   Hjoint[p] = sum_chunks fp16( fp16(-sum_{c,col in chunk} fp16(j log j)) * fp32(1/N_t) ),  j = fp16(fp16(pool @ targ) * fp32(1/K))
  * pool [Np, K, Cl], targ [Nt, K, Cl] fp16; col_chunk = chunk_size of the reference (columns of the flattened (t,c) axis).
+ * NOTE: torch's CPU kernels round differently (xlogy rounds log() to Half first); these entry points follow the CUDA
+ * kernels, i.e. what the reference computes when it runs on the GPU this library replaces it on.
+ *
+ * bvlm_epig_prepare_from_noise / _from_probs: E0 + E1 + the permute of epig.py:374-376 in ONE pass over the samples.
+ * Every output is optional (NULL): probs16 [N, K, Cl]; oper16 [N, Cl, bvlm_epig_operand_k(K)] = the K-major, zero-padded
+ * operand bvlm_epig_joint_entropy_operands consumes; marg16 [N] marginal entropies.
  * --------------------------------------------------------------------------------------------------------- */
+int bvlm_epig_operand_k(int64_t K);
+int bvlm_epig_prepare_from_noise(const float* mean, const float* var, const float* eps, int64_t N, int64_t K, int64_t Cl,
+                                 void* probs16, void* oper16, void* marg16, void* stream);
+int bvlm_epig_prepare_from_probs(const void* probs16, int64_t N, int64_t K, int64_t Cl, void* oper16, void* marg16,
+                                 void* stream);
+int bvlm_epig_joint_entropy_operands(const void* poolP, int64_t Np, const void* targP, int64_t Nt, int64_t K, int64_t Cl,
+                                     int64_t col_chunk, float* Hjoint, void* stream);
 int bvlm_epig_sample_probs(const float* mean, const float* var, const float* eps, int64_t N, int64_t K, int64_t Cl,
                            void* probs16, void* stream);
 int bvlm_epig_marginal_entropy_f16(const void* probs16, int64_t N, int64_t K, int64_t Cl, void* out16, void* stream);

@@ -263,45 +263,63 @@ def sample_probas(mean, var, eps):
     return _softmax(np.transpose(samples, (1, 0, 2)), axis=2)
 
 
-def _xlogy_f16(p16):
-    """torch.xlogy on Half tensors rounds log(y) to Half before the multiply (verified against torch 2.11 CPU)."""
+def _xlogy_f16(p16, device="cpu"):
+    """torch.xlogy(p, p) on Half tensors.  torch's two backends round differently (both verified against torch 2.11,
+    scripts/probe_epig_parity.py and tests/golden/torch_cuda_half_semantics.npz):
+      device="cpu":  log(y) is rounded to Half BEFORE the multiply (c10 Half math: `std::log(Half) -> Half`);
+      device="cuda": `x * std::log(y)` is evaluated in float in device code and rounded to Half ONCE."""
     p32 = p16.astype(F32)
     with np.errstate(divide="ignore", invalid="ignore"):
-        lg = np.log(p32).astype(F16).astype(F32)
+        lg = np.log(p32.astype(np.float64)).astype(F32)  # correctly rounded logf
+        if device == "cpu":
+            lg = lg.astype(F16).astype(F32)
         out = (p32 * lg).astype(F16)
     out[p16 == 0] = 0
     return out
 
 
-def entropy_from_probs_f16(p16):
+def _div_scalar_f16(x16, k, device="cpu"):
+    """Half tensor / python scalar: true fp32 division on the CPU, multiplication by the fp32 reciprocal (computed in
+    double) on CUDA (div_true_kernel_cuda's CPU-scalar shortcut); the two agree except for rare last-bit cases."""
+    if device == "cpu":
+        return (x16.astype(F32) / F32(k)).astype(F16)
+    return (x16.astype(F32) * F32(1.0 / float(k))).astype(F16)
+
+
+def entropy_from_probs_f16(p16, device="cpu"):
     """-sum xlogy with fp32 accumulation rounded to fp16 (epig.py:292 on Half input)."""
-    return (-(_xlogy_f16(p16).astype(F32).sum(-1).astype(F16))).astype(F16)
+    return (-(_xlogy_f16(p16, device).astype(F32).sum(-1).astype(F16))).astype(F16)
 
 
-def marginal_entropy_f16(probs16):
+def marginal_entropy_f16(probs16, device="cpu"):
     """H[mean_K p] on fp16 probabilities [N, K, Cl] with the reference's rounding points (epig.py:306-308)."""
     assert probs16.ndim == 3
     k = probs16.shape[1]
-    pbar = (probs16.astype(F32).sum(axis=1) / F32(k)).astype(F16)
-    return entropy_from_probs_f16(pbar)
+    s = probs16.astype(F32).sum(axis=1)
+    pbar = (s / F32(k)).astype(F16) if device == "cpu" else (s * F32(1.0 / k)).astype(F16)
+    return entropy_from_probs_f16(pbar, device)
 
 
-def epig_from_probs_f16(pool16, targ16, chunk_size=8192):
-    """EPIG scores with every fp16 rounding point of epig.py:342-397 (returns float32 [N_p])."""
+def epig_from_probs_f16(pool16, targ16, chunk_size=8192, device="cpu"):
+    """EPIG scores with every fp16 rounding point of epig.py:342-397 (returns float32 [N_p]).
+
+    `device` selects whose Half kernels are restated: the reference run on the CPU (the golden fixtures) or on CUDA (what
+    the B200 kernels must reproduce; pinned by tests/golden/torch_cuda_half_semantics.npz, recorded on a B200)."""
     assert pool16.ndim == targ16.ndim == 3
     n_t, k, cl = targ16.shape
-    h_pool = marginal_entropy_f16(pool16)                                               # :371
-    h_targ = marginal_entropy_f16(targ16)
-    h_targ_mean = (h_targ.astype(F32).sum() / F32(n_t)).astype(F16)                     # :372
+    h_pool = marginal_entropy_f16(pool16, device)                                       # :371
+    h_targ = marginal_entropy_f16(targ16, device)
+    ht = h_targ.astype(F32).sum()
+    h_targ_mean = (ht / F32(n_t)).astype(F16) if device == "cpu" else F16(ht * F32(1.0 / n_t))  # :372
     pool = np.transpose(pool16, (0, 2, 1)).astype(F32)                                  # [N_p, Cl, K]
     targ = np.transpose(targ16, (1, 0, 2)).reshape(k, n_t * cl).astype(F32)             # [K, N_t*Cl]
     acc = np.zeros(pool.shape[0], F32)                                                  # :381
     for lo in range(0, n_t * cl, chunk_size):                                           # :383
         joint = (pool @ targ[:, lo:lo + chunk_size]).astype(F16)                        # :387 fp32 acc -> fp16
-        joint = (joint.astype(F32) / F32(k)).astype(F16)                                # :388
-        xl = _xlogy_f16(joint)                                                          # :390
+        joint = _div_scalar_f16(joint, k, device)                                       # :388
+        xl = _xlogy_f16(joint, device)                                                  # :390
         s = xl.astype(F32).sum(axis=(-2, -1)).astype(F16)                               # :391 sum -> fp16
-        h = ((-s).astype(F32) / F32(n_t)).astype(F16)                                   # :391 "/ N_t" in fp16
+        h = _div_scalar_f16((-s).astype(F16), n_t, device)                              # :391 "/ N_t" in fp16
         acc += h.astype(F32)                                                            # :393 fp32 accumulate
     return (h_pool + h_targ_mean).astype(F32) - acc                                     # :395
 

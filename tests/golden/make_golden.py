@@ -170,7 +170,60 @@ def main():
     (OUT / "golden_meta.json").write_text(json.dumps(meta, indent=1))
     make_knn()
     make_selection()
+    make_epig_online()
     print("wrote", OUT)
+
+
+def epig_online_problem(seed=21, D=32, d_in=40, n_cls=6, n_pool=600, n_targ=300):
+    """Seeded inputs of the online-EPIG golden problem (also imported by the GPU parity test, which re-creates them)."""
+    g = torch.Generator().manual_seed(seed)
+    W = randn(g, D, d_in) / math.sqrt(d_in)
+    pool_a, targ_a = randn(g, n_pool, d_in), randn(g, n_targ, d_in)
+    label_e, label_a = randn(g, n_cls, D), randn(g, n_cls, D)
+    ids = torch.randint(0, n_cls, (n_pool,), generator=g)
+    A_img, A_txt, B_img, B_txt = spd(g, d_in, 3e3), spd(g, D, 3e3), spd(g, D, 20.0), spd(g, D, 20.0)
+    info = {"n_img": 1.0, "n_txt": 1.0, "lambda_img": 600.0, "lambda_txt": 220.0}
+    cfg = dict(budget=3, lr=1e-4, hessian_update_scale=10.0, num_samples=16, seed=0, pool_max_size=512, target_max_size=256,
+               chunk_size=256, logit_scale=math.log(20.0))
+    return dict(W=W, pool_a=pool_a, targ_a=targ_a, label_e=label_e, label_a=label_a, ids=ids, A_img=A_img, A_txt=A_txt,
+                B_img=B_img, B_txt=B_txt, info=info, cfg=cfg)
+
+
+def make_epig_online():
+    """The reference's own select_epig_online (bayesvlm/epig.py:44-273) and fused-chunk EPIG scores on the CPU -> epig_online_small.npz.
+    `python make_golden.py epig_online` regenerates only this file."""
+    import contextlib
+    import io
+
+    r_hess, r_vlm, r_epig, _ = load_reference()
+    pr = epig_online_problem()
+    c = pr["cfg"]
+    proj = torch.nn.Linear(pr["W"].shape[1], pr["W"].shape[0], bias=False)
+    with torch.no_grad():
+        proj.weight.copy_(pr["W"])
+        pool = r_vlm.EncoderResult(embeds=proj(pr["pool_a"]), activations=pr["pool_a"])
+        targ = r_vlm.EncoderResult(embeds=proj(pr["targ_a"]), activations=pr["targ_a"])
+    labels = r_vlm.EncoderResult(embeds=pr["label_e"], activations=pr["label_a"])
+    with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+        idx, scores = r_epig.select_epig_online(
+            label_features=labels, pool_features=pool, target_features=targ, pool_class_ids=pr["ids"], image_projection=proj,
+            clip=r_vlm.CLIP(logit_scale=c["logit_scale"]), A_img=pr["A_img"], A_txt=pr["A_txt"], B_img=pr["B_img"], B_txt=pr["B_txt"],
+            cov_info=dict(pr["info"]), budget=c["budget"], lr=c["lr"], hessian_update_scale=c["hessian_update_scale"],
+            device=torch.device("cpu"), num_samples=c["num_samples"], seed=c["seed"], pool_max_size=c["pool_max_size"],
+            target_max_size=c["target_max_size"], chunk_size=c["chunk_size"])
+    out = dict(selected=np.array(idx, np.int64), scores=np.array(scores, np.float64))
+    # fused-path shaped scores (chunk 256) of the reference's epig_from_probs_using_matmul on fp16 probabilities
+    g = torch.Generator().manual_seed(707)
+    Np, Nt, K, Cl, chunk = 96, 120, 32, 10, 256
+    mp, vp = randn(g, Np, Cl) * 2, torch.rand(Np, Cl, generator=g) * 3 + 0.1
+    mt, vt = randn(g, Nt, Cl) * 2, torch.rand(Nt, Cl, generator=g) * 3 + 0.1
+    ep, et = randn(g, K, Np, Cl), randn(g, K, Nt, Cl)
+    p16 = torch.softmax((ep * vp.sqrt() + mp).permute(1, 0, 2), dim=2).half()
+    t16 = torch.softmax((et * vt.sqrt() + mt).permute(1, 0, 2), dim=2).half()
+    out.update(fused_p16=p16.numpy(), fused_t16=t16.numpy(), fused_chunk=np.array([chunk], np.int64),
+               fused_scores=r_epig.epig_from_probs_using_matmul(p16, t16, chunk_size=chunk).numpy(),
+               fused_marginal=r_epig.marginal_entropy_from_probs(p16).numpy())
+    np.savez_compressed(OUT / "epig_online_small.npz", **out)
 
 
 def make_knn():
@@ -261,5 +314,7 @@ if __name__ == "__main__":
         make_knn()
     elif len(sys.argv) > 1 and sys.argv[1] == "selection":
         make_selection()
+    elif len(sys.argv) > 1 and sys.argv[1] == "epig_online":
+        make_epig_online()
     else:
         main()

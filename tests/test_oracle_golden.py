@@ -5,6 +5,7 @@ import numpy as np
 import pytest
 
 from oracle import laplace_oracle as O
+from conftest import GOLDEN as GOLDEN_DIR
 from conftest import relerr
 
 LS = math.log(100.0)
@@ -191,3 +192,61 @@ def test_product_prior_precision_matches_reference(golden):
     ld = compute_log_det_kfac(A + torch.eye(24), B + torch.eye(16))
     ref = torch.logdet(A + torch.eye(24)) * 24 + torch.logdet(B + torch.eye(16)) * 16
     assert torch.allclose(ld, ref)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# EPIG: CPU vs CUDA Half semantics of torch, the fused-chunk golden and the online loop
+# ---------------------------------------------------------------------------------------------------------------------
+def test_xlogy_half_semantics_of_both_torch_backends():
+    """The oracle's two xlogy modes against tables recorded from torch itself: `xlogy_cpu_bits` by torch's CPU kernel and
+    `xlogy_cuda_bits` by torch's CUDA kernel ON A B200 (scripts/probe_epig_parity.py) for every fp16 value in (0, 1]."""
+    g = np.load(GOLDEN_DIR / "torch_cuda_half_semantics.npz")
+    x = g["x_bits"].view(np.float16)
+    cpu = O._xlogy_f16(x, "cpu").view(np.uint16)
+    cuda = O._xlogy_f16(x, "cuda").view(np.uint16)
+    assert (cpu == g["xlogy_cpu_bits"]).all()
+    assert (cuda == g["xlogy_cuda_bits"]).mean() >= 0.9999  # one value of 15360: logf's last bit
+    # the two backends really differ (which is why the CUDA kernels cannot be pinned on CPU goldens bit for bit)
+    assert (g["xlogy_cpu_bits"] != g["xlogy_cuda_bits"]).mean() > 0.2
+    import torch
+
+    assert (torch.xlogy(torch.from_numpy(x), torch.from_numpy(x)).numpy().view(np.uint16) == g["xlogy_cpu_bits"]).all()
+
+
+def test_epig_fused_chunk_golden_cpu_semantics():
+    """Reference epig_from_probs_using_matmul (CPU) at chunk = 256, the fused kernel's tile width: bit-exact with the oracle's
+    CPU mode and with the torch port; the CUDA mode differs by score quanta only."""
+    import torch
+
+    from oracle import torch_port as T
+
+    g = np.load(GOLDEN_DIR / "epig_online_small.npz")
+    chunk = int(g["fused_chunk"][0])
+    s_cpu = O.epig_from_probs_f16(g["fused_p16"], g["fused_t16"], chunk, device="cpu")
+    assert np.array_equal(s_cpu, g["fused_scores"])
+    assert np.array_equal(O.marginal_entropy_f16(g["fused_p16"], "cpu"), g["fused_marginal"])
+    s_port = T.epig_from_probs(torch.from_numpy(g["fused_p16"]), torch.from_numpy(g["fused_t16"]), chunk_size=chunk)
+    assert np.array_equal(s_port.float().numpy(), g["fused_scores"])
+    s_cuda = O.epig_from_probs_f16(g["fused_p16"], g["fused_t16"], chunk, device="cuda")
+    assert np.abs(s_cuda - g["fused_scores"]).max() <= 4 * 2.0 ** -10
+
+
+def test_torch_port_online_loop_matches_reference():
+    """oracle/torch_port.select_epig_online (the checker of the GPU loop test) against the reference's own
+    select_epig_online run on the CPU by make_golden.py: same picks, same scores."""
+    import importlib.util
+
+    from oracle import torch_port as T
+
+    spec = importlib.util.spec_from_file_location("make_golden", GOLDEN_DIR / "make_golden.py")
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    pr = mg.epig_online_problem()
+    c = pr["cfg"]
+    g = np.load(GOLDEN_DIR / "epig_online_small.npz")
+    sel, sc, _, _ = T.select_epig_online(
+        pr["label_e"], pr["label_a"], pr["pool_a"] @ pr["W"].T, pr["pool_a"], pr["targ_a"] @ pr["W"].T, pr["targ_a"], pr["ids"],
+        pr["W"], c["logit_scale"], pr["A_img"], pr["A_txt"], pr["B_img"], pr["B_txt"], pr["info"], c["budget"], c["lr"],
+        c["hessian_update_scale"], "cpu", c["num_samples"], c["seed"], c["pool_max_size"], c["target_max_size"], c["chunk_size"])
+    assert sel == g["selected"].tolist()
+    np.testing.assert_allclose(sc, g["scores"], rtol=0, atol=1e-7)
