@@ -281,10 +281,13 @@ struct EpiEpigJoint {
     sts_f32(s + 4u * static_cast<uint32_t>((ctx.wid / 4) * 128 + r), st.valid ? st.chunk_acc : 0.f);
     epi_bar_sync(ctx);
     if (st.leader) {
-      float sum = 0.f;
+      // The fp16 rounding of this sum decides the score; it is accumulated in double (Cl * column groups addends of up to
+      // ~1e3, once per chunk and pool row) so that only the reference's own fp32 summation order can move it across a
+      // rounding boundary, not ours as well.
+      double sum = 0.0;
       for (int h = 0; h < ctx.n_warps / 4; ++h)
-        for (int c = 0; c < p.Cl; ++c) sum += lds_f32(s + 4u * static_cast<uint32_t>(h * 128 + r + c));
-      const float neg = -round_f16(sum);               // fp16(sum) then negate
+        for (int c = 0; c < p.Cl; ++c) sum += static_cast<double>(lds_f32(s + 4u * static_cast<uint32_t>(h * 128 + r + c)));
+      const float neg = -round_f16(static_cast<float>(sum));  // fp16(sum) then negate
       st.hj += round_f16(neg * p.inv_Nt);              // "/ N_t" on a Half tensor
     }
     st.chunk_acc = 0.f;

@@ -104,9 +104,12 @@ def syrk_accumulate(acts: torch.Tensor, out: Optional[torch.Tensor] = None, appe
 # K0: the KFAC accumulation loop
 # ----------------------------------------------------------------------------------------------------------------------
 def class_batch_schedule(num_class_batches: int, rank: int, world_size: int):
-    """Class batches owned by ``rank``: round-robin r, r+R, ... (each class batch carries its own paired targets, so
-    nothing is replicated and no data-path collective is needed until the final all-reduce)."""
-    return list(range(rank, num_class_batches, world_size))
+    """Class batches owned by ``rank``: a CONTIGUOUS block (sizes differ by at most one).  Each class batch carries its own
+    paired targets, so nothing is replicated and no data-path collective is needed until the final all-reduce; contiguous
+    blocks let a rank run its K1 SYRK over all of its rows in one launch (A is a plain sum over rows)."""
+    q, r = divmod(num_class_batches, world_size)
+    lo = rank * q + min(rank, r)
+    return list(range(lo, lo + q + (1 if rank < r else 0)))
 
 
 def reduce_factors(A: torch.Tensor, B: torch.Tensor, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -147,7 +150,7 @@ def _kfac_staging(dev: torch.device, num_classes: int, inputs):
 @torch.no_grad()
 def kfac_ggn(vlm, num_classes: int, batch_size: int, source_embeds: torch.Tensor, source_activations: torch.Tensor,
              target_embeds: torch.Tensor, device: str, likelihood: Literal["info_nce", "siglip"],
-             siglip_chunk_size_j: int = 8000, group=None, distributed: Optional[bool] = None
+             siglip_chunk_size_j: int = 8000, group=None, distributed: bool = False
              ) -> Tuple[torch.Tensor, torch.Tensor]:
     """K-FAC (last layer) of the GGN of ``-log p(target | source)``; reference scripts/hessian_estimation.py:26-109.
 
@@ -157,8 +160,11 @@ def kfac_ggn(vlm, num_classes: int, batch_size: int, source_embeds: torch.Tensor
     A is returned on ``device`` and B on the CPU (:84,:97,:100).
 
     New: the whole class batch is processed by one kernel pipeline (the per-row softmax makes the result independent of
-    the reference's data batching), and under an initialised ``torch.distributed`` process group the class batches are
-    sharded round-robin over ranks and summed with ONE all-reduce of [A || B].
+    the reference's data batching).  ``distributed=True`` (explicit opt-in; the default is the reference's single-process
+    semantics whatever process group happens to be initialised) shards the class batches over the ranks of ``group`` in
+    contiguous blocks and sums the factors with ONE all-reduce of [A || B].  CONTRACT: every rank must then call with the
+    IDENTICAL full dataset (each rank reads only its own class batches); ranks holding different shards, or a call from a
+    single rank, are not supported in this mode.
     """
     del siglip_chunk_size_j
     if likelihood not in ("info_nce", "siglip"):
@@ -169,9 +175,13 @@ def kfac_ggn(vlm, num_classes: int, batch_size: int, source_embeds: torch.Tensor
     dev = torch.device(device)
     if dev.type != "cuda":
         raise RuntimeError("kfac_ggn runs on CUDA (sm_100a) only; there is no CPU fallback")
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
     import torch.distributed as dist
 
-    use_dist = dist.is_available() and dist.is_initialized() if distributed is None else distributed
+    use_dist = bool(distributed)
+    if use_dist and not (dist.is_available() and dist.is_initialized()):
+        raise RuntimeError("kfac_ggn(distributed=True) needs an initialised torch.distributed process group")
     rank = dist.get_rank(group) if use_dist else 0
     world = dist.get_world_size(group) if use_dist else 1
 
@@ -180,8 +190,9 @@ def kfac_ggn(vlm, num_classes: int, batch_size: int, source_embeds: torch.Tensor
     logit_bias = float(vlm.logit_bias.detach())
     d_in = source_activations.shape[1] + (1 if siglip else 0)
     d_emb = source_embeds.shape[1]
-    A = torch.zeros((d_in, d_in), dtype=torch.float32, device=dev)
-    B = torch.zeros((d_emb, d_emb), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        A = torch.zeros((d_in, d_in), dtype=torch.float32, device=dev)
+        B = torch.zeros((d_emb, d_emb), dtype=torch.float32, device=dev)
 
     # Host-resident inputs (the reference's calling convention) are staged one class batch AHEAD on a copy stream, so that
     # the PCIe transfer of batch i+1 (235 MB at config 2, ~4.3 ms) overlaps the kernels of batch i (~4.6 ms).  Two sets of
@@ -193,6 +204,9 @@ def kfac_ggn(vlm, num_classes: int, batch_size: int, source_embeds: torch.Tensor
     staged = any(t.device.type == "cpu" for t in inputs)
     main_stream = torch.cuda.current_stream(dev)
     stage = _kfac_staging(dev, num_classes, inputs) if staged else None
+    # K1 (A += act^T act) is independent of the GGN pipeline: it runs on a side stream and fills the SMs the persistent GGN
+    # kernels leave idle at their tails.  Device-resident activations of the rank's contiguous block go through ONE launch.
+    syrk_stream = _kfac_side_stream(dev)
 
     def fetch(i, slot):
         lo, hi = i * num_classes, (i + 1) * num_classes
@@ -219,6 +233,13 @@ def kfac_ggn(vlm, num_classes: int, batch_size: int, source_embeds: torch.Tensor
         return tuple(stage["device"][slot]) + (ready,)
 
     schedule = list(class_batch_schedule(num_class_batches, rank, world))
+    syrk_stream.wait_stream(main_stream)
+    whole_block = (not staged and len(schedule) > 0 and source_activations.device == dev and
+                   source_activations.dtype == torch.float32)
+    if whole_block:
+        with torch.cuda.stream(syrk_stream):
+            syrk_accumulate(source_activations[schedule[0] * num_classes:(schedule[-1] + 1) * num_classes], out=A,
+                            append_one=siglip, accumulate=True)
     if staged:
         stage["stream"].wait_stream(main_stream)
     pending = fetch(schedule[0], 0) if schedule else None
@@ -227,14 +248,19 @@ def kfac_ggn(vlm, num_classes: int, batch_size: int, source_embeds: torch.Tensor
         pending = fetch(schedule[k + 1], (k + 1) % 2) if k + 1 < len(schedule) else None
         if ready is not None:
             main_stream.wait_event(ready)
+        if not whole_block:
+            syrk_stream.wait_stream(main_stream)  # (staged inputs: the copy has landed; also orders the staging-buffer reuse)
+            with torch.cuda.stream(syrk_stream):
+                syrk_accumulate(act, out=A, append_one=siglip, accumulate=True)
         used = (num_classes // batch_size) * batch_size  # data-batch remainder never reaches B
         if used > 0:
             _ggn(src[:used], tgt, logit_scale, logit_bias, siglip=siglip, out=B, accumulate=True)
-        syrk_accumulate(act, out=A, append_one=siglip, accumulate=True)
         if staged:
+            main_stream.wait_stream(syrk_stream)  # the staging set is free once BOTH consumers are done with it
             done = torch.cuda.Event()
             done.record(main_stream)
             stage["consumed"][k % 2] = done
+    main_stream.wait_stream(syrk_stream)
 
     if use_dist and world > 1:
         A, B = reduce_factors(A, B, group)
@@ -242,6 +268,16 @@ def kfac_ggn(vlm, num_classes: int, batch_size: int, source_embeds: torch.Tensor
     A = A / math.sqrt(n)
     B = B / math.sqrt(n)
     return A, B.cpu()
+
+
+_KFAC_SIDE_STREAMS = {}
+
+
+def _kfac_side_stream(dev: torch.device):
+    st = _KFAC_SIDE_STREAMS.get(dev.index)
+    if st is None:
+        st = _KFAC_SIDE_STREAMS[dev.index] = torch.cuda.Stream(dev)
+    return st
 
 
 # ----------------------------------------------------------------------------------------------------------------------

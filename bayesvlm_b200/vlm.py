@@ -420,9 +420,9 @@ class CLIP(torch.nn.Module):
             return
         if mean.stride(0) != var.stride(0) or (probs is not None and probs.stride(0) != mean.stride(0)):
             raise ValueError("mean / var / probs must share their row pitch")
-        ws_bytes = lib.bvlm_predictive_workspace_bytes(n, d, d_act, bias, prec)
-        ws = _lib.workspace(emb.device, ws_bytes)
         ls_host, ls_dev = self._logit_scale_args(emb.device)
+
+        ws = _lib.workspace(emb.device, lib.bvlm_predictive_workspace_bytes(n, d, d_act, bias, prec))
         _lib.run(
             emb.device, "bvlm_predictive",
             _lib.ptr(emb), n, d, emb.stride(0), _lib.ptr(act), d_act, act.stride(0), bias, _lib.ptr(src.factor.w16),
