@@ -16,7 +16,6 @@ using namespace bvlm;
 namespace {
 
 constexpr int EPIG_BN = 256;
-constexpr int EPIG_STAGES = 4;
 
 inline int64_t pad64(int64_t k) { return round_up_i64(k, 64); }
 
@@ -31,14 +30,6 @@ __device__ __forceinline__ float xlogx_f16(float x) {
   return round_f16(x * logf(x));
 }
 
-__device__ __forceinline__ void cp_async_4(uint32_t smem_dst, const void* gsrc) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_dst), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const void* gsrc) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
 // ---------------------------------------------------------------------------------------------------------------
 // E0 + E1 + operand layout in ONE pass over a block of R sample rows                 (vlm.py:116-123, epig.py:294-311, 374-376)
 //   FROM_NOISE : eps [K, N, Cl] fp32 (torch.randn order), mean / var [N, Cl]  ->  probs = softmax(eps * sqrt(var) + mean) -> fp16
@@ -46,95 +37,110 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // outputs (each optional): probs_out [N, K, Cl] fp16, oper [N, Cl, Kp] fp16 (the K-major operand of the joint-entropy GEMM,
 // zero padded along K), marg [N] fp16 marginal entropies with torch's CUDA rounding points (mean over K = fp32 sum times
 // 1/K -> fp16; xlogy -> fp16; sum over Cl in fp32 -> fp16; negate).
-// Data movement: the noise of a row block is one contiguous R*Cl run per MC sample, fetched with cp.async straight into
-// shared memory (odd row stride: the per-sample reads below are conflict free); results are staged in shared memory in
-// their GLOBAL layouts and leave with 128-bit stores; the reduction over K is a warp-shuffle sum with lanes along K.
+//
+// Layout of the work (second version; the first staged the noise of 15 rows in 100 KB of shared memory with 4-byte cp.async,
+// two 256-thread blocks per SM and strictly serial fetch / compute / store phases: 0.87 TB/s, bench r2 `epig.reductions`):
+//   * a block is 128 threads = 128 consecutive MC samples k, and owns R (1..8) sample rows; it needs only the R*Cl*Kp fp16
+//     operand tile in shared memory (10 KB at Cl = 10, K = 100), so 10+ blocks are resident per SM and the fetch of one block
+//     overlaps the arithmetic and the stores of the others;
+//   * thread k reads ITS Cl noise values of a row straight from global memory into registers (the R rows of a block are one
+//     contiguous run per sample, 64-/128-bit loads when Cl is even / a multiple of 4; the next row is fetched before the current
+//     one is evaluated), so no noise is staged anywhere;
+//   * the probabilities go to the shared tile in the OPERAND layout [row][class][k] (lanes along k: conflict free); the tile is
+//     the block's contiguous slice of `oper` and leaves with 128-bit stores, and the same 128-bit reads feed the sum over K of
+//     the marginal entropy (8 values per thread, 3 shuffles, fixed order: deterministic).
 // The softmax follows torch's softmax_warp_forward for rows of <= 16 classes (sum in the 16-lane butterfly order, expf,
 // true division), so the fp16 probabilities are bit-identical to the reference's on the same device.
 // ---------------------------------------------------------------------------------------------------------------
+constexpr int PREP_THREADS = 128;
+constexpr size_t PREP_SMEM_TARGET = 12 * 1024;  // per block when more than one row fits: >= 10 resident blocks per SM
+constexpr size_t PREP_SMEM_MAX = 100 * 1024;    // a single row's tile may take up to this much
+
 struct PrepLayout {
-  int R, estride;
-  size_t off_nk, off_eps, off_ms, bytes;
+  int R;
+  size_t off_part, off_ms, bytes;
 };
 
-inline PrepLayout prep_layout(int64_t K, int64_t Cl, int64_t Kp, bool from_noise, bool need_nk, size_t budget) {
+inline size_t prep_row_bytes(int64_t Cl, int64_t Kp) {
+  return static_cast<size_t>(Cl * Kp * 2) + static_cast<size_t>(Cl) * (Kp / 64) * 4 + static_cast<size_t>(Cl) * 8;
+}
+
+inline PrepLayout prep_layout(int64_t Cl, int64_t Kp) {
   PrepLayout L{};
-  const size_t per_row = static_cast<size_t>(Cl * Kp * 2) + (need_nk ? static_cast<size_t>(K * Cl * 2) : 0) +
-                         (from_noise ? static_cast<size_t>(K * Cl * 4 + 8 * Cl) : 0);
-  const size_t fixed = from_noise ? static_cast<size_t>(K) * 4 + 64 : 64;
-  int R = budget > fixed ? static_cast<int>((budget - fixed) / per_row) : 0;
-  if (R > 32) R = 32;
+  const size_t per_row = prep_row_bytes(Cl, Kp);
+  int R = static_cast<int>(PREP_SMEM_TARGET / per_row);
+  if (R > 8) R = 8;
+  if (R < 1) R = per_row <= PREP_SMEM_MAX ? 1 : 0;
   L.R = R;
   if (R <= 0) return L;
-  L.estride = static_cast<int>(R * Cl) | 1;
-  size_t off = static_cast<size_t>(R) * Cl * Kp * 2;
-  L.off_nk = off;
-  if (need_nk) off += (static_cast<size_t>(R) * K * Cl * 2 + 15) & ~static_cast<size_t>(15);
-  L.off_eps = off;
-  if (from_noise) off += static_cast<size_t>(K) * L.estride * 4;
-  L.off_ms = off;
-  if (from_noise) off += static_cast<size_t>(2 * R * Cl) * 4;
-  L.bytes = off;
+  L.off_part = static_cast<size_t>(R) * Cl * Kp * 2;                       // float [R*Cl][Kp/64] partial sums over K
+  L.off_ms = L.off_part + static_cast<size_t>(R) * Cl * (Kp / 64) * 4;     // float mean[R*Cl], std[R*Cl]
+  L.bytes = L.off_ms + static_cast<size_t>(R) * Cl * 8;
   return L;
 }
 
-template <bool FROM_NOISE, bool CL16>
-__global__ void __launch_bounds__(256)
+// Cl noise values of one (sample, row) into registers; VEC = floats per load (alignment guaranteed by the caller)
+template <int VEC>
+__device__ __forceinline__ void load_noise16(float (&e)[16], const float* __restrict__ src, int Cl) {
+  if constexpr (VEC == 4) {
+#pragma unroll
+    for (int c = 0; c < 16; c += 4)
+      if (c < Cl) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(src + c));
+        e[c] = v.x, e[c + 1] = v.y, e[c + 2] = v.z, e[c + 3] = v.w;
+      }
+  } else if constexpr (VEC == 2) {
+#pragma unroll
+    for (int c = 0; c < 16; c += 2)
+      if (c < Cl) {
+        const float2 v = __ldg(reinterpret_cast<const float2*>(src + c));
+        e[c] = v.x, e[c + 1] = v.y;
+      }
+  } else {
+#pragma unroll
+    for (int c = 0; c < 16; ++c)
+      if (c < Cl) e[c] = __ldg(src + c);
+  }
+}
+
+template <bool FROM_NOISE, bool CL16, int VEC>
+__global__ void __launch_bounds__(PREP_THREADS)
 k_epig_prepare(const float* __restrict__ mean, const float* __restrict__ var, const float* __restrict__ eps,
                const __half* __restrict__ probs_in, int64_t N, int K, int Cl, int Kp, const PrepLayout L,
                __half* __restrict__ probs_out, __half* __restrict__ oper, __half* __restrict__ marg) {
   extern __shared__ __align__(16) uint8_t ps[];
-  __half* s_op = reinterpret_cast<__half*>(ps);               // [R][Cl][Kp]
-  __half* s_nk = reinterpret_cast<__half*>(ps + L.off_nk);    // [R][K][Cl]
-  float* s_eps = reinterpret_cast<float*>(ps + L.off_eps);    // [K][estride]
-  float* s_mean = reinterpret_cast<float*>(ps + L.off_ms);    // [R*Cl]
+  __half* s_op = reinterpret_cast<__half*>(ps);                // [R][Cl][Kp]
+  float* s_part = reinterpret_cast<float*>(ps + L.off_part);   // [R*Cl][Kp/64]
+  float* s_mean = reinterpret_cast<float*>(ps + L.off_ms);     // [R*Cl]
   float* s_std = s_mean + L.R * Cl;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
   const int64_t n0 = static_cast<int64_t>(blockIdx.x) * L.R;
   const int rows = static_cast<int>(N - n0 < L.R ? N - n0 : L.R);
   const int seg = rows * Cl;
-  const bool need_nk = !FROM_NOISE || probs_out != nullptr;
+  const __half hzero = __float2half_rn(0.f);
 
-  // ---- phase 1: fetch the block's inputs
   if constexpr (FROM_NOISE) {
-    for (int k = warp; k < K; k += 8) {
-      const float* src = eps + (static_cast<int64_t>(k) * N + n0) * Cl;
-      const uint32_t dst = smem_u32(s_eps + k * L.estride);
-      for (int j = lane; j < seg; j += 32) cp_async_4(dst + 4u * j, src + j);
-    }
-    for (int j = tid; j < seg; j += 256) {
+    for (int j = tid; j < seg; j += PREP_THREADS) {
       s_mean[j] = mean[n0 * Cl + j];
       s_std[j] = sqrtf(var[n0 * Cl + j]);
     }
-  } else {
-    const __half* src = probs_in + n0 * K * Cl;
-    const int total = rows * K * Cl;
-    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-      for (int i = tid; i < total / 8; i += 256) cp_async_16(smem_u32(s_nk) + 16u * i, src + 8 * i);
-      for (int i = (total / 8) * 8 + tid; i < total; i += 256) s_nk[i] = src[i];
-    } else {
-      for (int i = tid; i < total; i += 256) s_nk[i] = src[i];
-    }
+    __syncthreads();
   }
-  // zero the K padding of the operand tile
-  if (Kp > K) {
-    const int padw = Kp - K;
-    for (int i = tid; i < seg * padw; i += 256) {
-      const int r = i / padw;
-      s_op[r * Kp + K + (i - r * padw)] = __float2half_rn(0.f);
-    }
-  }
-  cp_async_wait_all();
-  __syncthreads();
 
-  // ---- phase 2: one (row, MC sample) per thread, lanes along k
-  for (int i = tid; i < rows * K; i += 256) {
-    const int n = i / K, k = i - n * K;
-    if constexpr (FROM_NOISE) {
-      const float* e = s_eps + k * L.estride + n * Cl;
-      const float* m = s_mean + n * Cl;
-      const float* sd = s_std + n * Cl;
-      if constexpr (CL16) {
+  // ---- phase 1: one (row, MC sample) per thread and step, lanes along k
+  for (int k = tid; k < Kp; k += PREP_THREADS) {
+    if (k >= K) {  // zero padding of the operand along K
+      for (int i = 0; i < seg; ++i) s_op[i * Kp + k] = hzero;
+      continue;
+    }
+    if constexpr (FROM_NOISE && CL16) {
+      const float* src = eps + (static_cast<int64_t>(k) * N + n0) * Cl;
+      float e[16], en[16];
+      load_noise16<VEC>(e, src, Cl);
+      for (int n = 0; n < rows; ++n) {
+        if (n + 1 < rows) load_noise16<VEC>(en, src + (n + 1) * Cl, Cl);  // next row in flight during this row's math
+        const float* m = s_mean + n * Cl;
+        const float* sd = s_std + n * Cl;
         float z[16];
         float zmax = -INFINITY;
 #pragma unroll
@@ -149,66 +155,88 @@ k_epig_prepare(const float* __restrict__ mean, const float* __restrict__ var, co
                     t5 = z[5] + z[13], t6 = z[6] + z[14], t7 = z[7] + z[15];
         const float u0 = t0 + t4, u1 = t1 + t5, u2 = t2 + t6, u3 = t3 + t7;
         const float zsum = (u0 + u2) + (u1 + u3);
+        __half* dst_nk = probs_out != nullptr ? probs_out + ((n0 + n) * K + k) * Cl : nullptr;
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
           if (c < Cl) {
             const __half h = __float2half_rn(z[c] / zsum);
             s_op[(n * Cl + c) * Kp + k] = h;
-            if (need_nk) s_nk[(n * K + k) * Cl + c] = h;
+            if (dst_nk != nullptr) dst_nk[c] = h;
           }
         }
-      } else {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) e[c] = en[c];
+      }
+    } else if constexpr (FROM_NOISE) {
+      for (int n = 0; n < rows; ++n) {
+        const float* e = eps + (static_cast<int64_t>(k) * N + n0 + n) * Cl;  // re-read from L1 in the three sweeps
+        const float* m = s_mean + n * Cl;
+        const float* sd = s_std + n * Cl;
         float zmax = -INFINITY;
-        for (int c = 0; c < Cl; ++c) zmax = fmaxf(zmax, __fadd_rn(__fmul_rn(e[c], sd[c]), m[c]));
+        for (int c = 0; c < Cl; ++c) zmax = fmaxf(zmax, __fadd_rn(__fmul_rn(__ldg(e + c), sd[c]), m[c]));
         float zsum = 0.f;
-        for (int c = 0; c < Cl; ++c) zsum += expf(__fadd_rn(__fmul_rn(e[c], sd[c]), m[c]) - zmax);
+        for (int c = 0; c < Cl; ++c) zsum += expf(__fadd_rn(__fmul_rn(__ldg(e + c), sd[c]), m[c]) - zmax);
+        __half* dst_nk = probs_out != nullptr ? probs_out + ((n0 + n) * K + k) * Cl : nullptr;
         for (int c = 0; c < Cl; ++c) {
-          const __half h = __float2half_rn(expf(__fadd_rn(__fmul_rn(e[c], sd[c]), m[c]) - zmax) / zsum);
+          const __half h = __float2half_rn(expf(__fadd_rn(__fmul_rn(__ldg(e + c), sd[c]), m[c]) - zmax) / zsum);
           s_op[(n * Cl + c) * Kp + k] = h;
-          if (need_nk) s_nk[(n * K + k) * Cl + c] = h;
+          if (dst_nk != nullptr) dst_nk[c] = h;
         }
       }
     } else {
-      for (int c = 0; c < Cl; ++c) s_op[(n * Cl + c) * Kp + k] = s_nk[(n * K + k) * Cl + c];
+      for (int n = 0; n < rows; ++n) {
+        const __half* src = probs_in + ((n0 + n) * K + k) * Cl;
+        for (int c = 0; c < Cl; ++c) s_op[(n * Cl + c) * Kp + k] = src[c];
+      }
     }
   }
   __syncthreads();
 
-  // ---- phase 3: marginal entropies, one warp per row, shuffle reduction over K
-  if (marg != nullptr) {
-    const float inv_k = static_cast<float>(1.0 / static_cast<double>(K));  // torch multiplies by the fp32 reciprocal
-    for (int n = warp; n < rows; n += 8) {
-      float ent = 0.f;
-      for (int c = 0; c < Cl; ++c) {
-        const __half* row = s_op + (n * Cl + c) * Kp;
-        float s = 0.f;
-        for (int k = lane; k < K; k += 32) s += __half2float(row[k]);
-        s = warp_sum(s);
-        ent += xlogx_f16(round_f16(s * inv_k));
-      }
-      if (lane == 0) marg[n0 + n] = __float2half_rn(-round_f16(ent));
-    }
-  }
-
-  // ---- phase 4: results leave in their global layouts, 128 bits at a time
-  if (oper != nullptr) {
-    uint4* dst = reinterpret_cast<uint4*>(oper + n0 * Cl * Kp);  // Kp is a multiple of 64 halves: always 16-byte aligned
+  // ---- phase 2: the tile leaves as the block's contiguous slice of `oper` (128-bit stores); the same reads give the sums
+  // over K: 8 values per thread, then the 8 threads of a 64-sample group (Kp is a multiple of 64)
+  {
+    uint4* dst = oper != nullptr ? reinterpret_cast<uint4*>(oper + n0 * Cl * Kp) : nullptr;  // 16-byte aligned: Kp % 64 == 0
     const uint4* src = reinterpret_cast<const uint4*>(s_op);
-    for (int i = tid; i < seg * Kp / 8; i += 256) dst[i] = src[i];
-  }
-  if (FROM_NOISE && probs_out != nullptr) {
-    __half* dst = probs_out + n0 * K * Cl;
-    const int total = rows * K * Cl;
-    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-      for (int i = tid; i < total / 8; i += 256) reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(s_nk)[i];
-      for (int i = (total / 8) * 8 + tid; i < total; i += 256) dst[i] = s_nk[i];
-    } else {
-      for (int i = tid; i < total; i += 256) dst[i] = s_nk[i];
+    const int total = seg * Kp / 8;  // a multiple of 8
+    const int groups = Kp / 64;
+    for (int i0 = 0; i0 < total; i0 += PREP_THREADS) {
+      const int i = i0 + tid;
+      float s = 0.f;
+      if (i < total) {
+        const uint4 v = src[i];
+        if (dst != nullptr) dst[i] = v;
+        if (marg != nullptr) {
+          const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
+          const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+          const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&v.z));
+          const float2 d = __half22float2(*reinterpret_cast<const __half2*>(&v.w));
+          s = ((a.x + a.y) + (b.x + b.y)) + ((c.x + c.y) + (d.x + d.y));
+        }
+      }
+      if (marg != nullptr) {  // (uniform branch; every lane takes part in the shuffles)
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        if (i < total && (lane & 7) == 0) s_part[i >> 3] = s;  // [row * groups + group]
+      }
+    }
+    if (marg != nullptr) {
+      __syncthreads();
+      // ---- phase 3: marginal entropies, one thread per sample row
+      const float inv_k = static_cast<float>(1.0 / static_cast<double>(K));  // torch multiplies by the fp32 reciprocal
+      if (tid < rows) {
+        float ent = 0.f;
+        for (int c = 0; c < Cl; ++c) {
+          const float* part = s_part + (tid * Cl + c) * groups;
+          float s = part[0];
+          for (int g = 1; g < groups; ++g) s += part[g];
+          ent += xlogx_f16(round_f16(s * inv_k));
+        }
+        marg[n0 + tid] = __float2half_rn(-round_f16(ent));
+      }
     }
   }
 }
-
-constexpr size_t PREP_SMEM_BUDGET = 100 * 1024;  // two blocks per SM
 
 int launch_epig_prepare(const float* mean, const float* var, const float* eps, const __half* probs_in, int64_t N, int64_t K,
                         int64_t Cl, __half* probs_out, __half* oper, __half* marg, cudaStream_t st) {
@@ -216,24 +244,29 @@ int launch_epig_prepare(const float* mean, const float* var, const float* eps, c
   if (K <= 0 || Cl <= 0 || K > 4096 || Cl > 4096) return BVLM_EINVAL;
   const bool from_noise = eps != nullptr;
   const int64_t Kp = pad64(K);
-  const bool need_nk = !from_noise || probs_out != nullptr;
-  const PrepLayout L = prep_layout(K, Cl, Kp, from_noise, need_nk, PREP_SMEM_BUDGET);
-  if (L.R <= 0) return BVLM_ENOTSUP;  // one row's K x Cl block does not fit shared memory
+  const PrepLayout L = prep_layout(Cl, Kp);
+  if (L.R <= 0) return BVLM_ENOTSUP;  // one row's Cl x Kp tile does not fit shared memory
   const unsigned grid = static_cast<unsigned>(ceil_div_i64(N, L.R));
   const bool cl16 = Cl <= 16;
-#define BVLM_PREP_LAUNCH(FN, C16)                                                                                       \
+  // vector width of the noise loads: every (sample, row) run starts at a multiple of Cl floats
+  const bool base16 = (reinterpret_cast<uintptr_t>(eps) & 15) == 0;
+  const int vec = !from_noise || !cl16 ? 1 : (base16 && Cl % 4 == 0) ? 4 : (base16 && Cl % 2 == 0) ? 2 : 1;
+#define BVLM_PREP_LAUNCH(FN, C16, VEC)                                                                                  \
   do {                                                                                                                  \
-    auto kfn = k_epig_prepare<FN, C16>;                                                                                 \
-    BVLM_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(PREP_SMEM_BUDGET))); \
-    kfn<<<grid, 256, L.bytes, st>>>(mean, var, eps, probs_in, N, static_cast<int>(K), static_cast<int>(Cl),             \
-                                    static_cast<int>(Kp), L, probs_out, oper, marg);                                    \
+    auto kfn = k_epig_prepare<FN, C16, VEC>;                                                                            \
+    if (L.bytes > 48 * 1024)                                                                                            \
+      BVLM_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(PREP_SMEM_MAX))); \
+    kfn<<<grid, PREP_THREADS, L.bytes, st>>>(mean, var, eps, probs_in, N, static_cast<int>(K), static_cast<int>(Cl),    \
+                                             static_cast<int>(Kp), L, probs_out, oper, marg);                           \
   } while (0)
   timing_begin(TAG_EPIG_PREPARE, st);
   if (from_noise) {
-    if (cl16) BVLM_PREP_LAUNCH(true, true);
-    else BVLM_PREP_LAUNCH(true, false);
+    if (cl16 && vec == 4) BVLM_PREP_LAUNCH(true, true, 4);
+    else if (cl16 && vec == 2) BVLM_PREP_LAUNCH(true, true, 2);
+    else if (cl16) BVLM_PREP_LAUNCH(true, true, 1);
+    else BVLM_PREP_LAUNCH(true, false, 1);
   } else {
-    BVLM_PREP_LAUNCH(false, false);
+    BVLM_PREP_LAUNCH(false, false, 1);
   }
 #undef BVLM_PREP_LAUNCH
   timing_end(TAG_EPIG_PREPARE, st);

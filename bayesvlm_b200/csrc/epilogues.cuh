@@ -306,15 +306,9 @@ struct EpiPredictive {
     const float* a;   // padded to a multiple of BN entries (zeros beyond C)
     const float* b;
     int use_tma;      // 0: row pitch not a multiple of 16 bytes -> direct stores
-    // optional fused statistics of the probit softmax (scripts/zeroshot.py:119-120): per (row, column tile) the maximum of
-    // z2 = log2(e) * mean / sqrt(1 + pi/8 var) and sum_j 2^(z2_j - max) over the tile's valid columns, so that the
-    // normalising pass (k_probit_normalize) reads mean / var ONCE instead of running its own max / sum passes
-    float2* rowstat;  // [N, n_tiles] (max, sum), or nullptr
-    int n_tiles;
   };
   struct State {
     float u, v, rm;
-    float pm, ps;  // running (max, sum) of the probit statistics over this thread's columns of the tile
   };
   static constexpr bool ALL_CHUNKS = false;
   static constexpr bool UNROLL_CHUNKS = true;
@@ -336,8 +330,6 @@ struct EpiPredictive {
       st.v = s * s * al * rE;
       st.rm = s * p.mean_unscale * p.esc[row] * rsqrtf(E);
     }
-    st.pm = -INFINITY;
-    st.ps = 0.f;
   }
   __device__ static void chunk(State& st, const Params& p, const EpiCtx& ctx, const TileCoord& tc, float (&v)[32], int c) {
     const int row = epi_row(ctx, tc);
@@ -356,29 +348,6 @@ struct EpiPredictive {
     }
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] *= st.rm;
-    if (p.rowstat != nullptr) {
-      constexpr float kPi8 = 0.39269908169872414f, kLog2e = 1.4426950408889634f;
-      const int n_valid = ctx.N - col0;
-      float z[32];
-      float cm = -INFINITY;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        z[j] = v[j] * (rsqrtf(fmaf(kPi8, var[j], 1.0f)) * kLog2e);
-        if (j >= n_valid) z[j] = -INFINITY;
-        cm = fmaxf(cm, z[j]);
-      }
-      if (cm > st.pm) {
-        st.ps *= fast_exp2(st.pm - cm);  // 0 * 2^(-inf) = 0 on the first chunk
-        st.pm = cm;
-      }
-      float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-      for (int j = 0; j < 32; j += 2) {
-        s0 += fast_exp2(z[j] - st.pm);
-        s1 += fast_exp2(z[j + 1] - st.pm);
-      }
-      st.ps += s0 + s1;
-    }
 #ifdef BVLM_DIAG
     if (p.use_tma == 2) return;  // (diagnostic build only: main loop without output traffic, BVLM_DEBUG_NOSTORE=1)
 #endif
@@ -407,15 +376,7 @@ struct EpiPredictive {
     store_row32_f32(p.mean + off, v, n_valid, al);
     store_row32_f32(p.var + off, var, n_valid, al);
   }
-  __device__ static void tile_end(State& st, const Params& p, const EpiCtx& ctx, const TileCoord& tc) {
-    if (p.rowstat == nullptr) return;
-    const int row = epi_row(ctx, tc);
-    if (ctx.n_warps > 4) {  // two warps share a row (one per column half): merge through shared memory
-      // (the statistics are only requested in the 4-warp configuration; see predictive.cu)
-      return;
-    }
-    if (row < ctx.M) p.rowstat[static_cast<int64_t>(row) * p.n_tiles + tc.n] = make_float2(st.pm, st.ps);
-  }
+  __device__ static void tile_end(State&, const Params&, const EpiCtx&, const TileCoord&) {}
   __device__ static void item_end(State&, const Params&, const EpiCtx&, const TileCoord&) {}
 };
 

@@ -675,6 +675,11 @@ __global__ void k_col_pow2_scale(const unsigned int* __restrict__ amax_bits, int
 }
 
 // ------------------------------------------------------------------------------------------------
+// P3: probs = softmax_j( mean_j / sqrt(1 + pi/8 var_j) )  (scripts/zeroshot.py:119-120).  One warp per row; rows of up to 1024
+// classes make ONE pass over HBM: every load of the row (32 + 32 per lane, 128-bit when the row pitch allows) is issued
+// before the first dependent instruction, so a warp keeps 8 KB in flight; z is evaluated with MUFU.RSQ / MUFU.EX2
+// (the precise division + sqrt of the first version serialised loads and arithmetic: 2.9 TB/s, bench r2 `with_probs`).
+template <bool VEC4>
 __global__ void __launch_bounds__(ROW_BLOCK)
 k_probit_softmax(const float* __restrict__ mean, const float* __restrict__ var, int64_t N, int64_t C, int64_t ld,
                  float* __restrict__ probs) {
@@ -687,37 +692,68 @@ k_probit_softmax(const float* __restrict__ mean, const float* __restrict__ var, 
   constexpr float kPi8 = 0.39269908169872414f;
   constexpr float kLog2e = 1.4426950408889634f;
   constexpr int CACHE = 32;  // rows up to 1024 classes stay in registers
-  float z[CACHE];
-  float zmax = -INFINITY;
   if (C <= CACHE * 32) {
+    float z[CACHE], w[CACHE];
+    if constexpr (VEC4) {  // lane owns columns 4 * (lane + 32 i) .. + 3
+#pragma unroll
+      for (int i = 0; i < CACHE / 4; ++i) {
+        const int64_t j = 4 * (lane + 32 * i);
+        const int64_t jc = j < C ? j : 0;  // C is a multiple of 4 here; clamped, not predicated: the loads hoist freely
+        const float4 a = __ldcs(reinterpret_cast<const float4*>(m + jc));
+        const float4 b = __ldcs(reinterpret_cast<const float4*>(v + jc));
+        z[4 * i] = a.x, z[4 * i + 1] = a.y, z[4 * i + 2] = a.z, z[4 * i + 3] = a.w;
+        w[4 * i] = b.x, w[4 * i + 1] = b.y, w[4 * i + 2] = b.z, w[4 * i + 3] = b.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < CACHE; ++i) {
+        const int64_t j = lane + 32 * i;
+        const int64_t jc = j < C ? j : 0;
+        z[i] = __ldcs(m + jc);
+        w[i] = __ldcs(v + jc);
+      }
+    }
+    asm volatile("" ::: "memory");  // every load of the row is issued before the first use
+    float zmax = -INFINITY;
 #pragma unroll
     for (int i = 0; i < CACHE; ++i) {
-      const int64_t j = lane + 32 * i;
-      z[i] = j < C ? m[j] / sqrtf(fmaf(kPi8, v[j], 1.0f)) * kLog2e : -INFINITY;
+      const int64_t j = VEC4 ? 4 * (lane + 32 * (i / 4)) + (i & 3) : lane + 32 * i;
+      z[i] = j < C ? z[i] * (rsqrtf(fmaf(kPi8, w[i], 1.0f)) * kLog2e) : -INFINITY;
       zmax = fmaxf(zmax, z[i]);
     }
     zmax = warp_max(zmax);
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < CACHE; ++i) {
-      z[i] = exp2f(z[i] - zmax);
+      z[i] = fast_exp2(z[i] - zmax);
       s += z[i];
     }
     s = warp_sum(s);
     const float inv = 1.0f / s;
+    if constexpr (VEC4) {
 #pragma unroll
-    for (int i = 0; i < CACHE; ++i) {
-      const int64_t j = lane + 32 * i;
-      if (j < C) p[j] = z[i] * inv;
+      for (int i = 0; i < CACHE / 4; ++i) {
+        const int64_t j = 4 * (lane + 32 * i);
+        if (j < C)
+          __stcs(reinterpret_cast<float4*>(p + j),
+                 make_float4(z[4 * i] * inv, z[4 * i + 1] * inv, z[4 * i + 2] * inv, z[4 * i + 3] * inv));
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < CACHE; ++i) {
+        const int64_t j = lane + 32 * i;
+        if (j < C) __stcs(p + j, z[i] * inv);
+      }
     }
   } else {
-    for (int64_t j = lane; j < C; j += 32) zmax = fmaxf(zmax, m[j] / sqrtf(fmaf(kPi8, v[j], 1.0f)) * kLog2e);
+    float zmax = -INFINITY;
+    for (int64_t j = lane; j < C; j += 32) zmax = fmaxf(zmax, m[j] * (rsqrtf(fmaf(kPi8, v[j], 1.0f)) * kLog2e));
     zmax = warp_max(zmax);
     float s = 0.f;
-    for (int64_t j = lane; j < C; j += 32) s += exp2f(m[j] / sqrtf(fmaf(kPi8, v[j], 1.0f)) * kLog2e - zmax);
+    for (int64_t j = lane; j < C; j += 32) s += fast_exp2(m[j] * (rsqrtf(fmaf(kPi8, v[j], 1.0f)) * kLog2e) - zmax);
     s = warp_sum(s);
     const float inv = 1.0f / s;
-    for (int64_t j = lane; j < C; j += 32) p[j] = exp2f(m[j] / sqrtf(fmaf(kPi8, v[j], 1.0f)) * kLog2e - zmax) * inv;
+    for (int64_t j = lane; j < C; j += 32) p[j] = fast_exp2(m[j] * (rsqrtf(fmaf(kPi8, v[j], 1.0f)) * kLog2e) - zmax) * inv;
   }
 }
 
@@ -914,7 +950,12 @@ int launch_col_pow2_scale(const float* x, int64_t n, int64_t d, int64_t ld, int 
 int launch_probit_softmax(const float* mean, const float* var, int64_t N, int64_t C, int64_t ld, float* probs,
                           cudaStream_t st) {
   if (N <= 0 || C <= 0) return BVLM_OK;
-  k_probit_softmax<<<row_grid(N), ROW_BLOCK, 0, st>>>(mean, var, N, C, ld, probs);
+  const auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  const bool vec4 = C % 4 == 0 && ld % 4 == 0 && al16(mean) && al16(var) && al16(probs);
+  timing_begin(TAG_PROBIT, st);
+  if (vec4) k_probit_softmax<true><<<row_grid(N), ROW_BLOCK, 0, st>>>(mean, var, N, C, ld, probs);
+  else k_probit_softmax<false><<<row_grid(N), ROW_BLOCK, 0, st>>>(mean, var, N, C, ld, probs);
+  timing_end(TAG_PROBIT, st);
   count_launch();
   BVLM_CUDA_TRY(cudaGetLastError());
   return BVLM_OK;

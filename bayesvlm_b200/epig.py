@@ -26,10 +26,11 @@ def _kernel_path_ok(probs: torch.Tensor) -> bool:
 
 
 def _prepare_fits(k: int, cl: int, from_noise: bool) -> bool:
-    """One sample row (K x Cl) of the fused kernel's staging must fit its shared-memory budget."""
+    """One sample row's [Cl, Kp] fp16 operand tile (+ its partial sums and mean / std) must fit the shared-memory budget of
+    the fused kernel (csrc/epig.cu: prep_row_bytes / PREP_SMEM_MAX)."""
+    del from_noise  # the noise is read straight into registers: both variants stage the same tile
     kp = int(lib.bvlm_epig_operand_k(k))
-    per_row = cl * kp * 2 + (k * cl * 4 + 8 * cl if from_noise else k * cl * 2)
-    return per_row + 4 * k + 64 <= _PREP_SMEM
+    return cl * kp * 2 + cl * (kp // 64) * 4 + cl * 8 <= _PREP_SMEM
 
 
 def _joint_fused_ok(k: int, cl: int, chunk_size: int) -> bool:
