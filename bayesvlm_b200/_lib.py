@@ -68,8 +68,10 @@ SIGNATURES = {
     ),
     "bvlm_probit_softmax": (c_int, [_P, _P, _I, _I, _I, _P, _P]),
     "bvlm_epig_operand_k": (c_int, [_I]),
+    "bvlm_epig_prepare_supported": (c_int, [_I, _I, c_int]),
     "bvlm_epig_prepare_from_noise": (c_int, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
     "bvlm_epig_prepare_from_probs": (c_int, [_P, _I, _I, _I, _P, _P, _P]),
+    "bvlm_epig_prepare_pair_from_noise": (c_int, [_P, _P, _P, _I, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _P]),
     "bvlm_epig_joint_entropy_operands": (c_int, [_P, _I, _P, _I, _I, _I, _I, _P, _P]),
     "bvlm_epig_sample_probs": (c_int, [_P, _P, _P, _I, _I, _I, _P, _P]),
     "bvlm_epig_marginal_entropy_f16": (c_int, [_P, _I, _I, _I, _P, _P]),

@@ -99,14 +99,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug must trap instead of hanging the GPU (≈ 2–3 s at 1.3–1.9 GHz).
+template <bool BACKOFF = false>
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   // The poll loop runs next to the epilogue warps of the same scheduler for the whole kernel (a producer / MMA thread of an
   // epilogue-bound kernel waits almost all the time): every instruction in it is an issue slot taken from them.  ncu
   // (profiles/r1e EPIG capture) attributed ~12 % of all issued instructions to the previous clock64()-based timeout
   // check, so the bound is an iteration counter (each failed try_wait already sleeps in hardware for its time hint).
+  // BACKOFF: waits that are off the critical path (a producer waiting for a free stage, the MMA thread waiting for a drained
+  // accumulator) sleep 128 ns between polls after the first few -- one poll per ~250 cycles instead of one per ~60.
   if (mbar_try_wait(bar, parity)) return;
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
+    if (BACKOFF && spins >= 4) __nanosleep(128);
     if (++spins == (1u << 26)) {  // >= 64 Mi failed polls of >= ~60 cycles each: seconds, i.e. a protocol bug
       printf("bvlm: mbarrier wait timed out (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
       __trap();

@@ -38,92 +38,192 @@ __device__ __forceinline__ float xlogx_f16(float x) {
 // zero padded along K), marg [N] fp16 marginal entropies with torch's CUDA rounding points (mean over K = fp32 sum times
 // 1/K -> fp16; xlogy -> fp16; sum over Cl in fp32 -> fp16; negate).
 //
-// Layout of the work (second version; the first staged the noise of 15 rows in 100 KB of shared memory with 4-byte cp.async,
-// two 256-thread blocks per SM and strictly serial fetch / compute / store phases: 0.87 TB/s, bench r2 `epig.reductions`):
-//   * a block is 128 threads = 128 consecutive MC samples k, and owns R (1..8) sample rows; it needs only the R*Cl*Kp fp16
-//     operand tile in shared memory (10 KB at Cl = 10, K = 100), so 10+ blocks are resident per SM and the fetch of one block
-//     overlaps the arithmetic and the stores of the others;
-//   * thread k reads ITS Cl noise values of a row straight from global memory into registers (the R rows of a block are one
-//     contiguous run per sample, 64-/128-bit loads when Cl is even / a multiple of 4; the next row is fetched before the current
-//     one is evaluated), so no noise is staged anywhere;
-//   * the probabilities go to the shared tile in the OPERAND layout [row][class][k] (lanes along k: conflict free); the tile is
-//     the block's contiguous slice of `oper` and leaves with 128-bit stores, and the same 128-bit reads feed the sum over K of
-//     the marginal entropy (8 values per thread, 3 shuffles, fixed order: deterministic).
+// Layout of the work (third version.  v1 staged 15 rows in 100 KB with 4-byte cp.async, two 256-thread blocks per SM:
+// 0.87 TB/s.  v2 had every thread read its own sample's noise from global memory: 32 cache lines per warp instruction, the
+// L1 tag stage at 64 % and the loads latency bound, 39 us for 66 MB; profiles/r2_*):
+//   * a block is 128 threads = 128 consecutive MC samples k and owns R = 4 sample rows (28 KB of shared memory at Cl = 10,
+//     K = 100: 7 blocks per SM, the fetch of one block overlaps the arithmetic and the stores of the others);
+//   * the block's noise is ONE contiguous run of R*Cl floats per sample: cp.async with consecutive threads on consecutive
+//     16- / 8- / 4-byte pieces (coalesced), all of the block's bytes in flight at once, into [k][R*Cl + V] rows whose stride
+//     makes the per-sample vector reads below bank-conflict free;
+//   * thread k evaluates the softmax of its sample for each row in registers (compile-time class count for Cl <= 16) and
+//     writes the fp16 probabilities to the shared tile in the OPERAND layout [row][class][k] (lanes along k: conflict free);
+//   * the tile is the block's contiguous slice of `oper` and leaves with 128-bit stores; the same 128-bit reads feed the sum
+//     over K of the marginal entropy (8 values per thread, 3 shuffles, fixed order: deterministic).
 // The softmax follows torch's softmax_warp_forward for rows of <= 16 classes (sum in the 16-lane butterfly order, expf,
 // true division), so the fp16 probabilities are bit-identical to the reference's on the same device.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int PREP_THREADS = 128;
-constexpr size_t PREP_SMEM_TARGET = 12 * 1024;  // per block when more than one row fits: >= 10 resident blocks per SM
-constexpr size_t PREP_SMEM_MAX = 100 * 1024;    // a single row's tile may take up to this much
+constexpr int PREP_ROWS = 4;                    // rows per block (compile-time class counts); 4 | R * Cl: 16-byte aligned runs
+constexpr size_t PREP_SMEM_MAX = 100 * 1024;    // a block may take up to this much
 
 struct PrepLayout {
-  int R;
-  size_t off_part, off_ms, bytes;
+  int R, estride;
+  size_t off_part, off_ms, off_eps, bytes;
 };
 
-inline size_t prep_row_bytes(int64_t Cl, int64_t Kp) {
-  return static_cast<size_t>(Cl * Kp * 2) + static_cast<size_t>(Cl) * (Kp / 64) * 4 + static_cast<size_t>(Cl) * 8;
-}
+// noise vector width (floats) of the per-sample reads for a compile-time class count
+constexpr int prep_vec(int cl) { return cl % 4 == 0 ? 4 : cl % 2 == 0 ? 2 : 1; }
 
-inline PrepLayout prep_layout(int64_t Cl, int64_t Kp) {
+inline PrepLayout prep_layout_for(int64_t R, int64_t K, int64_t Cl, int64_t Kp, bool from_noise) {
   PrepLayout L{};
-  const size_t per_row = prep_row_bytes(Cl, Kp);
-  int R = static_cast<int>(PREP_SMEM_TARGET / per_row);
-  if (R > 8) R = 8;
-  if (R < 1) R = per_row <= PREP_SMEM_MAX ? 1 : 0;
-  L.R = R;
-  if (R <= 0) return L;
+  L.R = static_cast<int>(R);
+  // [k][estride] floats.  Cl <= 16 (R = 4): even class counts use estride = 4 Cl + 4 (rows 16-byte aligned for 16-byte
+  // cp.async; the 128-bit reads of a quarter warp are conflict free, the 64-bit reads of Cl = 2 mod 4 two-way), odd ones
+  // 4 Cl + 1 (scalar reads, conflict free).  Generic path: odd stride, scalar reads.
+  L.estride = Cl <= 16 ? static_cast<int>(R * Cl + (Cl % 2 == 0 ? 4 : 1)) : static_cast<int>((R * Cl) | 1);
   L.off_part = static_cast<size_t>(R) * Cl * Kp * 2;                       // float [R*Cl][Kp/64] partial sums over K
   L.off_ms = L.off_part + static_cast<size_t>(R) * Cl * (Kp / 64) * 4;     // float mean[R*Cl], std[R*Cl]
-  L.bytes = L.off_ms + static_cast<size_t>(R) * Cl * 8;
+  L.off_eps = (L.off_ms + static_cast<size_t>(R) * Cl * 8 + 15) & ~static_cast<size_t>(15);  // float [K][estride] noise
+  L.bytes = L.off_eps + (from_noise ? static_cast<size_t>(K) * L.estride * 4 : 0);
   return L;
 }
 
-// Cl noise values of one (sample, row) into registers; VEC = floats per load (alignment guaranteed by the caller)
-template <int VEC>
-__device__ __forceinline__ void load_noise16(float (&e)[16], const float* __restrict__ src, int Cl) {
-  if constexpr (VEC == 4) {
+inline PrepLayout prep_layout(int64_t K, int64_t Cl, int64_t Kp, bool from_noise) {
+  if (Cl <= 16) {
+    const PrepLayout L = prep_layout_for(PREP_ROWS, K, Cl, Kp, from_noise);
+    if (L.bytes <= PREP_SMEM_MAX) return L;
+  }
+  PrepLayout L = prep_layout_for(1, K, Cl, Kp, from_noise);
+  if (Cl <= 16) L.estride = static_cast<int>(Cl | 1);  // (generic kernel: scalar reads)
+  if (Cl <= 16) L.bytes = L.off_eps + (from_noise ? static_cast<size_t>(K) * L.estride * 4 : 0);
+  if (L.bytes > PREP_SMEM_MAX) L.R = 0;
+  return L;
+}
+
+__device__ __forceinline__ void cp_async_4(uint32_t smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_8(uint32_t smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// CL floats from shared memory with V-float vector loads (the address is V-float aligned by construction)
+template <int CL, int V>
+__device__ __forceinline__ void load_vec(float (&e)[CL], const float* __restrict__ ep) {
+  if constexpr (V == 4) {
 #pragma unroll
-    for (int c = 0; c < 16; c += 4)
-      if (c < Cl) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(src + c));
-        e[c] = v.x, e[c + 1] = v.y, e[c + 2] = v.z, e[c + 3] = v.w;
-      }
-  } else if constexpr (VEC == 2) {
+    for (int c = 0; c < CL; c += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(ep + c);
+      e[c] = v.x, e[c + 1] = v.y, e[c + 2] = v.z, e[c + 3] = v.w;
+    }
+  } else if constexpr (V == 2) {
 #pragma unroll
-    for (int c = 0; c < 16; c += 2)
-      if (c < Cl) {
-        const float2 v = __ldg(reinterpret_cast<const float2*>(src + c));
-        e[c] = v.x, e[c + 1] = v.y;
-      }
+    for (int c = 0; c < CL; c += 2) {
+      const float2 v = *reinterpret_cast<const float2*>(ep + c);
+      e[c] = v.x, e[c + 1] = v.y;
+    }
   } else {
 #pragma unroll
-    for (int c = 0; c < 16; ++c)
-      if (c < Cl) e[c] = __ldg(src + c);
+    for (int c = 0; c < CL; ++c) e[c] = ep[c];
   }
 }
 
-template <bool FROM_NOISE, bool CL16, int VEC>
+// softmax(e * std + mean) of one (sample, row) -> fp16, written into the operand tile (stride Kp along the class) and, if
+// requested, to the [N, K, Cl] probabilities.  Arithmetic = torch's: randn * std + mean with two roundings, expf, the sum in
+// softmax_warp_forward's butterfly order over 16 lanes (missing classes add exact zeros), true division -- evaluated as
+// q = z * r, q' = fma(fma(-q, s, z), r, q) with r = RN(1 / s): the correctly rounded quotient (Markstein) in 3 instructions
+// per class instead of the ~12 of the generic division sequence with its slow-path check.
+template <int CL, bool WANT_PROBS>
+__device__ __forceinline__ void softmax_row_f16(const float* __restrict__ ep, const float* __restrict__ m, const float* __restrict__ sd,
+                                                __half* __restrict__ s_dst, int Kp, __half* __restrict__ g_dst) {
+  constexpr int V = prep_vec(CL);
+  float e[CL], mm[CL], ss[CL];
+  load_vec<CL, V>(e, ep);
+  load_vec<CL, V>(mm, m);   // (row n of the block starts at n * CL floats in all three arrays: same alignment)
+  load_vec<CL, V>(ss, sd);
+  float z[16];
+  float zmax = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < CL; ++c) {
+    z[c] = __fadd_rn(__fmul_rn(e[c], ss[c]), mm[c]);
+    zmax = fmaxf(zmax, z[c]);
+  }
+#pragma unroll
+  for (int c = 0; c < 16; ++c) z[c] = c < CL ? expf(z[c] - zmax) : 0.f;
+  const float t0 = z[0] + z[8], t1 = z[1] + z[9], t2 = z[2] + z[10], t3 = z[3] + z[11], t4 = z[4] + z[12],
+              t5 = z[5] + z[13], t6 = z[6] + z[14], t7 = z[7] + z[15];
+  const float u0 = t0 + t4, u1 = t1 + t5, u2 = t2 + t6, u3 = t3 + t7;
+  const float zsum = (u0 + u2) + (u1 + u3);  // in [1, 16]
+  const float r = __frcp_rn(zsum);
+#pragma unroll
+  for (int c = 0; c < CL; ++c) {
+    const float q = __fmul_rn(z[c], r);
+    const __half h = __float2half_rn(__fmaf_rn(__fmaf_rn(-q, zsum, z[c]), r, q));
+    s_dst[c * Kp] = h;
+    if constexpr (WANT_PROBS) g_dst[c] = h;
+  }
+}
+
+// CL > 0: compile-time class count (<= 16), R = PREP_ROWS.  CL == 0: any class count, one row per block, three sweeps.
+// One side (pool or target set) of a prepare launch.
+struct PrepSide {
+  const float* mean;
+  const float* var;
+  const float* eps;
+  const __half* probs_in;
+  int64_t N;
+  __half* probs_out;
+  __half* oper;
+  __half* marg;
+  int piece;  // floats per cp.async of the noise fetch (4, 2 or 1: alignment of this side's runs)
+};
+
+// CL > 0: compile-time class count (<= 16), R = PREP_ROWS.  CL == 0: any class count, one row per block, three sweeps.
+// Blocks [0, blocks0) work on side a, the rest on side b (EPIG prepares the target set and a pool chunk in ONE launch).
+template <bool FROM_NOISE, int CL>
 __global__ void __launch_bounds__(PREP_THREADS)
-k_epig_prepare(const float* __restrict__ mean, const float* __restrict__ var, const float* __restrict__ eps,
-               const __half* __restrict__ probs_in, int64_t N, int K, int Cl, int Kp, const PrepLayout L,
-               __half* __restrict__ probs_out, __half* __restrict__ oper, __half* __restrict__ marg) {
+k_epig_prepare(const PrepSide sa, const PrepSide sb, const unsigned blocks0, int K, int Cl, int Kp, const PrepLayout L) {
   extern __shared__ __align__(16) uint8_t ps[];
+  const bool second = blockIdx.x >= blocks0;
+  const float* __restrict__ mean = second ? sb.mean : sa.mean;
+  const float* __restrict__ var = second ? sb.var : sa.var;
+  const float* __restrict__ eps = second ? sb.eps : sa.eps;
+  const __half* __restrict__ probs_in = second ? sb.probs_in : sa.probs_in;
+  const int64_t N = second ? sb.N : sa.N;
+  __half* __restrict__ probs_out = second ? sb.probs_out : sa.probs_out;
+  __half* __restrict__ oper = second ? sb.oper : sa.oper;
+  __half* __restrict__ marg = second ? sb.marg : sa.marg;
+  const int piece = second ? sb.piece : sa.piece;
   __half* s_op = reinterpret_cast<__half*>(ps);                // [R][Cl][Kp]
   float* s_part = reinterpret_cast<float*>(ps + L.off_part);   // [R*Cl][Kp/64]
   float* s_mean = reinterpret_cast<float*>(ps + L.off_ms);     // [R*Cl]
   float* s_std = s_mean + L.R * Cl;
+  float* s_eps = reinterpret_cast<float*>(ps + L.off_eps);     // [K][estride]: sample k's noise of the block's rows
   const int tid = threadIdx.x, lane = tid & 31;
-  const int64_t n0 = static_cast<int64_t>(blockIdx.x) * L.R;
+  const int64_t n0 = static_cast<int64_t>(blockIdx.x - (second ? blocks0 : 0u)) * L.R;
   const int rows = static_cast<int>(N - n0 < L.R ? N - n0 : L.R);
   const int seg = rows * Cl;
   const __half hzero = __float2half_rn(0.f);
 
   if constexpr (FROM_NOISE) {
+    const float* base = eps + n0 * Cl;
+    const int64_t kstride = N * Cl;
+    const uint32_t dst0 = smem_u32(s_eps);
+    // piece = floats per cp.async (4, 2 or 1), chosen by the host from the alignment of the runs; the tail block's shorter
+    // run may not be a multiple of it
+    const int pw = (seg % piece) == 0 ? piece : 1;
+    const int pieces = seg / pw, total = pieces * K;
+    const float inv_pieces = 1.0f / static_cast<float>(pieces);
+    for (int i = tid; i < total; i += PREP_THREADS) {
+      // k = i / pieces without an integer division: (i + 0.5) / pieces is at least 0.5 / pieces away from an integer and
+      // the fp32 error is < 1e-3 for i < 2^17
+      const int k = __float2int_rz((static_cast<float>(i) + 0.5f) * inv_pieces), j = (i - k * pieces) * pw;
+      const uint32_t d = dst0 + 4u * static_cast<uint32_t>(k * L.estride + j);
+      const float* g = base + k * kstride + j;
+      if (pw == 4) cp_async_16(d, g);
+      else if (pw == 2) cp_async_8(d, g);
+      else cp_async_4(d, g);
+    }
     for (int j = tid; j < seg; j += PREP_THREADS) {
       s_mean[j] = mean[n0 * Cl + j];
       s_std[j] = sqrtf(var[n0 * Cl + j]);
     }
+    cp_async_wait_all();
     __syncthreads();
   }
 
@@ -133,52 +233,32 @@ k_epig_prepare(const float* __restrict__ mean, const float* __restrict__ var, co
       for (int i = 0; i < seg; ++i) s_op[i * Kp + k] = hzero;
       continue;
     }
-    if constexpr (FROM_NOISE && CL16) {
-      const float* src = eps + (static_cast<int64_t>(k) * N + n0) * Cl;
-      float e[16], en[16];
-      load_noise16<VEC>(e, src, Cl);
-      for (int n = 0; n < rows; ++n) {
-        if (n + 1 < rows) load_noise16<VEC>(en, src + (n + 1) * Cl, Cl);  // next row in flight during this row's math
-        const float* m = s_mean + n * Cl;
-        const float* sd = s_std + n * Cl;
-        float z[16];
-        float zmax = -INFINITY;
+    if constexpr (FROM_NOISE && CL > 0) {
+      const float* ek = s_eps + k * L.estride;
+      if (probs_out != nullptr) {  // (E0 alone, vlm.py:116-123: the [N, K, Cl] probabilities are an output)
+        for (int n = 0; n < rows; ++n)
+          softmax_row_f16<CL, true>(ek + n * CL, s_mean + n * CL, s_std + n * CL, s_op + n * CL * Kp + k, Kp,
+                                    probs_out + ((n0 + n) * K + k) * CL);
+      } else if (rows == PREP_ROWS) {
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          z[c] = c < Cl ? __fadd_rn(__fmul_rn(e[c], sd[c]), m[c]) : -INFINITY;  // torch: randn * std + mean, two roundings
-          zmax = fmaxf(zmax, z[c]);
-        }
-#pragma unroll
-        for (int c = 0; c < 16; ++c) z[c] = c < Cl ? expf(z[c] - zmax) : 0.f;
-        // torch softmax_warp_forward: butterfly sum over the 16 lanes of a row (xor 8, 4, 2, 1)
-        const float t0 = z[0] + z[8], t1 = z[1] + z[9], t2 = z[2] + z[10], t3 = z[3] + z[11], t4 = z[4] + z[12],
-                    t5 = z[5] + z[13], t6 = z[6] + z[14], t7 = z[7] + z[15];
-        const float u0 = t0 + t4, u1 = t1 + t5, u2 = t2 + t6, u3 = t3 + t7;
-        const float zsum = (u0 + u2) + (u1 + u3);
-        __half* dst_nk = probs_out != nullptr ? probs_out + ((n0 + n) * K + k) * Cl : nullptr;
-#pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          if (c < Cl) {
-            const __half h = __float2half_rn(z[c] / zsum);
-            s_op[(n * Cl + c) * Kp + k] = h;
-            if (dst_nk != nullptr) dst_nk[c] = h;
-          }
-        }
-#pragma unroll
-        for (int c = 0; c < 16; ++c) e[c] = en[c];
+        for (int n = 0; n < PREP_ROWS; ++n)
+          softmax_row_f16<CL, false>(ek + n * CL, s_mean + n * CL, s_std + n * CL, s_op + n * CL * Kp + k, Kp, nullptr);
+      } else {
+        for (int n = 0; n < rows; ++n)
+          softmax_row_f16<CL, false>(ek + n * CL, s_mean + n * CL, s_std + n * CL, s_op + n * CL * Kp + k, Kp, nullptr);
       }
     } else if constexpr (FROM_NOISE) {
       for (int n = 0; n < rows; ++n) {
-        const float* e = eps + (static_cast<int64_t>(k) * N + n0 + n) * Cl;  // re-read from L1 in the three sweeps
+        const float* e = s_eps + k * L.estride + n * Cl;
         const float* m = s_mean + n * Cl;
         const float* sd = s_std + n * Cl;
         float zmax = -INFINITY;
-        for (int c = 0; c < Cl; ++c) zmax = fmaxf(zmax, __fadd_rn(__fmul_rn(__ldg(e + c), sd[c]), m[c]));
+        for (int c = 0; c < Cl; ++c) zmax = fmaxf(zmax, __fadd_rn(__fmul_rn(e[c], sd[c]), m[c]));
         float zsum = 0.f;
-        for (int c = 0; c < Cl; ++c) zsum += expf(__fadd_rn(__fmul_rn(__ldg(e + c), sd[c]), m[c]) - zmax);
+        for (int c = 0; c < Cl; ++c) zsum += expf(__fadd_rn(__fmul_rn(e[c], sd[c]), m[c]) - zmax);
         __half* dst_nk = probs_out != nullptr ? probs_out + ((n0 + n) * K + k) * Cl : nullptr;
         for (int c = 0; c < Cl; ++c) {
-          const __half h = __float2half_rn(expf(__fadd_rn(__fmul_rn(__ldg(e + c), sd[c]), m[c]) - zmax) / zsum);
+          const __half h = __float2half_rn(expf(__fadd_rn(__fmul_rn(e[c], sd[c]), m[c]) - zmax) / zsum);
           s_op[(n * Cl + c) * Kp + k] = h;
           if (dst_nk != nullptr) dst_nk[c] = h;
         }
@@ -238,38 +318,65 @@ k_epig_prepare(const float* __restrict__ mean, const float* __restrict__ var, co
   }
 }
 
-int launch_epig_prepare(const float* mean, const float* var, const float* eps, const __half* probs_in, int64_t N, int64_t K,
-                        int64_t Cl, __half* probs_out, __half* oper, __half* marg, cudaStream_t st) {
-  if (N <= 0) return BVLM_OK;
-  if (K <= 0 || Cl <= 0 || K > 4096 || Cl > 4096) return BVLM_EINVAL;
-  const bool from_noise = eps != nullptr;
-  const int64_t Kp = pad64(K);
-  const PrepLayout L = prep_layout(Cl, Kp);
-  if (L.R <= 0) return BVLM_ENOTSUP;  // one row's Cl x Kp tile does not fit shared memory
-  const unsigned grid = static_cast<unsigned>(ceil_div_i64(N, L.R));
-  const bool cl16 = Cl <= 16;
-  // vector width of the noise loads: every (sample, row) run starts at a multiple of Cl floats
-  const bool base16 = (reinterpret_cast<uintptr_t>(eps) & 15) == 0;
-  const int vec = !from_noise || !cl16 ? 1 : (base16 && Cl % 4 == 0) ? 4 : (base16 && Cl % 2 == 0) ? 2 : 1;
-#define BVLM_PREP_LAUNCH(FN, C16, VEC)                                                                                  \
-  do {                                                                                                                  \
-    auto kfn = k_epig_prepare<FN, C16, VEC>;                                                                            \
-    if (L.bytes > 48 * 1024)                                                                                            \
-      BVLM_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(PREP_SMEM_MAX))); \
-    kfn<<<grid, PREP_THREADS, L.bytes, st>>>(mean, var, eps, probs_in, N, static_cast<int>(K), static_cast<int>(Cl),    \
-                                             static_cast<int>(Kp), L, probs_out, oper, marg);                           \
-  } while (0)
-  timing_begin(TAG_EPIG_PREPARE, st);
-  if (from_noise) {
-    if (cl16 && vec == 4) BVLM_PREP_LAUNCH(true, true, 4);
-    else if (cl16 && vec == 2) BVLM_PREP_LAUNCH(true, true, 2);
-    else if (cl16) BVLM_PREP_LAUNCH(true, true, 1);
-    else BVLM_PREP_LAUNCH(true, false, 1);
-  } else {
-    BVLM_PREP_LAUNCH(false, false, 1);
+template <bool FN, int CL>
+int launch_prepare_variant(unsigned grid, unsigned blocks0, const PrepLayout& L, const PrepSide& sa, const PrepSide& sb, int K,
+                           int Cl, int Kp, cudaStream_t st) {
+  auto kfn = k_epig_prepare<FN, CL>;
+  if (L.bytes > 48 * 1024)
+    BVLM_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(PREP_SMEM_MAX)));
+  kfn<<<grid, PREP_THREADS, L.bytes, st>>>(sa, sb, blocks0, K, Cl, Kp, L);
+  return BVLM_OK;
+}
+
+// cp.async piece (floats): every (sample, block) run must start on a piece boundary in global AND shared memory
+inline int prep_piece(const float* eps, int64_t N, int64_t Cl, bool fixed_cl) {
+  if (!fixed_cl || eps == nullptr) return 1;
+  const uintptr_t a = reinterpret_cast<uintptr_t>(eps);
+  if (Cl % 2 == 0 && (a & 15) == 0 && (N * Cl) % 4 == 0) return 4;  // (shared rows of even class counts are 16-byte aligned)
+  if (Cl % 2 == 0 && (a & 7) == 0) return 2;
+  return 1;
+}
+
+// one or two sides (sb.N == 0: one) sharing K and Cl, all from noise or all from probabilities
+int launch_epig_prepare(PrepSide sa, PrepSide sb, int64_t K, int64_t Cl, cudaStream_t st) {
+  if (sa.N <= 0 && sb.N <= 0) return BVLM_OK;
+  if (sa.N <= 0) {
+    sa = sb;
+    sb.N = 0;
   }
-#undef BVLM_PREP_LAUNCH
+  if (K <= 0 || Cl <= 0 || K > 4096 || Cl > 4096) return BVLM_EINVAL;
+  const bool from_noise = sa.eps != nullptr;
+  if (sb.N > 0 && (sb.eps != nullptr) != from_noise) return BVLM_EINVAL;
+  const int64_t Kp = pad64(K);
+  const PrepLayout L = prep_layout(K, Cl, Kp, from_noise);
+  if (L.R <= 0) return BVLM_ENOTSUP;  // one row's tiles do not fit shared memory
+  const unsigned blocks0 = static_cast<unsigned>(ceil_div_i64(sa.N, L.R));
+  const unsigned grid = blocks0 + static_cast<unsigned>(sb.N > 0 ? ceil_div_i64(sb.N, L.R) : 0);
+  const bool fixed_cl = from_noise && Cl <= 16 && L.R == PREP_ROWS;
+  sa.piece = prep_piece(sa.eps, sa.N, Cl, fixed_cl);
+  sb.piece = prep_piece(sb.eps, sb.N, Cl, fixed_cl);
+  const int Ki = static_cast<int>(K), Cli = static_cast<int>(Cl), Kpi = static_cast<int>(Kp);
+  int rc = BVLM_OK;
+#define BVLM_PREP_CL(C)                                                                              \
+  case C:                                                                                            \
+    rc = launch_prepare_variant<true, C>(grid, blocks0, L, sa, sb, Ki, Cli, Kpi, st);                \
+    break
+  timing_begin(TAG_EPIG_PREPARE, st);
+  if (fixed_cl) {
+    switch (Cli) {
+      BVLM_PREP_CL(1); BVLM_PREP_CL(2); BVLM_PREP_CL(3); BVLM_PREP_CL(4); BVLM_PREP_CL(5); BVLM_PREP_CL(6); BVLM_PREP_CL(7);
+      BVLM_PREP_CL(8); BVLM_PREP_CL(9); BVLM_PREP_CL(10); BVLM_PREP_CL(11); BVLM_PREP_CL(12); BVLM_PREP_CL(13);
+      BVLM_PREP_CL(14); BVLM_PREP_CL(15); BVLM_PREP_CL(16);
+      default: rc = BVLM_EINVAL;
+    }
+  } else if (from_noise) {
+    rc = launch_prepare_variant<true, 0>(grid, blocks0, L, sa, sb, Ki, Cli, Kpi, st);
+  } else {
+    rc = launch_prepare_variant<false, 0>(grid, blocks0, L, sa, sb, Ki, Cli, Kpi, st);
+  }
+#undef BVLM_PREP_CL
   timing_end(TAG_EPIG_PREPARE, st);
+  if (rc) return rc;
   count_launch();
   BVLM_CUDA_TRY(cudaGetLastError());
   return BVLM_OK;
@@ -299,7 +406,7 @@ struct EpiEpigJoint {
     bool valid;
     bool leader;
     int64_t p;
-    int cur_chunk;
+    int cur_chunk;  // tiles consumed of the current column chunk
   };
   static constexpr bool ALL_CHUNKS = false;
   static constexpr bool UNROLL_CHUNKS = false;
@@ -334,14 +441,14 @@ struct EpiEpigJoint {
     st.leader = st.valid && (r - pl * p.Cl == 0) && ctx.wid < 4;
     st.chunk_acc = 0.f;
     st.hj = 0.f;
-    st.cur_chunk = 0;
+    st.cur_chunk = tc.n % p.tiles_per_chunk;  // tiles of the current column chunk seen so far (a panel starts at tc.n)
   }
-  __device__ static void tile_begin(State& st, const Params& p, const EpiCtx& ctx, const TileCoord& tc) {
-    const int ch = tc.n / p.tiles_per_chunk;
-    if (ch != st.cur_chunk) {
+  __device__ static void tile_begin(State& st, const Params& p, const EpiCtx& ctx, const TileCoord&) {
+    if (st.cur_chunk == p.tiles_per_chunk) {  // (a counter, not tc.n / tiles_per_chunk: no division per tile)
       flush(st, p, ctx);
-      st.cur_chunk = ch;
+      st.cur_chunk = 0;
     }
+    ++st.cur_chunk;
   }
   __device__ static void chunk(State& st, const Params& p, const EpiCtx&, const TileCoord&, float (&v)[32], int) {
     // columns beyond N are TMA zero fill: j = 0 -> 0 * log 0 = NaN, which the NaN-suppressing min below turns into 0
@@ -374,19 +481,37 @@ extern "C" {
 
 int bvlm_epig_operand_k(int64_t K) { return static_cast<int>(pad64(K)); }
 
+int bvlm_epig_prepare_supported(int64_t K, int64_t Cl, int from_noise) {
+  if (K <= 0 || Cl <= 0 || K > 4096 || Cl > 4096) return 0;
+  return prep_layout(K, Cl, pad64(K), from_noise != 0).R > 0 ? 1 : 0;
+}
+
 int bvlm_epig_prepare_from_noise(const float* mean, const float* var, const float* eps, int64_t N, int64_t K, int64_t Cl,
                                  void* probs16, void* oper16, void* marg16, void* stream) {
   if (mean == nullptr || var == nullptr || eps == nullptr) return BVLM_EINVAL;
   if (probs16 == nullptr && oper16 == nullptr && marg16 == nullptr) return BVLM_EINVAL;
-  return launch_epig_prepare(mean, var, eps, nullptr, N, K, Cl, static_cast<__half*>(probs16), static_cast<__half*>(oper16),
-                             static_cast<__half*>(marg16), static_cast<cudaStream_t>(stream));
+  const PrepSide sa{mean, var, eps, nullptr, N, static_cast<__half*>(probs16), static_cast<__half*>(oper16),
+                    static_cast<__half*>(marg16), 1};
+  return launch_epig_prepare(sa, PrepSide{}, K, Cl, static_cast<cudaStream_t>(stream));
+}
+
+int bvlm_epig_prepare_pair_from_noise(const float* mean_a, const float* var_a, const float* eps_a, int64_t Na, void* oper_a,
+                                      void* marg_a, const float* mean_b, const float* var_b, const float* eps_b, int64_t Nb,
+                                      void* oper_b, void* marg_b, int64_t K, int64_t Cl, void* stream) {
+  if (mean_a == nullptr || var_a == nullptr || eps_a == nullptr || mean_b == nullptr || var_b == nullptr || eps_b == nullptr)
+    return BVLM_EINVAL;
+  if ((oper_a == nullptr && marg_a == nullptr) || (oper_b == nullptr && marg_b == nullptr)) return BVLM_EINVAL;
+  const PrepSide sa{mean_a, var_a, eps_a, nullptr, Na, nullptr, static_cast<__half*>(oper_a), static_cast<__half*>(marg_a), 1};
+  const PrepSide sb{mean_b, var_b, eps_b, nullptr, Nb, nullptr, static_cast<__half*>(oper_b), static_cast<__half*>(marg_b), 1};
+  return launch_epig_prepare(sa, sb, K, Cl, static_cast<cudaStream_t>(stream));
 }
 
 int bvlm_epig_prepare_from_probs(const void* probs16, int64_t N, int64_t K, int64_t Cl, void* oper16, void* marg16,
                                  void* stream) {
   if (probs16 == nullptr || (oper16 == nullptr && marg16 == nullptr)) return BVLM_EINVAL;
-  return launch_epig_prepare(nullptr, nullptr, nullptr, static_cast<const __half*>(probs16), N, K, Cl, nullptr,
-                             static_cast<__half*>(oper16), static_cast<__half*>(marg16), static_cast<cudaStream_t>(stream));
+  const PrepSide sa{nullptr, nullptr, nullptr, static_cast<const __half*>(probs16), N, nullptr, static_cast<__half*>(oper16),
+                    static_cast<__half*>(marg16), 1};
+  return launch_epig_prepare(sa, PrepSide{}, K, Cl, static_cast<cudaStream_t>(stream));
 }
 
 int bvlm_epig_sample_probs(const float* mean, const float* var, const float* eps, int64_t N, int64_t K, int64_t Cl,

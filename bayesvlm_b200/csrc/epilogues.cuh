@@ -502,11 +502,13 @@ constexpr float GGN_WSCALE = 4096.f;
 // InfoNCE: |d| reaches 2 s log2(e) (~290 at s = 100) while the conditional weight of the runner-up target is ~1, so
 // omega * d is stored with a smaller scale than omega itself to stay inside fp16 (max 65504).
 constexpr float GGN_WDSCALE = 64.f;
+constexpr int GGN_W_SLABS = 2;  // output slabs per epilogue warp of the weights pass (2: 64 KB, leaves room for a 4th operand stage)
 
 template <int BN, bool SIGLIP>
 struct EpiGgnWeights {
-  // per epilogue warp three rotating output slabs (12 KB), then 4 x BN floats of per-quadrant column sums
-  static constexpr size_t scratch_bytes(int warps) { return warps * 3 * SLAB_BYTES + 4 * BN * sizeof(float); }
+  // per epilogue warp NSLAB output slabs (4 KB each), then 4 x BN floats of per-quadrant column sums
+  static constexpr int NSLAB = GGN_W_SLABS;
+  static constexpr size_t scratch_bytes(int warps) { return warps * NSLAB * SLAB_BYTES + 4 * BN * sizeof(float); }
   struct Params {
     CUtensorMap tm_w, tm_wl;  // [B, Cp] fp16, box {64 cols, 32 rows}, SWIZZLE_128B
     const float4* rowinfo;  // [B] per source: {m2, lgw, wq, pivot bits} (InfoNCE) / {0, 0, wq, 0} (SigLIP); see k_ggn_rowinfo
@@ -526,7 +528,7 @@ struct EpiGgnWeights {
   static constexpr bool UNROLL_CHUNKS = false;  // the body is large: keep one copy
   static constexpr bool DRAIN_FIRST = false;
   __device__ static uint32_t qsum_addr(const EpiCtx& ctx) {
-    return ctx.scratch_u32 + static_cast<uint32_t>(ctx.n_warps) * (3 * SLAB_BYTES);
+    return ctx.scratch_u32 + static_cast<uint32_t>(ctx.n_warps) * (NSLAB * SLAB_BYTES);
   }
   __device__ static void kernel_begin(State& st, const Params&, const EpiCtx&) {
     st.sidx = 0;
@@ -596,11 +598,13 @@ struct EpiGgnWeights {
       }
     }
     // ---- stage fp16 omega / omega*(d|L) in the warp's rotating slabs (two 32-column chunks fill one 64-column slab)
-    const uint32_t wbase = ctx.scratch_u32 + static_cast<uint32_t>(ctx.wid) * (3 * SLAB_BYTES);
+    const uint32_t wbase = ctx.scratch_u32 + static_cast<uint32_t>(ctx.wid) * (NSLAB * SLAB_BYTES);
     const int h = c & 1;
-    const int b0 = st.sidx % 3;
-    const int b1 = SIGLIP ? b0 : (st.sidx + 1) % 3;
-    if (h == 0) slab_wait_free<1>(ctx.lane);  // every bulk store but the most recent one has finished reading
+    const int b0 = st.sidx % NSLAB;
+    const int b1 = SIGLIP ? b0 : (st.sidx + 1) % NSLAB;
+    // NSLAB = 3: every bulk store but the most recent one has finished reading; NSLAB = 2 (InfoNCE uses both per chunk pair):
+    // all of them have -- they were issued two chunks (~2 us) ago
+    if (h == 0) slab_wait_free<(NSLAB >= 3 ? 1 : 0)>(ctx.lane);
     if constexpr (!SIGLIP) slab_write_f16_half(wbase + static_cast<uint32_t>(b0) * SLAB_BYTES, ctx.lane, h, om);
 #pragma unroll
     for (int j = 0; j < 32; j += 2) {
@@ -618,7 +622,7 @@ struct EpiGgnWeights {
       slab_issue(&p.tm_wl, wbase + static_cast<uint32_t>(b1) * SLAB_BYTES, ctx.lane, col0 - 32, row0);
       slab_commit(ctx.lane);
       st.sidx += SIGLIP ? 1 : 2;
-      if (st.sidx >= 3) st.sidx -= 3;
+      if (st.sidx >= NSLAB) st.sidx -= NSLAB;
     }
     // ---- weighted column sums of this 32 x 32 block: butterfly over the rows, accumulated in shared memory
     const float2 w2 = make_float2(st.w, st.w);

@@ -186,8 +186,9 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       uint32_t phase = 0;
       for (int item = cluster_id; item < n_items; item += n_clusters) {
         const int n_inner = plan_inner<BN>(plan, item);
+        const TileCoord tbase = plan_tile<BN>(plan, item);
         for (int inner = 0; inner < n_inner; ++inner) {
-          const TileCoord tc = plan_tile<BN>(plan, item, inner);
+          const TileCoord tc = plan_tile_at<BN>(plan, tbase, inner);
           const int row_a = (tc.m * PAIRS + static_cast<int>(pair)) * GEMM2_BM + static_cast<int>(rank) * GEMM_BM;
           const int row_b = tc.n * BN + static_cast<int>(rank) * (BN / 2);
           const bool load_b = PAIRS == 1 || pair == 0;  // pair 0 multicasts the shared B tile to the other pair
@@ -203,7 +204,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 ++seg_v;
               }
             }
-            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            mbar_wait<true>(&empty_bar[stage], phase ^ 1u);
             mbar_arrive_expect_tx_leader(&full_bar[stage], plan.a_tx_bytes + B_BYTES);
             if (kb >= plan.kb_alt) {  // FP8 phase: same 128-byte K blocks, 128 elements each, second pair of tensor maps
               const int col8 = (kb - plan.kb_alt) * 128;
@@ -248,9 +249,10 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       uint32_t acc_phase = 0;
       for (int item = cluster_id; item < n_items; item += n_clusters) {
         const int n_inner = plan_inner<BN>(plan, item);
+        const TileCoord tbase = plan_tile<BN>(plan, item);
         for (int inner = 0; inner < n_inner; ++inner) {
-          const TileCoord tc = plan_tile<BN>(plan, item, inner);
-          mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+          const TileCoord tc = plan_tile_at<BN>(plan, tbase, inner);
+          mbar_wait<true>(&tempty_bar[acc], acc_phase ^ 1u);
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BN);
           for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
@@ -311,7 +313,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       t0.row0_next = -1;
       Epi::item_begin(st, ep, ctx, t0);
       for (int inner = 0; inner < n_inner; ++inner) {
-        TileCoord tc = plan_tile<BN>(plan, item, inner);
+        TileCoord tc = plan_tile_at<BN>(plan, t0, inner);
         tc.row0 = (tc.m * PAIRS + static_cast<int>(pair)) * GEMM2_BM + static_cast<int>(rank) * GEMM_BM;
         tc.row0_next = (plan.mode == SCHED_COL_PANEL && inner + 1 < n_inner) ? tc.row0 + PAIRS * GEMM2_BM : -1;
         Epi::tile_begin(st, ep, ctx, tc);

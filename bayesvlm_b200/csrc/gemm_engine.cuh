@@ -70,45 +70,73 @@ __host__ __device__ inline int plan_num_items(const GemmPlan& p) {
     default: return p.m_tiles * p.n_tiles * p.splits;
   }
 }
+// (32-bit unsigned arithmetic on purpose: these run per item in EVERY thread of the role loops, and a 64-bit division is
+//  ~100 instructions; split * tiles < 2^31 for every schedule the library builds)
 __host__ __device__ inline int col_panel_m0(const GemmPlan& p, int split) {
-  return static_cast<int>(static_cast<long long>(split) * p.m_tiles / p.splits);
+  return static_cast<int>(static_cast<uint32_t>(split) * static_cast<uint32_t>(p.m_tiles) / static_cast<uint32_t>(p.splits));
 }
 __host__ __device__ inline int row_panel_n0(const GemmPlan& p, int split) {
-  return static_cast<int>(static_cast<long long>(split) * p.n_tiles / p.splits);
+  return static_cast<int>(static_cast<uint32_t>(split) * static_cast<uint32_t>(p.n_tiles) / static_cast<uint32_t>(p.splits));
 }
 template <int BN>
 __host__ __device__ inline int plan_inner(const GemmPlan& p, int item) {
   switch (p.mode) {
     case SCHED_ROW_PANEL: {
-      const int split = item % p.splits;
+      if (p.splits == 1) return p.n_tiles;
+      const int split = static_cast<int>(static_cast<uint32_t>(item) % static_cast<uint32_t>(p.splits));
       return row_panel_n0(p, split + 1) - row_panel_n0(p, split);
     }
     case SCHED_COL_PANEL: {
-      const int split = item / p.n_tiles;
+      if (p.splits == 1) return p.m_tiles;
+      const int split = static_cast<int>(static_cast<uint32_t>(item) / static_cast<uint32_t>(p.n_tiles));
       return col_panel_m0(p, split + 1) - col_panel_m0(p, split);
     }
     default: return 1;
   }
 }
 template <int BN>
-__device__ __forceinline__ TileCoord plan_tile(const GemmPlan& p, int item, int inner) {
+__device__ __forceinline__ int plan_tri_kb_end(const GemmPlan& p, int n) {
+  int kb_end = p.kb_total;
+  if (p.tri_k) {
+    const int lim = ((n + 1) * BN + GEMM_BK - 1) / GEMM_BK;
+    kb_end = lim < kb_end ? lim : kb_end;
+  }
+  return kb_end;
+}
+// First tile (inner = 0) of an item.
+template <int BN>
+__device__ __forceinline__ TileCoord plan_tile(const GemmPlan& p, int item, int inner = 0) {
   TileCoord t;
-  int ksplit = 0, ksplits = 1;  // split-K index / count (tile schedules only)
+  uint32_t ksplit = 0, ksplits = 1;  // split-K index / count (tile schedules only)
+  const uint32_t uitem = static_cast<uint32_t>(item);
   t.split = 0;
   if (p.mode == SCHED_ROW_PANEL) {
     // consecutive items share the M tile (its A panel stays hot in L2) and walk different N ranges
-    t.m = item / p.splits;
-    t.split = item % p.splits;
-    t.n = row_panel_n0(p, t.split) + inner;
+    if (p.splits == 1) {
+      t.m = item;
+      t.n = inner;
+    } else {
+      t.m = static_cast<int>(uitem / static_cast<uint32_t>(p.splits));
+      t.split = item - t.m * p.splits;
+      t.n = row_panel_n0(p, t.split) + inner;
+    }
   } else if (p.mode == SCHED_COL_PANEL) {
-    t.n = item % p.n_tiles;
-    t.split = item / p.n_tiles;
-    t.m = col_panel_m0(p, t.split) + inner;
+    if (p.splits == 1) {
+      t.n = item;
+      t.m = inner;
+    } else {
+      t.split = static_cast<int>(uitem / static_cast<uint32_t>(p.n_tiles));
+      t.n = item - t.split * p.n_tiles;
+      t.m = col_panel_m0(p, t.split) + inner;
+    }
   } else if (p.mode == SCHED_TRI_TILES) {
     const int tri = p.m_tiles * (p.m_tiles + 1) / 2;
-    const int idx = item % tri;
-    ksplit = item / tri;
-    ksplits = p.splits;
+    int idx = item;
+    if (p.splits > 1) {
+      ksplit = uitem / static_cast<uint32_t>(tri);
+      idx = item - static_cast<int>(ksplit) * tri;
+      ksplits = static_cast<uint32_t>(p.splits);
+    }
     int m = static_cast<int>((sqrtf(8.0f * static_cast<float>(idx) + 1.0f) - 1.0f) * 0.5f);
     while ((m + 1) * (m + 2) / 2 <= idx) ++m;
     while (m * (m + 1) / 2 > idx) --m;
@@ -116,20 +144,38 @@ __device__ __forceinline__ TileCoord plan_tile(const GemmPlan& p, int item, int 
     t.n = idx - m * (m + 1) / 2;
   } else {
     const int tiles = p.m_tiles * p.n_tiles;
-    const int idx = item % tiles;
-    ksplit = item / tiles;
-    ksplits = p.splits;
-    t.m = idx / p.n_tiles;
-    t.n = idx % p.n_tiles;
+    int idx = item;
+    if (p.splits > 1) {
+      ksplit = uitem / static_cast<uint32_t>(tiles);
+      idx = item - static_cast<int>(ksplit) * tiles;
+      ksplits = static_cast<uint32_t>(p.splits);
+    }
+    t.m = static_cast<int>(static_cast<uint32_t>(idx) / static_cast<uint32_t>(p.n_tiles));
+    t.n = idx - t.m * p.n_tiles;
   }
-  int kb_end = p.kb_total;
-  if (p.tri_k) {
-    const int lim = ((t.n + 1) * BN + GEMM_BK - 1) / GEMM_BK;
-    kb_end = lim < kb_end ? lim : kb_end;
+  const int kb_end = plan_tri_kb_end<BN>(p, t.n);
+  if (ksplits == 1) {
+    t.kb0 = 0;
+    t.kb1 = kb_end;
+  } else {
+    t.kb0 = static_cast<int>(ksplit * static_cast<uint32_t>(kb_end) / ksplits);
+    t.kb1 = static_cast<int>((ksplit + 1) * static_cast<uint32_t>(kb_end) / ksplits);
   }
-  t.kb0 = static_cast<int>(static_cast<long long>(ksplit) * kb_end / ksplits);
-  t.kb1 = static_cast<int>(static_cast<long long>(ksplit + 1) * kb_end / ksplits);
   t.row0 = t.m * GEMM_BM;
+  return t;
+}
+// Tile `inner` of the item whose first tile is `base`: panels advance by one N (row panel) or M (column panel) tile, which
+// needs no division at all -- the role loops call this once per tile.
+template <int BN>
+__device__ __forceinline__ TileCoord plan_tile_at(const GemmPlan& p, const TileCoord& base, int inner) {
+  TileCoord t = base;
+  if (p.mode == SCHED_ROW_PANEL) {
+    t.n = base.n + inner;
+    t.kb1 = plan_tri_kb_end<BN>(p, t.n);  // (panels are never split along K: kb0 = 0)
+  } else if (p.mode == SCHED_COL_PANEL) {
+    t.m = base.m + inner;
+    t.row0 = t.m * GEMM_BM;
+  }
   return t;
 }
 
@@ -262,8 +308,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t phase = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int n_inner = plan_inner<BN>(plan, item);
+        const TileCoord tbase = plan_tile<BN>(plan, item);
         for (int inner = 0; inner < n_inner; ++inner) {
-          const TileCoord tc = plan_tile<BN>(plan, item, inner);
+          const TileCoord tc = plan_tile_at<BN>(plan, tbase, inner);
           int seg_v = 0, seg_off = tc.kb0;  // virtual segment / K block inside it (split plans always start at kb0 = 0)
           for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
             int col_a = kb * GEMM_BK, col_b = col_a;
@@ -300,8 +347,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t acc_phase = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int n_inner = plan_inner<BN>(plan, item);
+        const TileCoord tbase = plan_tile<BN>(plan, item);
         for (int inner = 0; inner < n_inner; ++inner) {
-          const TileCoord tc = plan_tile<BN>(plan, item, inner);
+          const TileCoord tc = plan_tile_at<BN>(plan, tbase, inner);
           mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BN);

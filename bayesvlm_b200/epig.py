@@ -18,7 +18,6 @@ from .hessians import compute_covariances, compute_hessian_analytic_InfoNCE, opt
 from .vlm import CLIP, EncoderResult, ProbabilisticLogits
 
 _JOINT_TILE_N = 256  # column tile of the joint-entropy kernel; chunk_size must be a multiple of it
-_PREP_SMEM = 100 * 1024  # shared-memory budget of the fused sample / permute / marginal-entropy kernel (csrc/epig.cu)
 
 
 def _kernel_path_ok(probs: torch.Tensor) -> bool:
@@ -26,11 +25,8 @@ def _kernel_path_ok(probs: torch.Tensor) -> bool:
 
 
 def _prepare_fits(k: int, cl: int, from_noise: bool) -> bool:
-    """One sample row's [Cl, Kp] fp16 operand tile (+ its partial sums and mean / std) must fit the shared-memory budget of
-    the fused kernel (csrc/epig.cu: prep_row_bytes / PREP_SMEM_MAX)."""
-    del from_noise  # the noise is read straight into registers: both variants stage the same tile
-    kp = int(lib.bvlm_epig_operand_k(k))
-    return cl * kp * 2 + cl * (kp // 64) * 4 + cl * 8 <= _PREP_SMEM
+    """The fused sample / permute / marginal-entropy kernel stages a block's tiles in shared memory (csrc/epig.cu)."""
+    return bool(lib.bvlm_epig_prepare_supported(k, cl, 1 if from_noise else 0))
 
 
 def _joint_fused_ok(k: int, cl: int, chunk_size: int) -> bool:
@@ -65,6 +61,27 @@ def prepare_from_noise(mean: torch.Tensor, var: torch.Tensor, eps: torch.Tensor,
     _lib.run(dev, "bvlm_epig_prepare_from_noise", _lib.ptr(mean.contiguous()), _lib.ptr(var.contiguous()),
              _lib.ptr(eps.contiguous()), n, k, cl, _lib.ptr(probs), _lib.ptr(oper), _lib.ptr(marg), _lib.stream_ptr(dev))
     return probs, oper, marg
+
+
+def prepare_pair_from_noise(mean_a, var_a, eps_a, mean_b, var_b, eps_b):
+    """``prepare_from_noise`` for two sample sets sharing [K, Cl] (the target set and one pool chunk of reference
+    epig.py:326-333) in ONE kernel launch; returns (operand_a, entropy_a, operand_b, entropy_b)."""
+    from .vlm import _check_noise_shapes
+
+    k, na, cl = _check_noise_shapes(mean_a, var_a, eps_a)
+    kb, nb, clb = _check_noise_shapes(mean_b, var_b, eps_b)
+    if (k, cl) != (kb, clb) or mean_a.device != mean_b.device:
+        raise ValueError("both sample sets must share [K, Cl] and the device")
+    dev = mean_a.device
+    f16 = dict(dtype=torch.float16, device=dev)
+    kp = int(lib.bvlm_epig_operand_k(k))
+    oper_a, oper_b = torch.empty((na, cl, kp), **f16), torch.empty((nb, cl, kp), **f16)
+    marg_a, marg_b = torch.empty(na, **f16), torch.empty(nb, **f16)
+    _lib.run(dev, "bvlm_epig_prepare_pair_from_noise", _lib.ptr(mean_a.contiguous()), _lib.ptr(var_a.contiguous()),
+             _lib.ptr(eps_a.contiguous()), na, _lib.ptr(oper_a), _lib.ptr(marg_a), _lib.ptr(mean_b.contiguous()),
+             _lib.ptr(var_b.contiguous()), _lib.ptr(eps_b.contiguous()), nb, _lib.ptr(oper_b), _lib.ptr(marg_b), k, cl,
+             _lib.stream_ptr(dev))
+    return oper_a, marg_a, oper_b, marg_b
 
 
 def entropy_from_probs(probs: torch.Tensor) -> torch.Tensor:
@@ -163,13 +180,12 @@ def epig_from_logits_using_matmul(logits_pool: ProbabilisticLogits, logits_targ:
             continue
         dev = logits_targ.mean.device
         torch.manual_seed(seed + lo)
-        eps = torch.randn((num_samples,) + tuple(logits_targ.mean.shape), device=dev)
-        _, oper_t, ent_t = prepare_from_noise(logits_targ.mean, logits_targ.var, eps)
+        eps_t = torch.randn((num_samples,) + tuple(logits_targ.mean.shape), device=dev)
         mean_p, var_p = logits_pool.mean[lo:lo + chunk_size], logits_pool.var[lo:lo + chunk_size]
         torch.manual_seed(seed + lo)
-        eps = torch.randn((num_samples,) + tuple(mean_p.shape), device=mean_p.device)
-        _, oper_p, ent_p = prepare_from_noise(mean_p, var_p, eps)
-        del eps
+        eps_p = torch.randn((num_samples,) + tuple(mean_p.shape), device=mean_p.device)
+        oper_t, ent_t, oper_p, ent_p = prepare_pair_from_noise(logits_targ.mean, logits_targ.var, eps_t, mean_p, var_p, eps_p)
+        del eps_t, eps_p
         joint = joint_entropy_from_operands(oper_p, oper_t, num_samples, chunk_size)
         pieces.append((ent_p + torch.mean(ent_t) - joint).to(torch.float32))
     return torch.cat(pieces, dim=0)

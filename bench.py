@@ -583,7 +583,7 @@ def run_b200(args, rank, world, local_rank):
                "target_rows": ec["target"], "joint_kernel_ms": joint_ms,
                "joint_log_evals_per_s": epairs * cl ** 2 / max(joint_ms * 1e-3, 1e-12),
                "joint_frac_of_mufu_roof": epairs * cl ** 2 / max(joint_ms * 1e-3, 1e-12) / (16.0 * 148 * 1.965e9),
-               "reductions": {"what": "E0 sample -> fp16 -> permuted GEMM operand -> E1 marginal entropy, one kernel per side and pool chunk",
+               "reductions": {"what": "E0 sample -> fp16 -> permuted GEMM operand -> E1 marginal entropy; target set + pool chunk in ONE launch per chunk",
                               "launches": ek.get("epig_prepare", (0, 0.0))[0], "bytes": prep_bytes, "ms": prep_ms,
                               "gbs": prep_bytes / max(prep_ms * 1e-3, 1e-12) / 1e9,
                               "frac": prep_bytes / max(prep_ms * 1e-3, 1e-12) / 1e9 / peaks["hbm_gbs"], "peak_gbs": peaks["hbm_gbs"]}}

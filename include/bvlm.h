@@ -133,12 +133,19 @@ int bvlm_probit_softmax(const float* mean, const float* var, int64_t N, int64_t 
  * bvlm_epig_prepare_from_noise / _from_probs: E0 + E1 + the permute of epig.py:374-376 in ONE pass over the samples.
  * Every output is optional (NULL): probs16 [N, K, Cl]; oper16 [N, Cl, bvlm_epig_operand_k(K)] = the K-major, zero-padded
  * operand bvlm_epig_joint_entropy_operands consumes; marg16 [N] marginal entropies.
+ * bvlm_epig_prepare_supported: 1 when a sample row's tiles fit the kernel's shared memory for this (K, Cl), else 0 (the
+ * prepare entry points then return BVLM_ENOTSUP and the caller keeps the generic device expression).
  * --------------------------------------------------------------------------------------------------------- */
 int bvlm_epig_operand_k(int64_t K);
+int bvlm_epig_prepare_supported(int64_t K, int64_t Cl, int from_noise);
 int bvlm_epig_prepare_from_noise(const float* mean, const float* var, const float* eps, int64_t N, int64_t K, int64_t Cl,
                                  void* probs16, void* oper16, void* marg16, void* stream);
 int bvlm_epig_prepare_from_probs(const void* probs16, int64_t N, int64_t K, int64_t Cl, void* oper16, void* marg16,
                                  void* stream);
+/* two sample sets sharing K and Cl (EPIG: the target set and one pool chunk, epig.py:326-333) in ONE launch */
+int bvlm_epig_prepare_pair_from_noise(const float* mean_a, const float* var_a, const float* eps_a, int64_t Na, void* oper_a,
+                                      void* marg_a, const float* mean_b, const float* var_b, const float* eps_b, int64_t Nb,
+                                      void* oper_b, void* marg_b, int64_t K, int64_t Cl, void* stream);
 int bvlm_epig_joint_entropy_operands(const void* poolP, int64_t Np, const void* targP, int64_t Nt, int64_t K, int64_t Cl,
                                      int64_t col_chunk, float* Hjoint, void* stream);
 int bvlm_epig_sample_probs(const float* mean, const float* var, const float* eps, int64_t N, int64_t K, int64_t Cl,

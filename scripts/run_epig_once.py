@@ -5,9 +5,10 @@ import bench
 from bayesvlm_b200.epig import epig_from_logits_using_matmul
 from bayesvlm_b200.vlm import ProbabilisticLogits
 ec = bench.EPIG
+CL = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 gen = torch.Generator(device="cuda").manual_seed(1)
-mk = lambda n: ProbabilisticLogits(torch.randn(n, ec["Cl"], generator=gen, device="cuda") * 2,
-                                   torch.rand(n, ec["Cl"], generator=gen, device="cuda") * 3 + 0.1)
+mk = lambda n: ProbabilisticLogits(torch.randn(n, CL, generator=gen, device="cuda") * 2,
+                                   torch.rand(n, CL, generator=gen, device="cuda") * 3 + 0.1)
 lp, lt = mk(4096), mk(ec["target"])
 for _ in range(int(sys.argv[1]) if len(sys.argv) > 1 else 2):
     s = epig_from_logits_using_matmul(lp, lt, seed=0, num_samples=ec["K"], chunk_size=ec["chunk"])
