@@ -14,7 +14,8 @@ import torch
 
 from . import _lib
 from ._lib import lib
-from .hessians import compute_covariances, compute_hessian_analytic_InfoNCE, optimize_prior_precision
+from .hessians import (FactorSpectrum, compute_covariances, compute_hessian_analytic_InfoNCE, covariance_from_spectra,
+                       optimize_prior_precision)
 from .vlm import CLIP, EncoderResult, ProbabilisticLogits
 
 _JOINT_TILE_N = 256  # column tile of the joint-entropy kernel; chunk_size must be a multiple of it
@@ -307,11 +308,15 @@ def select_epig_online(label_features: EncoderResult, pool_features: EncoderResu
         A_img = (s0 * A_img + A_new * hessian_update_scale) / s1
         B_img = (s0 * B_img + B_new * hessian_update_scale) / s1
 
+        # ONE eigendecomposition per updated image factor feeds the 20 Adam steps on lambda AND the covariance of the
+        # optimised lambda; the text-side covariance never changes inside the loop (reference epig.py:255-263 re-inverts all
+        # four factors and re-factorises A_img / B_img twenty times per pick).
+        spectra = (FactorSpectrum.of(A_img, device), FactorSpectrum.of(B_img, device))
         lmbda_img = optimize_prior_precision(projection=image_projection, A=A_img, B=B_img,
                                              lmbda_init=cov_info["lambda_img"], n=cov_info["n_img"], lr=1e-3,
-                                             num_steps=20, device=device, retain_graph=True)
+                                             num_steps=20, device=device, retain_graph=True, spectra=spectra)
         cov_info["lambda_img"] = lmbda_img.item()
-        cov_img, cov_txt = compute_covariances(A_img, B_img, A_txt, B_txt, cov_info)
+        cov_img = covariance_from_spectra(spectra[0], spectra[1], cov_info["n_img"], cov_info["lambda_img"], dtype=A_img.dtype)
         clip.set_covariances(cov_img, cov_txt)
 
     return selected_indices, epig_scores

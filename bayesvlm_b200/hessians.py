@@ -318,6 +318,41 @@ def compute_covariances(A_img: torch.Tensor, B_img: torch.Tensor, A_txt: torch.T
     return cov_img, cov_txt
 
 
+@dataclass
+class FactorSpectrum:
+    """Eigendecomposition ``F = V diag(e) V^T`` of one (symmetrised) Kronecker factor, fp64 on the factor's device.
+
+    ONE ``syevd`` per factor serves both consumers of the online loop: the prior-precision optimiser needs
+    ``logdet(sqrt(n) F + sqrt(lambda) I) = sum_k log(sqrt(n) e_k + sqrt(lambda))`` for many lambdas, and the covariance needs
+    ``(sqrt(n) F + sqrt(lambda) I)^-1 = V diag(1 / (sqrt(n) e_k + sqrt(lambda))) V^T`` for the optimised one -- a d x d GEMM
+    instead of a fresh LU factorisation + inverse (reference hessians.py:170-184 and :219-265 factorise 2 + 2 * num_steps times).
+    """
+
+    evals: torch.Tensor
+    evecs: torch.Tensor
+
+    @staticmethod
+    def of(F: torch.Tensor, device=None) -> "FactorSpectrum":
+        F64 = F.detach().to(device if device is not None else F.device).double()
+        evals, evecs = torch.linalg.eigh(0.5 * (F64 + F64.T))
+        return FactorSpectrum(evals=evals, evecs=evecs)
+
+    def logdet_regularised(self, sqrt_n, sqrt_l) -> torch.Tensor:
+        return torch.log(self.evals * sqrt_n + sqrt_l).sum()
+
+    def inverse_regularised(self, sqrt_n: float, sqrt_l: float, dtype=torch.float32) -> torch.Tensor:
+        d = 1.0 / (self.evals * sqrt_n + sqrt_l)
+        return ((self.evecs * d) @ self.evecs.T).to(dtype)
+
+
+def covariance_from_spectra(spec_A: FactorSpectrum, spec_B: FactorSpectrum, n: float, lmbda: float,
+                            dtype=torch.float32) -> KroneckerFactorizedCovariance:
+    """``_compute_covariance`` (reference hessians.py:170-184) from precomputed factor spectra."""
+    sqrt_n, sqrt_l = math.sqrt(float(n)), math.sqrt(float(lmbda))
+    return KroneckerFactorizedCovariance(A_inv=spec_A.inverse_regularised(sqrt_n, sqrt_l, dtype),
+                                         B_inv=spec_B.inverse_regularised(sqrt_n, sqrt_l, dtype))
+
+
 def load_hessians(la_dir: str, tag: Literal["img", "txt"], return_info: bool = False):
     A = torch.load(Path(la_dir) / f"A_{tag}_analytic.pt", map_location="cpu")
     B = torch.load(Path(la_dir) / f"B_{tag}_analytic.pt", map_location="cpu")
@@ -362,11 +397,14 @@ def compute_log_det_kfac(A: torch.Tensor, B: torch.Tensor):
 
 
 def optimize_prior_precision(projection: torch.nn.Module, A: torch.Tensor, B: torch.Tensor, lmbda_init: float, n: float,
-                             lr: float, num_steps: int, device: str, retain_graph: bool = False, verbose: bool = False):
+                             lr: float, num_steps: int, device: str, retain_graph: bool = False, verbose: bool = False,
+                             spectra: Optional[Tuple["FactorSpectrum", "FactorSpectrum"]] = None):
     """Adam ascent on log(lambda) of ``log_prior - logdet_kfac`` (no 1/2 on the log-det: reference hessians.py:260).
 
     The reference re-factorises both d x d matrices every step; here each factor is diagonalised once
     (``logdet(F sqrt(n) + sqrt(lambda) I) = sum_k log(sqrt(n) e_k + sqrt(lambda))``), which makes a step O(d).
+    With ``spectra=(FactorSpectrum.of(A), FactorSpectrum.of(B))`` no factorisation happens here at all, and the same
+    spectra give the covariance of the optimised lambda through ``covariance_from_spectra``.
     """
     del retain_graph, verbose
     for p in projection.parameters():
@@ -378,7 +416,8 @@ def optimize_prior_precision(projection: torch.nn.Module, A: torch.Tensor, B: to
         F64 = F.to(device).double()
         return torch.linalg.eigvalsh(0.5 * (F64 + F64.T))
 
-    eig_a, eig_b = spectrum(A), spectrum(B)
+    # ``spectra``: eigendecompositions the caller already holds (and will reuse for the covariance) -- no factorisation here
+    eig_a, eig_b = (spectra[0].evals.to(device), spectra[1].evals.to(device)) if spectra is not None else (spectrum(A), spectrum(B))
     p_dim, q_dim = A.shape[0], B.shape[0]
     log_lmbda = torch.nn.Parameter(torch.tensor(lmbda_init, device=device, dtype=torch.float32).log())
     sqrt_n = math.sqrt(n)

@@ -171,7 +171,68 @@ def main():
     make_knn()
     make_selection()
     make_epig_online()
+    make_shipped()
     print("wrote", OUT)
+
+
+def shipped_problem(which: str):
+    """Seeded inputs of the shipped-factor golden problems (also imported by the GPU parity test, which re-creates them).
+    L-14 (BASELINE config 3 shape): 4096 images x 1000 classes, D = 768, d_img = 1024, d_txt = 768 -- the reference ships
+    A_txt, B_img, B_txt for this model, A_img (1024^2) is a seeded surrogate.  SigLIP (config 5): 1024 images x 257 classes,
+    D = 768, d_img = 3072 (+1 bias), d_txt = 768 (+1): shipped A_txt (769^2), B_img, B_txt; A_img (3073^2) surrogate."""
+    if which == "l14":
+        cfg = dict(name="hessian_CLIP-ViT-L-14-laion2B-s32B-b82K", N=4096, C=1000, D=768, d_img=1024, d_txt=768, bias=0, seed=3100,
+                   logit_scale=math.log(100.0), logit_bias=0.0, rows=48)
+    else:
+        cfg = dict(name="hessian_siglip-base-patch16-256", N=1024, C=257, D=768, d_img=3072, d_txt=768, bias=1, seed=5100,
+                   logit_scale=4.765, logit_bias=-12.93, rows=48)
+    g = torch.Generator().manual_seed(cfg["seed"])
+    t = dict(img_e=randn(g, cfg["N"], cfg["D"]), img_a=randn(g, cfg["N"], cfg["d_img"]), txt_e=randn(g, cfg["C"], cfg["D"]),
+             txt_a=randn(g, cfg["C"], cfg["d_txt"]), A_img=spd(g, cfg["d_img"] + cfg["bias"], 3e3))
+    t["rows"] = torch.randperm(cfg["N"], generator=g)[:cfg["rows"]].sort().values
+    return cfg, t
+
+
+def sym_from_lower(tri: np.ndarray, d: int) -> np.ndarray:
+    """Symmetric [d, d] matrix from its packed lower triangle (np.tril_indices order)."""
+    m = np.zeros((d, d), tri.dtype)
+    il = np.tril_indices(d)
+    m[il] = tri
+    return m + np.tril(m, -1).T
+
+
+def make_shipped():
+    """Predictive on the factors the reference SHIPS for ViT-L-14 and SigLIP (hessians/...): the real three-decade spectra.
+    The fixture stores the packed lower triangles (the shipped B factors are symmetric to 1.5e-7 relative; BOTH the reference
+    run below and the GPU test use the matrices rebuilt from these triangles) + the reference's outputs on 48 seeded rows.
+    `python make_golden.py shipped` regenerates only these files."""
+    r_hess, r_vlm, _, _ = load_reference()
+    for which in ("l14", "siglip"):
+        cfg, t = shipped_problem(which)
+        la = REF / "hessians" / cfg["name"]
+        info = json.loads((la / "prior_precision_analytic.json").read_text())
+        fx = {}
+        facs = {}
+        for tag in ("A_txt", "B_img", "B_txt"):
+            full = torch.load(la / f"{tag}_analytic.pt", map_location="cpu").numpy()
+            d = full.shape[0]
+            fx[tag + "_tril"] = full[np.tril_indices(d)]
+            facs[tag] = torch.from_numpy(sym_from_lower(fx[tag + "_tril"], d))
+            fx[tag + "_asym"] = np.array([np.abs(full - full.T).max() / np.abs(full).max()], np.float64)
+        cov_img, cov_txt = r_hess.compute_covariances(t["A_img"], facs["B_img"], facs["A_txt"], facs["B_txt"], info)
+        if which == "l14":
+            model = r_vlm.CLIP(logit_scale=cfg["logit_scale"])
+        else:
+            model = r_vlm.SIGLIP(logit_scale=cfg["logit_scale"], logit_bias=cfg["logit_bias"])
+        model.set_covariances(cov_img, cov_txt)
+        rows = t["rows"]
+        with torch.no_grad():
+            pl = model(r_vlm.EncoderResult(embeds=t["img_e"][rows], activations=t["img_a"][rows]),
+                       r_vlm.EncoderResult(embeds=t["txt_e"], activations=t["txt_a"]))
+        fx.update(mean=pl.mean.numpy(), var=pl.var.numpy(), rows=rows.numpy(),
+                  info=np.array([info["n_img"], info["n_txt"], info["lambda_img"], info["lambda_txt"]], np.float64))
+        np.savez_compressed(OUT / f"shipped_{which}.npz", **fx)
+        print(which, "mean range", float(pl.mean.min()), float(pl.mean.max()), "var range", float(pl.var.min()), float(pl.var.max()))
 
 
 def epig_online_problem(seed=21, D=32, d_in=40, n_cls=6, n_pool=600, n_targ=300):
@@ -316,5 +377,7 @@ if __name__ == "__main__":
         make_selection()
     elif len(sys.argv) > 1 and sys.argv[1] == "epig_online":
         make_epig_online()
+    elif len(sys.argv) > 1 and sys.argv[1] == "shipped":
+        make_shipped()
     else:
         main()

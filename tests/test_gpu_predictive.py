@@ -84,6 +84,38 @@ def test_config1_shipped_b32_factors(golden_b32, precision):
                   strict=precision != "fp16")
 
 
+@pytest.mark.parametrize("precision", ["fp16x3", "fp16+fp8"])
+@pytest.mark.parametrize("which", ["l14", "siglip"])
+def test_shipped_l14_and_siglip_factors(which, precision):
+    """BASELINE configs 3 / 5 on the factors the reference ships for ViT-L-14 (A_txt, B_img, B_txt) and SigLIP (A_txt 769^2,
+    B_img, B_txt): the real three-decade spectra go through the fp16 quadratic forms.  Golden = the reference's own
+    CLIP / SIGLIP.forward on 48 seeded rows (tests/golden/make_golden.py `shipped`); all N rows are predicted (so the golden
+    rows sit in different row panels) and the covariances are assembled on the device from the packed factors."""
+    import sys
+
+    from conftest import GOLDEN
+
+    sys.path.insert(0, str(GOLDEN))
+    from make_golden import shipped_problem, sym_from_lower
+
+    from bayesvlm_b200.hessians import compute_covariances
+    from bayesvlm_b200.vlm import CLIP, SIGLIP, EncoderResult
+
+    fx = dict(np.load(GOLDEN / f"shipped_{which}.npz"))
+    cfg, t = shipped_problem(which)
+    fac = {k: _cuda(sym_from_lower(fx[k + "_tril"], cfg["D"] + (cfg["bias"] if k == "A_txt" else 0))) for k in ("A_txt", "B_img", "B_txt")}
+    info = dict(zip(("n_img", "n_txt", "lambda_img", "lambda_txt"), (float(v) for v in fx["info"])))
+    cov_img, cov_txt = compute_covariances(t["A_img"].cuda(), fac["B_img"], fac["A_txt"], fac["B_txt"], info)
+    cls = SIGLIP if cfg["bias"] else CLIP
+    model = cls(logit_scale=cfg["logit_scale"], logit_bias=cfg["logit_bias"], device="cuda", precision=precision)
+    model.set_covariances(cov_img, cov_txt)
+    with torch.no_grad():
+        out = model(EncoderResult(t["img_e"].cuda(), t["img_a"].cuda()), EncoderResult(t["txt_e"].cuda(), t["txt_a"].cuda()))
+    rows = torch.from_numpy(fx["rows"]).cuda()
+    _check_logits(out.mean[rows], out.var[rows], fx["mean"].astype(np.float64), fx["var"].astype(np.float64),
+                  math.exp(cfg["logit_scale"]), strict=True)
+
+
 def _surrogate_spd(gen, d, scale):
     w = torch.randn(4 * d, d, generator=gen, dtype=torch.float64)
     return ((w.T @ w) / math.sqrt(4 * d) * scale).float()

@@ -1,5 +1,6 @@
 """The CPU oracle against outputs of the reference implementation itself (tests/golden/make_golden.py)."""
 import math
+import sys
 
 import numpy as np
 import pytest
@@ -110,6 +111,32 @@ def test_predictive_config1_shipped_b32_factors(golden_b32):
     np.testing.assert_allclose(var, b["var"], rtol=1e-3)
 
 
+@pytest.mark.parametrize("which", ["l14", "siglip"])
+def test_predictive_on_shipped_l14_and_siglip_factors(which):
+    """The factors the reference SHIPS for ViT-L-14 (A_txt, B_img, B_txt) and SigLIP (A_txt 769^2, B_img, B_txt): three-decade
+    spectra, d = 768 / 769.  Golden = the reference's CLIP / SIGLIP.forward on 48 seeded rows (tests/golden/make_golden.py
+    `shipped`); the oracle must reproduce it from the same packed factors."""
+    sys.path.insert(0, str(GOLDEN_DIR))
+    from make_golden import shipped_problem, sym_from_lower
+
+    fx = dict(np.load(GOLDEN_DIR / f"shipped_{which}.npz"))
+    cfg, t = shipped_problem(which)
+    n_img, n_txt, l_img, l_txt = fx["info"]
+    fac = {k: sym_from_lower(fx[k + "_tril"], cfg["D"] + (cfg["bias"] if k == "A_txt" else 0)) for k in ("A_txt", "B_img", "B_txt")}
+    Ai, Bi = O.covariance(t["A_img"].numpy(), fac["B_img"], n_img, l_img)
+    At, Bt = O.covariance(fac["A_txt"], fac["B_txt"], n_txt, l_txt)
+    rows = fx["rows"]
+    assert (rows == t["rows"].numpy()).all()
+    mean, var = O.predictive(t["img_e"].numpy()[rows], t["img_a"].numpy()[rows], t["txt_e"].numpy(), t["txt_a"].numpy(), Ai, Bi,
+                             At, Bt, cfg["logit_scale"], src_bias=bool(cfg["bias"]), tgt_bias=bool(cfg["bias"]), dtype=np.float64)
+    s = math.exp(cfg["logit_scale"])
+    assert np.abs(mean - fx["mean"]).max() <= 1e-4 * max(np.abs(fx["mean"]).max(), 0.01 * s)
+    np.testing.assert_allclose(var, fx["var"], rtol=2e-4)
+    # the spectra the fp16 quadratic forms have to survive (SURVEY §7): more than two decades between the extreme eigenvalues
+    ev = np.linalg.eigvalsh(fac["A_txt"].astype(np.float64))
+    assert ev.max() / max(ev.min(), 1e-30) > 500
+
+
 def test_epig_fp16_rounding_points(golden):
     p32, t32 = golden["epig_probs_p"], golden["epig_probs_t"]
     np.testing.assert_allclose(O.sample_probas(golden["epig_mean_p"], golden["epig_var_p"], golden["epig_eps_p"]), p32,
@@ -192,6 +219,30 @@ def test_product_prior_precision_matches_reference(golden):
     ld = compute_log_det_kfac(A + torch.eye(24), B + torch.eye(16))
     ref = torch.logdet(A + torch.eye(24)) * 24 + torch.logdet(B + torch.eye(16)) * 16
     assert torch.allclose(ld, ref)
+
+
+def test_factor_spectrum_feeds_prior_precision_and_covariance(golden):
+    """§8(f)#1: ONE eigendecomposition per factor gives the reference's Adam result for lambda (hessians.py:219-265) and the
+    reference's regularised inverses (hessians.py:170-184)."""
+    import torch
+
+    from bayesvlm_b200.hessians import (FactorSpectrum, _compute_covariance, covariance_from_spectra,
+                                        optimize_prior_precision)
+
+    lam0, n, lr, steps = golden["prior_cfg"]
+    proj = torch.nn.Linear(24, 16, bias=False)
+    with torch.no_grad():
+        proj.weight.copy_(torch.from_numpy(golden["prior_W"]))
+    A, B = torch.from_numpy(golden["prior_A"]), torch.from_numpy(golden["prior_B"])
+    spectra = (FactorSpectrum.of(A), FactorSpectrum.of(B))
+    lam = optimize_prior_precision(proj, A, B, lmbda_init=float(lam0), n=float(n), lr=float(lr), num_steps=int(steps),
+                                   device="cpu", spectra=spectra)
+    assert abs(lam.item() - float(golden["prior_lambda"][0])) <= 2e-3 * float(golden["prior_lambda"][0])
+    cov = covariance_from_spectra(spectra[0], spectra[1], float(n), lam.item())
+    ref = _compute_covariance(A, B, torch.tensor(float(n)), torch.tensor(lam.item()))  # torch.linalg.inv, as the reference
+    for ours, theirs in ((cov.A_inv, ref.A_inv), (cov.B_inv, ref.B_inv)):
+        assert ours.dtype == torch.float32
+        assert (ours - theirs).abs().max() <= 1e-5 * theirs.abs().max()
 
 
 # ---------------------------------------------------------------------------------------------------------------------
