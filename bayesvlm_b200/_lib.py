@@ -67,6 +67,7 @@ SIGNATURES = {
          _P, _I, _P, c_size_t, _P],
     ),
     "bvlm_probit_softmax": (c_int, [_P, _P, _I, _I, _I, _P, _P]),
+    "bvlm_mc_softmax_accumulate": (c_int, [_P, _P, _P, _I, _I, _I, _P, _P, _P]),
     "bvlm_epig_operand_k": (c_int, [_I]),
     "bvlm_epig_prepare_supported": (c_int, [_I, _I, c_int]),
     "bvlm_epig_prepare_from_noise": (c_int, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),

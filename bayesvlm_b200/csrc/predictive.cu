@@ -279,4 +279,11 @@ int bvlm_probit_softmax(const float* mean, const float* var, int64_t N, int64_t 
   return launch_probit_softmax(mean, var, N, C, ld, probs, static_cast<cudaStream_t>(stream));
 }
 
+int bvlm_mc_softmax_accumulate(const float* mean, const float* var, const float* eps, int64_t N, int64_t C, int64_t G,
+                               float* acc_probs, float* acc_entropy, void* stream) {
+  if (mean == nullptr || var == nullptr || eps == nullptr || (acc_probs == nullptr && acc_entropy == nullptr)) return BVLM_EINVAL;
+  if (G > 0x7fffffff) return BVLM_EINVAL;
+  return launch_mc_softmax(mean, var, eps, N, C, static_cast<int>(G), acc_probs, acc_entropy, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

@@ -757,6 +757,71 @@ k_probit_softmax(const float* __restrict__ mean, const float* __restrict__ var, 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Monte-Carlo methods of ProbabilisticLogits (vlm.py:68-103 softmax, :142-159 expected_aleatoric_entropy) for a diagonal
+// logit covariance: for G noise draws eps_g [N, C] (one torch.randn call each: the reference's RNG contract)
+//     p_g = softmax(mean + eps_g * std)        acc_p += p_g        acc_h += -sum_j p_gj log p_gj
+// One warp per row, the row's mean / std / running sums in registers (C <= 32 * NI), one pass over the noise: the
+// reference's per-draw sequence (mul, add, softmax, +=: ~13 tensor passes per draw) becomes ONE read of eps_g.  The sums
+// start from the values already in acc_p / acc_h and grow draw by draw in the reference's order (same association).
+// ------------------------------------------------------------------------------------------------
+template <int NI>
+__global__ void __launch_bounds__(ROW_BLOCK)
+k_mc_softmax(const float* __restrict__ mean, const float* __restrict__ var, const float* __restrict__ eps, int64_t N, int64_t C,
+             int G, float* __restrict__ acc_p, float* __restrict__ acc_h) {
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= N) return;
+  const float* m = mean + row * C;
+  const float* v = var + row * C;
+  float mu[NI], sd[NI], ap[NI];
+#pragma unroll
+  for (int i = 0; i < NI; ++i) {
+    const int64_t j = lane + 32 * i;
+    const bool ok = j < C;
+    mu[i] = ok ? m[j] : -INFINITY;  // padded classes: exp(-inf) = 0, never stored
+    sd[i] = ok ? sqrtf(v[j]) : 0.f;
+    ap[i] = (ok && acc_p != nullptr) ? acc_p[row * C + j] : 0.f;
+  }
+  float ah = acc_h != nullptr ? acc_h[row] : 0.f;
+  for (int g = 0; g < G; ++g) {
+    const float* e = eps + (static_cast<int64_t>(g) * N + row) * C;
+    float z[NI];
+    float zmax = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const int64_t j = lane + 32 * i;
+      const float ev = j < C ? __ldcs(e + j) : 0.f;
+      z[i] = __fadd_rn(mu[i], __fmul_rn(ev, sd[i]));  // torch: mean + (randn * std), two roundings
+      zmax = fmaxf(zmax, z[i]);
+    }
+    zmax = warp_max(zmax);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      z[i] = expf(z[i] - zmax);
+      s += z[i];
+    }
+    s = warp_sum(s);
+    float h = 0.f;
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const float p = z[i] / s;
+      ap[i] += p;
+      if (acc_h != nullptr && lane + 32 * i < C) h += p * logf(p);  // (0 * log 0 = NaN, as in the reference)
+    }
+    if (acc_h != nullptr) ah -= warp_sum(h);
+  }
+  if (acc_p != nullptr) {
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const int64_t j = lane + 32 * i;
+      if (j < C) acc_p[row * C + j] = ap[i];
+    }
+  }
+  if (acc_h != nullptr && lane == 0) acc_h[row] = ah;
+}
+
 __global__ void k_symmetrize_scale(float* __restrict__ A, int64_t d, int64_t ld, float scale) {
   const int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t i = blockIdx.y;
@@ -942,6 +1007,22 @@ int launch_col_pow2_scale(const float* x, int64_t n, int64_t d, int64_t ld, int 
   count_launch();
   const int64_t dA = d + (append_one ? 1 : 0);
   k_col_pow2_scale<<<static_cast<unsigned>((dA + 255) / 256), 256, 0, st>>>(amax_bits, d, append_one, scale, unscale);
+  count_launch();
+  BVLM_CUDA_TRY(cudaGetLastError());
+  return BVLM_OK;
+}
+
+int launch_mc_softmax(const float* mean, const float* var, const float* eps, int64_t N, int64_t C, int G, float* acc_p,
+                      float* acc_h, cudaStream_t st) {
+  if (N <= 0 || C <= 0 || G <= 0) return BVLM_OK;
+  if (C > 1024) return BVLM_ENOTSUP;  // the row must fit the warp's registers
+  const unsigned grid = row_grid(N);
+  timing_begin(TAG_PROBIT, st);
+  if (C <= 128) k_mc_softmax<4><<<grid, ROW_BLOCK, 0, st>>>(mean, var, eps, N, C, G, acc_p, acc_h);
+  else if (C <= 256) k_mc_softmax<8><<<grid, ROW_BLOCK, 0, st>>>(mean, var, eps, N, C, G, acc_p, acc_h);
+  else if (C <= 512) k_mc_softmax<16><<<grid, ROW_BLOCK, 0, st>>>(mean, var, eps, N, C, G, acc_p, acc_h);
+  else k_mc_softmax<32><<<grid, ROW_BLOCK, 0, st>>>(mean, var, eps, N, C, G, acc_p, acc_h);
+  timing_end(TAG_PROBIT, st);
   count_launch();
   BVLM_CUDA_TRY(cudaGetLastError());
   return BVLM_OK;

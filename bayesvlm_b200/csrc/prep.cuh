@@ -84,6 +84,8 @@ int launch_col_pow2_scale(const float* x, int64_t n, int64_t d, int64_t ld, int 
                           float* scale, float* unscale, cudaStream_t st);
 
 // Canonical probit softmax (scripts/zeroshot.py:119-120): probs = softmax_j(mean / sqrt(1 + pi/8 var)).
+int launch_mc_softmax(const float* mean, const float* var, const float* eps, int64_t N, int64_t C, int G, float* acc_p,
+                      float* acc_h, cudaStream_t st);
 int launch_probit_softmax(const float* mean, const float* var, int64_t N, int64_t C, int64_t ld, float* probs,
                           cudaStream_t st);
 

@@ -93,6 +93,39 @@ def sample_probas_from_noise(mean: torch.Tensor, var: torch.Tensor, eps: torch.T
     return out
 
 
+_MC_NOISE_BYTES = 1 << 30  # noise of one kernel launch: G draws of [N, C] fp32
+
+
+def _mc_kernel_ok(mean: torch.Tensor, var: torch.Tensor, dim: int) -> bool:
+    """The fused Monte-Carlo kernel handles fp32 CUDA [N, C <= 1024] logits reduced over the class axis."""
+    return (mean.is_cuda and var.is_cuda and mean.dim() == 2 and mean.shape == var.shape and dim in (-1, 1) and
+            mean.dtype == torch.float32 and var.dtype == torch.float32 and 0 < mean.shape[1] <= 1024 and mean.shape[0] > 0 and
+            not (mean.requires_grad or var.requires_grad))
+
+
+def _mc_accumulate(mean: torch.Tensor, var: torch.Tensor, num_samples: int, want_probs: bool = False,
+                   want_entropy: bool = False):
+    """sum_g softmax(mean + eps_g sqrt(var)) and / or sum_g H[softmax(...)] over ``num_samples`` draws (reference vlm.py:86-89,
+    :145-149).  Every draw is its own ``torch.randn(var.shape)`` call on the default generator, like the reference's loop, so
+    a shared seed reproduces its noise on the same device; G draws at a time are consumed by ONE kernel launch."""
+    mean, var = mean.contiguous(), var.contiguous()
+    n, c = mean.shape
+    dev = mean.device
+    acc_p = torch.zeros_like(mean) if want_probs else None
+    acc_h = torch.zeros(n, dtype=torch.float32, device=dev) if want_entropy else None
+    group = max(1, min(num_samples, _MC_NOISE_BYTES // (4 * n * c)))
+    noise = torch.empty((group, n, c), dtype=torch.float32, device=dev)
+    done = 0
+    while done < num_samples:
+        g = min(group, num_samples - done)
+        for i in range(g):
+            torch.randn((n, c), device=dev, out=noise[i])
+        _lib.run(dev, "bvlm_mc_softmax_accumulate", _lib.ptr(mean), _lib.ptr(var), _lib.ptr(noise), n, c, g, _lib.ptr(acc_p),
+                 _lib.ptr(acc_h), _lib.stream_ptr(dev))
+        done += g
+    return acc_p, acc_h
+
+
 @dataclass
 class ProbabilisticLogits:
     """Gaussian over logits: mean [N,C], var [N,C] (or full covariances [N,C,C]); reference vlm.py:63-204."""
@@ -110,6 +143,8 @@ class ProbabilisticLogits:
             diag = self.var.diagonal(dim1=-2, dim2=-1)
             return torch.softmax(self.mean / torch.sqrt(1 + torch.pi / 8 * diag), dim=dim)
         if self.var.ndim == 2:
+            if _mc_kernel_ok(self.mean, self.var, dim):
+                return _mc_accumulate(self.mean, self.var, num_samples, want_probs=True)[0] / num_samples
             std = self.var.sqrt()
             acc = torch.zeros_like(self.mean)
             for _ in range(num_samples):
@@ -161,6 +196,8 @@ class ProbabilisticLogits:
 
     def expected_aleatoric_entropy(self, num_samples=400, dim=-1):
         total = 0
+        if self.var.ndim == 2 and num_samples > 0 and _mc_kernel_ok(self.mean, self.var, dim):
+            return _mc_accumulate(self.mean, self.var, num_samples, want_entropy=True)[1] / num_samples
         if self.var.ndim == 2:
             std = self.var.sqrt()
             for _ in range(num_samples):

@@ -118,6 +118,14 @@ int bvlm_predictive(const float* E, int64_t N, int64_t D, int64_t lde, const flo
 int bvlm_probit_softmax(const float* mean, const float* var, int64_t N, int64_t C, int64_t ld, float* probs,
                         void* stream);
 
+/* T2 -- Monte-Carlo methods of ProbabilisticLogits with a diagonal logit covariance (bayesvlm/vlm.py:68-103 softmax,
+ * :142-159 expected_aleatoric_entropy): for G noise draws eps [G, N, C] (one torch.randn call each)
+ *   acc_probs [N, C] += softmax(mean + eps_g * sqrt(var)),  acc_entropy [N] += -sum_j p log p   (either may be NULL),
+ * added draw by draw onto the values already in the accumulators (the reference's summation order).  C <= 1024, contiguous rows;
+ * returns BVLM_ENOTSUP otherwise (the caller keeps the device expression). */
+int bvlm_mc_softmax_accumulate(const float* mean, const float* var, const float* eps, int64_t N, int64_t C, int64_t G,
+                               float* acc_probs, float* acc_entropy, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * E0 -- MC class probabilities  (bayesvlm/vlm.py:116-123):  probs[n,k,:] = softmax(mean[n,:] + eps[k,n,:] sqrt(var[n,:]))
  * eps [K, N, Cl] fp32 comes from torch.randn under the caller's torch.manual_seed (RNG parity with the reference);
