@@ -328,6 +328,13 @@ int bvlm_syrk_f32acc(const float* X, int64_t n, int64_t d, int64_t ldx, int appe
   const int tri = plan.m_tiles * (plan.m_tiles + 1) / 2;
   int splits = (device_sm_count() / 2) / tri;
   if (splits < 1) splits = 1;
+  // Bound the length of one tensor-core accumulation chain: the fp32 accumulator truncates, which biases a sum of n squares
+  // by about -5.4e-9 per row of the chain (measured, scripts/syrk_bias.py: -5.5e-4 at n = 2^20 rows in 12 chains).  Chains of at
+  // most 128 K blocks (8192 rows) keep the bias below 5e-5 -- the size of the fp16 operand rounding itself; every extra
+  // partial tile costs one red.global.add pass (200 MB at n = 2^20, d = 768).
+  constexpr int SYRK_MAX_CHAIN_KB = 128;
+  const int min_splits = (plan.kb_total + SYRK_MAX_CHAIN_KB - 1) / SYRK_MAX_CHAIN_KB;
+  if (splits < min_splits) splits = min_splits;
   if (splits > plan.kb_total) splits = plan.kb_total;
   plan.splits = splits;
   plan.idesc = make_idesc_f16(GEMM2_BM, BN, FMT_F16, FMT_F16, 1, 1);

@@ -149,6 +149,24 @@ def test_syrk_vs_fp64(shape):
     _check_factor(A2, 1.5 * ref)
 
 
+def test_syrk_accumulation_bias_is_bounded_for_long_row_blocks():
+    """A rank's whole contiguous block goes through ONE launch (config 2: 2^20 rows).  The tensor cores' fp32 accumulator
+    truncates, which biases sums of squares by ~ -5e-9 per row of an accumulation chain (scripts/syrk_bias.py: -5.5e-4 at 2^20
+    rows before the chain length was bounded); the split-K schedule must keep it at the level of the operand rounding."""
+    from bayesvlm_b200.hessians import syrk_accumulate
+
+    n, d = 1 << 20, 64
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    X = torch.randn(n, d, generator=gen, device="cuda")
+    A = syrk_accumulate(X).double()
+    ref = torch.zeros(d, d, dtype=torch.float64, device="cuda")
+    for lo in range(0, n, 1 << 18):
+        xb = X[lo:lo + (1 << 18)].double()
+        ref += xb.T @ xb
+    assert float((A - ref).norm() / ref.norm()) <= 1e-4
+    assert float(((A.diagonal() - ref.diagonal()) / ref.diagonal()).abs().max()) <= 1e-4
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # K0
 # ----------------------------------------------------------------------------------------------------------------------
