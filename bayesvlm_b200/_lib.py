@@ -73,7 +73,8 @@ SIGNATURES = {
     "bvlm_epig_prepare_from_noise": (c_int, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
     "bvlm_epig_prepare_from_probs": (c_int, [_P, _I, _I, _I, _P, _P, _P]),
     "bvlm_epig_prepare_pair_from_noise": (c_int, [_P, _P, _P, _I, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _P]),
-    "bvlm_epig_joint_entropy_operands": (c_int, [_P, _I, _P, _I, _I, _I, _I, _P, _P]),
+    "bvlm_epig_joint_operands_workspace_bytes": (c_size_t, [_I, _I, _I, _I]),
+    "bvlm_epig_joint_entropy_operands": (c_int, [_P, _I, _P, _I, _I, _I, _I, _P, _P, c_size_t, _P]),
     "bvlm_epig_sample_probs": (c_int, [_P, _P, _P, _I, _I, _I, _P, _P]),
     "bvlm_epig_marginal_entropy_f16": (c_int, [_P, _I, _I, _I, _P, _P]),
     "bvlm_epig_joint_workspace_bytes": (c_size_t, [_I, _I, _I, _I]),

@@ -383,30 +383,34 @@ int launch_epig_prepare(PrepSide sa, PrepSide sb, int64_t K, int64_t Cl, cudaStr
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// E2 epilogue. Tile rows are (pool row, class) pairs packed ppt = floor(128/Cl) pool rows per 128-row CTA slab; tile
-// columns are the flattened (target, class) axis. Row panels: each CTA pair walks all column tiles of its pool rows.
+// E2 epilogue. Tile rows are the FLATTENED (pool row, class) axis of the operand [Np * Cl, Kp] -- every lane of every
+// 128-row slab carries a real row whatever Cl is (the first version packed floor(128 / Cl) whole pool rows per slab: 51 %
+// of the lanes at Cl = 65, and Cl > 128 was not supported); tile columns are the flattened (target, class) axis.  Row
+// panels: each CTA pair walks all column tiles of its 256 flat rows.
 // Per element (torch's CUDA rounding points; two elements at a time):
 //   h = fp16(acc); j = fp16(h * (1/K)); t = fp16(j * log j)  [fp32 log and product, one rounding]; sum += t  (fp32)
+// Per (pool row, column chunk) the sum over the row's Cl classes may span slabs, CTAs and CTA pairs: every slab adds its
+// share -- summed in double from the per-thread fp32 partials -- to S[pool row, chunk] with one double atomicAdd, and
+// k_epig_joint_finalize applies the remaining roundings  Hjoint[p] = sum_chunks fp16( fp16(-S) * (1/N_t) )  in chunk order.
 // ---------------------------------------------------------------------------------------------------------------
 template <int BN>
 struct EpiEpigJoint {
   static constexpr size_t scratch_bytes(int warps) { return (warps / 4) * 128 * sizeof(float); }
   struct Params {
-    float* Hjoint;      // [Np]
-    int64_t Np;
+    double* S;            // [Np, n_chunks], zeroed by the host
+    int64_t rows_total;   // Np * Cl
     int Cl;
-    int ppt;            // pool rows per 128-row slab
+    int n_chunks;
     int tiles_per_chunk;  // col_chunk / BN
-    float inv_K;        // fp32(1 / K): torch's CUDA `tensor / python_scalar` multiplies by the fp32 reciprocal
-    float inv_Nt;       // fp32(1 / N_t), same rule
+    float inv_K;          // fp32(1 / K): torch's CUDA `tensor / python_scalar` multiplies by the fp32 reciprocal
   };
   struct State {
-    float chunk_acc;  // running fp32 sum of fp16(xlogy) over the current column chunk (this thread's row, its column half)
-    float hj;         // accumulated joint entropy of the pool row (held by the class-0 thread of the lower column half)
+    float chunk_acc;  // running fp32 sum of fp16(xlogy) over the current column chunk (this thread's row, its column group)
+    int64_t p;        // pool row of this thread's flat row
+    int head_rows;    // > 0: this thread sums that many consecutive flat rows of pool row p (the part inside this slab)
+    int chunk;        // current column chunk
+    int seen;         // tiles consumed of the current column chunk
     bool valid;
-    bool leader;
-    int64_t p;
-    int cur_chunk;  // tiles consumed of the current column chunk
   };
   static constexpr bool ALL_CHUNKS = false;
   static constexpr bool UNROLL_CHUNKS = false;
@@ -420,35 +424,41 @@ struct EpiEpigJoint {
     epi_bar_sync(ctx);
     sts_f32(s + 4u * static_cast<uint32_t>((ctx.wid / 4) * 128 + r), st.valid ? st.chunk_acc : 0.f);
     epi_bar_sync(ctx);
-    if (st.leader) {
-      // The fp16 rounding of this sum decides the score; it is accumulated in double (Cl * column groups addends of up to
-      // ~1e3, once per chunk and pool row) so that only the reference's own fp32 summation order can move it across a
-      // rounding boundary, not ours as well.
+    if (st.head_rows > 0) {
+      // The fp16 rounding of the chunk sum decides the score; it is accumulated in double (from here to the finalize
+      // kernel) so that only the reference's own fp32 summation order can move it across a rounding boundary, not ours.
       double sum = 0.0;
       for (int h = 0; h < ctx.n_warps / 4; ++h)
-        for (int c = 0; c < p.Cl; ++c) sum += static_cast<double>(lds_f32(s + 4u * static_cast<uint32_t>(h * 128 + r + c)));
-      const float neg = -round_f16(static_cast<float>(sum));  // fp16(sum) then negate
-      st.hj += round_f16(neg * p.inv_Nt);              // "/ N_t" on a Half tensor
+        for (int c = 0; c < st.head_rows; ++c) sum += static_cast<double>(lds_f32(s + 4u * static_cast<uint32_t>(h * 128 + r + c)));
+      atomicAdd(p.S + st.p * p.n_chunks + st.chunk, sum);
     }
     st.chunk_acc = 0.f;
   }
 
   __device__ static void item_begin(State& st, const Params& p, const EpiCtx& ctx, const TileCoord& tc) {
     const int r = ctx.ew * 32 + ctx.lane;
-    const int pl = r / p.Cl;
-    st.p = static_cast<int64_t>(tc.row0 / GEMM_BM) * p.ppt + pl;
-    st.valid = (pl < p.ppt) && (st.p < p.Np);
-    st.leader = st.valid && (r - pl * p.Cl == 0) && ctx.wid < 4;
+    const int64_t flat = static_cast<int64_t>(tc.row0) + r;  // tc.row0: first flat row of this CTA's 128-row slab
+    st.valid = flat < p.rows_total;
+    st.p = flat / p.Cl;
+    const int c = static_cast<int>(flat - st.p * p.Cl);
+    st.head_rows = 0;
+    if (st.valid && ctx.wid < 4 && (r == 0 || c == 0)) {  // first row of pool row p inside this slab
+      int n = p.Cl - c;
+      if (n > GEMM_BM - r) n = GEMM_BM - r;
+      if (n > p.rows_total - flat) n = static_cast<int>(p.rows_total - flat);
+      st.head_rows = n;
+    }
     st.chunk_acc = 0.f;
-    st.hj = 0.f;
-    st.cur_chunk = tc.n % p.tiles_per_chunk;  // tiles of the current column chunk seen so far (a panel starts at tc.n)
+    st.chunk = tc.n / p.tiles_per_chunk;
+    st.seen = tc.n - st.chunk * p.tiles_per_chunk;  // a panel starts at tc.n
   }
   __device__ static void tile_begin(State& st, const Params& p, const EpiCtx& ctx, const TileCoord&) {
-    if (st.cur_chunk == p.tiles_per_chunk) {  // (a counter, not tc.n / tiles_per_chunk: no division per tile)
+    if (st.seen == p.tiles_per_chunk) {  // (a counter, not tc.n / tiles_per_chunk: no division per tile)
       flush(st, p, ctx);
-      st.cur_chunk = 0;
+      ++st.chunk;
+      st.seen = 0;
     }
-    ++st.cur_chunk;
+    ++st.seen;
   }
   __device__ static void chunk(State& st, const Params& p, const EpiCtx&, const TileCoord&, float (&v)[32], int) {
     // columns beyond N are TMA zero fill: j = 0 -> 0 * log 0 = NaN, which the NaN-suppressing min below turns into 0
@@ -469,11 +479,21 @@ struct EpiEpigJoint {
     st.chunk_acc += s0 + s1;
   }
   __device__ static void tile_end(State&, const Params&, const EpiCtx&, const TileCoord&) {}
-  __device__ static void item_end(State& st, const Params& p, const EpiCtx& ctx, const TileCoord&) {
-    flush(st, p, ctx);
-    if (st.leader) p.Hjoint[st.p] = st.hj;
-  }
+  __device__ static void item_end(State& st, const Params& p, const EpiCtx& ctx, const TileCoord&) { flush(st, p, ctx); }
 };
+
+// Hjoint[p] = sum over chunks (in order, fp32) of fp16( fp16(-S[p, chunk]) * fp32(1 / N_t) )        (epig.py:391-393)
+__global__ void k_epig_joint_finalize(const double* __restrict__ S, int64_t Np, int n_chunks, float inv_Nt,
+                                      float* __restrict__ Hjoint) {
+  const int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (p >= Np) return;
+  float hj = 0.f;
+  for (int ch = 0; ch < n_chunks; ++ch) {
+    const float neg = -round_f16(static_cast<float>(S[p * n_chunks + ch]));  // fp16(sum) then negate
+    hj += round_f16(neg * inv_Nt);                                             // "/ N_t" on a Half tensor
+  }
+  Hjoint[p] = hj;
+}
 
 }  // namespace
 
@@ -525,39 +545,50 @@ int bvlm_epig_marginal_entropy_f16(const void* probs16, int64_t N, int64_t K, in
   return bvlm_epig_prepare_from_probs(probs16, N, K, Cl, nullptr, out16, stream);
 }
 
+size_t bvlm_epig_joint_operands_workspace_bytes(int64_t Np, int64_t Nt, int64_t Cl, int64_t col_chunk) {
+  if (Np <= 0 || Nt <= 0 || Cl <= 0 || col_chunk <= 0) return 0;
+  const int64_t n_chunks = ceil_div_i64(Nt * Cl, col_chunk);
+  return static_cast<size_t>(Np * n_chunks) * sizeof(double) + 256;
+}
+
 int bvlm_epig_joint_entropy_operands(const void* poolP, int64_t Np, const void* targP, int64_t Nt, int64_t K, int64_t Cl,
-                                     int64_t col_chunk, float* Hjoint, void* stream) {
-  if (poolP == nullptr || targP == nullptr || Hjoint == nullptr) return BVLM_EINVAL;
+                                     int64_t col_chunk, float* Hjoint, void* ws, size_t ws_bytes, void* stream) {
+  if (poolP == nullptr || targP == nullptr || Hjoint == nullptr || ws == nullptr) return BVLM_EINVAL;
   if (Np <= 0 || Nt <= 0 || K <= 0 || Cl <= 0) return BVLM_EINVAL;
-  if (Cl > 128 || col_chunk <= 0 || (col_chunk % EPIG_BN) != 0) return BVLM_ENOTSUP;
-  if (Nt * Cl > 0x7fffffff || Np > 0x7fffffff) return BVLM_EINVAL;
-  if ((reinterpret_cast<uintptr_t>(poolP) & 15) != 0 || (reinterpret_cast<uintptr_t>(targP) & 15) != 0) return BVLM_EINVAL;
+  if (col_chunk <= 0 || (col_chunk % EPIG_BN) != 0) return BVLM_ENOTSUP;
+  if (Nt * Cl > 0x7fffffff || Np * Cl > 0x7fffffff) return BVLM_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(poolP) & 15) != 0 || (reinterpret_cast<uintptr_t>(targP) & 15) != 0 ||
+      (reinterpret_cast<uintptr_t>(ws) & 7) != 0)
+    return BVLM_EINVAL;
+  if (ws_bytes < bvlm_epig_joint_operands_workspace_bytes(Np, Nt, Cl, col_chunk)) return BVLM_EWORKSPACE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t Kp = pad64(K);
-  const int ppt = static_cast<int>(128 / Cl);
+  const int n_chunks = static_cast<int>(ceil_div_i64(Nt * Cl, col_chunk));
+  double* S = static_cast<double*>(ws);
+  BVLM_CUDA_TRY(cudaMemsetAsync(S, 0, static_cast<size_t>(Np) * n_chunks * sizeof(double), st));
   CUtensorMap tmA, tmB;
-  int rc = make_tmap_3d(&tmA, poolP, TM_F16, static_cast<uint64_t>(Kp), static_cast<uint64_t>(Cl),
-                        static_cast<uint64_t>(Np), static_cast<uint64_t>(Kp) * 2, static_cast<uint64_t>(Cl * Kp) * 2,
-                        GEMM_BK, static_cast<uint32_t>(Cl), static_cast<uint32_t>(ppt), 1);
-  if (rc) return rc;
+  int rc;
+  Operand16 opA{poolP, Np * Cl, Kp, FMT_F16};
   Operand16 opB{targP, Nt * Cl, Kp, FMT_F16};
+  if ((rc = operand_tmap<GEMM_BM>(&tmA, opA))) return rc;
   if ((rc = operand_tmap<EPIG_BN / 2>(&tmB, opB))) return rc;  // CTA pairs: each CTA loads half of the B tile
-  const int m_tiles = static_cast<int>(ceil_div_i64(Np, 2 * ppt));  // a CTA pair covers 2 * ppt pool rows
-  GemmPlan plan = make_plan2<EPIG_BN>(m_tiles * GEMM2_BM, static_cast<int>(Nt * Cl), static_cast<int>(Kp), SCHED_ROW_PANEL, 1,
+  GemmPlan plan = make_plan2<EPIG_BN>(static_cast<int>(Np * Cl), static_cast<int>(Nt * Cl), static_cast<int>(Kp), SCHED_ROW_PANEL, 1,
                                       FMT_F16);
-  plan.m_tiles = m_tiles;
-  plan.a_is_3d = 1;
-  plan.a_outer_step = ppt;
-  plan.a_tx_bytes = static_cast<uint32_t>(ppt * Cl * GEMM_BK * 2);
-  EpiEpigJoint<EPIG_BN>::Params ep{Hjoint, Np, static_cast<int>(Cl), ppt, static_cast<int>(col_chunk / EPIG_BN),
-                                   static_cast<float>(1.0 / static_cast<double>(K)),
-                                   static_cast<float>(1.0 / static_cast<double>(Nt))};
-  return launch_gemm2<EPIG_BN, 6, 16, EpiEpigJoint<EPIG_BN>>(tmA, tmB, plan, ep, st, TAG_EPIG_JOINT);
+  EpiEpigJoint<EPIG_BN>::Params ep{S, Np * Cl, static_cast<int>(Cl), n_chunks, static_cast<int>(col_chunk / EPIG_BN),
+                                   static_cast<float>(1.0 / static_cast<double>(K))};
+  if ((rc = launch_gemm2<EPIG_BN, 6, 16, EpiEpigJoint<EPIG_BN>>(tmA, tmB, plan, ep, st, TAG_EPIG_JOINT))) return rc;
+  k_epig_joint_finalize<<<static_cast<unsigned>(ceil_div_i64(Np, 256)), 256, 0, st>>>(
+      S, Np, n_chunks, static_cast<float>(1.0 / static_cast<double>(Nt)), Hjoint);
+  count_launch();
+  BVLM_CUDA_TRY(cudaGetLastError());
+  return BVLM_OK;
 }
 
 size_t bvlm_epig_joint_workspace_bytes(int64_t Np, int64_t Nt, int64_t K, int64_t Cl) {
   const int64_t Kp = pad64(K);
-  return static_cast<size_t>(round_up_i64(Np * Cl * Kp * 2, 256) + round_up_i64(Nt * Cl * Kp * 2, 256) + 1024);
+  // operands + the per-(pool row, chunk) sums at the smallest supported chunk (one column tile)
+  return static_cast<size_t>(round_up_i64(Np * Cl * Kp * 2, 256) + round_up_i64(Nt * Cl * Kp * 2, 256) + 1024) +
+         bvlm_epig_joint_operands_workspace_bytes(Np, Nt, Cl, EPIG_BN);
 }
 
 int bvlm_epig_joint_entropy_f16(const void* pool16, int64_t Np, const void* targ16, int64_t Nt, int64_t K, int64_t Cl,
@@ -567,12 +598,15 @@ int bvlm_epig_joint_entropy_f16(const void* pool16, int64_t Np, const void* targ
   if (ws_bytes < bvlm_epig_joint_workspace_bytes(Np, Nt, K, Cl)) return BVLM_EWORKSPACE;
   if ((reinterpret_cast<uintptr_t>(ws) & 255) != 0) return BVLM_EINVAL;
   const int64_t Kp = pad64(K);
-  void* poolP = ws;
-  void* targP = static_cast<uint8_t*>(ws) + round_up_i64(Np * Cl * Kp * 2, 256);
+  uint8_t* base = static_cast<uint8_t*>(ws);
+  void* poolP = base;
+  void* targP = base + round_up_i64(Np * Cl * Kp * 2, 256);
+  void* sums = base + round_up_i64(Np * Cl * Kp * 2, 256) + round_up_i64(Nt * Cl * Kp * 2, 256);
+  const size_t sums_bytes = ws_bytes - static_cast<size_t>(static_cast<uint8_t*>(sums) - base);
   int rc = bvlm_epig_prepare_from_probs(pool16, Np, K, Cl, poolP, nullptr, stream);
   if (rc) return rc;
   if ((rc = bvlm_epig_prepare_from_probs(targ16, Nt, K, Cl, targP, nullptr, stream))) return rc;
-  return bvlm_epig_joint_entropy_operands(poolP, Np, targP, Nt, K, Cl, col_chunk, Hjoint, stream);
+  return bvlm_epig_joint_entropy_operands(poolP, Np, targP, Nt, K, Cl, col_chunk, Hjoint, sums, sums_bytes, stream);
 }
 
 }  // extern "C"

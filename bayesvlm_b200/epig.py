@@ -31,7 +31,7 @@ def _prepare_fits(k: int, cl: int, from_noise: bool) -> bool:
 
 
 def _joint_fused_ok(k: int, cl: int, chunk_size: int) -> bool:
-    return cl <= 128 and chunk_size % _JOINT_TILE_N == 0 and chunk_size > 0
+    return chunk_size % _JOINT_TILE_N == 0 and chunk_size > 0
 
 
 def prepare_from_probs(probs: torch.Tensor, want_operand: bool = True, want_entropy: bool = True):
@@ -107,8 +107,9 @@ def joint_entropy_from_operands(oper_pool: torch.Tensor, oper_targ: torch.Tensor
     n_t = oper_targ.shape[0]
     dev = oper_pool.device
     out = torch.empty(n_p, dtype=torch.float32, device=dev)
+    ws = _lib.workspace(dev, lib.bvlm_epig_joint_operands_workspace_bytes(n_p, n_t, cl, int(chunk_size)), tag="epig_joint")
     _lib.run(dev, "bvlm_epig_joint_entropy_operands", _lib.ptr(oper_pool), n_p, _lib.ptr(oper_targ), n_t, k, cl,
-             int(chunk_size), _lib.ptr(out), _lib.stream_ptr(dev))
+             int(chunk_size), _lib.ptr(out), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev))
     return out
 
 

@@ -154,8 +154,11 @@ int bvlm_epig_prepare_from_probs(const void* probs16, int64_t N, int64_t K, int6
 int bvlm_epig_prepare_pair_from_noise(const float* mean_a, const float* var_a, const float* eps_a, int64_t Na, void* oper_a,
                                       void* marg_a, const float* mean_b, const float* var_b, const float* eps_b, int64_t Nb,
                                       void* oper_b, void* marg_b, int64_t K, int64_t Cl, void* stream);
+/* joint-entropy term from the permuted operands; ws: caller-owned scratch of bvlm_epig_joint_operands_workspace_bytes
+ * (per-(pool row, column chunk) sums in double), 8-byte aligned.  Any Cl (a pool row's classes may span CTAs). */
+size_t bvlm_epig_joint_operands_workspace_bytes(int64_t Np, int64_t Nt, int64_t Cl, int64_t col_chunk);
 int bvlm_epig_joint_entropy_operands(const void* poolP, int64_t Np, const void* targP, int64_t Nt, int64_t K, int64_t Cl,
-                                     int64_t col_chunk, float* Hjoint, void* stream);
+                                     int64_t col_chunk, float* Hjoint, void* ws, size_t ws_bytes, void* stream);
 int bvlm_epig_sample_probs(const float* mean, const float* var, const float* eps, int64_t N, int64_t K, int64_t Cl,
                            void* probs16, void* stream);
 int bvlm_epig_marginal_entropy_f16(const void* probs16, int64_t N, int64_t K, int64_t Cl, void* out16, void* stream);

@@ -176,6 +176,8 @@ def test_marginal_entropy_golden_and_generic_dtype(golden):
 @pytest.mark.parametrize("cfg", [dict(Np=45, Nt=30, K=16, Cl=5, chunk=256), dict(Np=300, Nt=200, K=100, Cl=10, chunk=512),
                                  dict(Np=257, Nt=129, K=64, Cl=65, chunk=4096), dict(Np=64, Nt=77, K=33, Cl=128, chunk=1024),
                                  dict(Np=1000, Nt=700, K=100, Cl=10, chunk=4096),
+                                 dict(Np=37, Nt=41, K=20, Cl=200, chunk=2048),         # a pool row spans CTAs (ImageNet-R: 200 classes)
+                                 dict(Np=9, Nt=12, K=8, Cl=300, chunk=1024),           # ... and CTA pairs
                                  dict(Np=4096, Nt=10000, K=100, Cl=10, chunk=4096),    # config 5, primary
                                  dict(Np=4096, Nt=10000, K=100, Cl=65, chunk=4096)])   # config 5, secondary (OfficeHome)
 def test_epig_scores_vs_reference_sequence_on_same_gpu(cfg):
