@@ -577,20 +577,7 @@ int bvlm_epig_joint_entropy_operands(const void* poolP, int64_t Np, const void* 
   // Row panels are cut into column ranges so that the items fill whole rounds of the CTA pairs: a 4096-row pool chunk at
   // Cl = 10 is 160 panels = 2.16 rounds of 74 pairs (72 % of the machine busy); 6 ranges each make 960 items = 12.97 rounds.
   // (Ranges need not be chunk aligned: a (pool row, chunk) sum is the atomic sum of whatever items cover it.)
-  {
-    const int pairs = device_sm_count() / 2;
-    int best = 1;
-    double best_eff = 0.0;
-    for (int sp = 1; sp <= 16 && sp <= plan.n_tiles; ++sp) {
-      const long long items = static_cast<long long>(plan.m_tiles) * sp;
-      const double eff = static_cast<double>(items) / static_cast<double>(ceil_div_i64(items, pairs) * pairs);
-      if (eff > best_eff + 0.02) {  // prefer fewer ranges (each reloads its A panel and flushes its chunk sums)
-        best_eff = eff;
-        best = sp;
-      }
-    }
-    plan.splits = best;
-  }
+  plan.splits = balanced_panel_splits(plan.m_tiles, plan.n_tiles, device_sm_count() / 2, 16);
   EpiEpigJoint<EPIG_BN>::Params ep{S, Np * Cl, static_cast<int>(Cl), n_chunks, static_cast<int>(col_chunk / EPIG_BN),
                                    static_cast<float>(1.0 / static_cast<double>(K))};
   if ((rc = launch_gemm2<EPIG_BN, 6, 16, EpiEpigJoint<EPIG_BN>>(tmA, tmB, plan, ep, st, TAG_EPIG_JOINT))) return rc;

@@ -179,6 +179,25 @@ __device__ __forceinline__ TileCoord plan_tile_at(const GemmPlan& p, const TileC
   return t;
 }
 
+// Number of ranges (1 .. max_splits) to cut every panel into so that `panels * splits` items fill whole rounds of `pairs`
+// persistent CTA pairs: the smallest count whose round efficiency is within 2 % of the best (each extra range reloads the
+// panel's stationary operand and flushes its partial results once more).  Host side.
+inline int balanced_panel_splits(int panels, int inner_tiles, int pairs, int max_splits) {
+  if (panels <= 0 || pairs <= 0) return 1;
+  if (max_splits > inner_tiles) max_splits = inner_tiles;
+  if (max_splits < 1) max_splits = 1;
+  auto eff = [&](int sp) {
+    const long long items = static_cast<long long>(panels) * sp;
+    const long long rounds = (items + pairs - 1) / pairs;
+    return static_cast<double>(items) / static_cast<double>(rounds * pairs);
+  };
+  double best = 0.0;
+  for (int sp = 1; sp <= max_splits; ++sp) best = eff(sp) > best ? eff(sp) : best;
+  for (int sp = 1; sp <= max_splits; ++sp)
+    if (eff(sp) >= best - 0.02) return sp;
+  return 1;
+}
+
 // Per-thread view the epilogue functors get.
 struct EpiCtx {
   int ew;          // TMEM lane quadrant 0..3 of this warp (rows 32*ew .. 32*ew+31 of the CTA's slab)

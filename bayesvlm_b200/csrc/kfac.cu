@@ -148,13 +148,9 @@ int ggn_impl(const float* X, int64_t B, int64_t ldx, const float* Y, int64_t C, 
   int* pivot = g.pivot;
   if (!siglip) {
     GemmPlan p1 = logit_plan(SCHED_ROW_PANEL);
-    int S = 1;
-    if (p1.m_tiles < 4 * pairs) {
-      S = (8 * pairs + p1.m_tiles - 1) / p1.m_tiles;
-      if (S > p1.n_tiles) S = p1.n_tiles;
-      if (S > GGN_ROWSTAT_SPLITS_MAX) S = GGN_ROWSTAT_SPLITS_MAX;
-      if (S < 1) S = 1;
-    }
+    // whole rounds of the CTA pairs (B = 32768: 128 panels x 4 ranges = 512 items = 6.92 rounds, 98.8 % of the machine busy;
+    // the first version's 5 ranges made 8.65 rounds = 96 %)
+    const int S = balanced_panel_splits(p1.m_tiles, p1.n_tiles, pairs, GGN_ROWSTAT_SPLITS_MAX);
     p1.splits = S;
     EpiRowLse<GGN_BN>::Params e1{g.rowmax2, g.rest, g.pivot, s * kLog2e / op2, S};
     if (ggn_pairs_env() == 2 && prec != 3) {
@@ -178,12 +174,7 @@ int ggn_impl(const float* X, int64_t B, int64_t ldx, const float* Y, int64_t C, 
   {
     GemmPlan p2 = logit_plan(SCHED_COL_PANEL);
     // cut every column panel into M ranges so that all SMs get an even share; q is then accumulated atomically
-    int ps = 1;
-    if (p2.n_tiles < 4 * pairs) {
-      ps = (8 * pairs + p2.n_tiles - 1) / p2.n_tiles;
-      if (ps > p2.m_tiles) ps = p2.m_tiles;
-      if (ps < 1) ps = 1;
-    }
+    const int ps = balanced_panel_splits(p2.n_tiles, p2.m_tiles, pairs, 16);
     p2.splits = ps;
     // both CTAs of a pair (and every M range) contribute to the same q columns: always accumulate atomically
     BVLM_CUDA_TRY(cudaMemsetAsync(g.q, 0, static_cast<size_t>(C) * sizeof(float), st));
