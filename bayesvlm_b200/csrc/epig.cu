@@ -80,13 +80,16 @@ inline PrepLayout prep_layout_for(int64_t R, int64_t K, int64_t Cl, int64_t Kp, 
 }
 
 inline PrepLayout prep_layout(int64_t K, int64_t Cl, int64_t Kp, bool from_noise) {
-  if (Cl <= 16) {
-    const PrepLayout L = prep_layout_for(PREP_ROWS, K, Cl, Kp, from_noise);
-    if (L.bytes <= PREP_SMEM_MAX) return L;
+  PrepLayout L{};
+  if (Cl <= 16) {  // register-resident softmax with a compile-time class count: 4, 2 or 1 rows per block, whatever fits
+    for (int r : {PREP_ROWS, 2, 1}) {
+      L = prep_layout_for(r, K, Cl, Kp, from_noise);
+      if (L.bytes <= PREP_SMEM_MAX) return L;
+    }
+    L.R = 0;
+    return L;
   }
-  PrepLayout L = prep_layout_for(1, K, Cl, Kp, from_noise);
-  if (Cl <= 16) L.estride = static_cast<int>(Cl | 1);  // (generic kernel: scalar reads)
-  if (Cl <= 16) L.bytes = L.off_eps + (from_noise ? static_cast<size_t>(K) * L.estride * 4 : 0);
+  L = prep_layout_for(1, K, Cl, Kp, from_noise);
   if (L.bytes > PREP_SMEM_MAX) L.R = 0;
   return L;
 }
@@ -159,7 +162,7 @@ __device__ __forceinline__ void softmax_row_f16(const float* __restrict__ ep, co
   }
 }
 
-// CL > 0: compile-time class count (<= 16), R = PREP_ROWS.  CL == 0: any class count, one row per block, three sweeps.
+// CL > 0: compile-time class count (<= 16), R = 4, 2 or 1 rows per block.  CL == 0: any class count, one row per block, three sweeps.
 // One side (pool or target set) of a prepare launch.
 struct PrepSide {
   const float* mean;
@@ -173,7 +176,7 @@ struct PrepSide {
   int piece;  // floats per cp.async of the noise fetch (4, 2 or 1: alignment of this side's runs)
 };
 
-// CL > 0: compile-time class count (<= 16), R = PREP_ROWS.  CL == 0: any class count, one row per block, three sweeps.
+// CL > 0: compile-time class count (<= 16), R = 4, 2 or 1 rows per block.  CL == 0: any class count, one row per block, three sweeps.
 // Blocks [0, blocks0) work on side a, the rest on side b (EPIG prepares the target set and a pool chunk in ONE launch).
 template <bool FROM_NOISE, int CL>
 __global__ void __launch_bounds__(PREP_THREADS)
@@ -329,11 +332,11 @@ int launch_prepare_variant(unsigned grid, unsigned blocks0, const PrepLayout& L,
 }
 
 // cp.async piece (floats): every (sample, block) run must start on a piece boundary in global AND shared memory
-inline int prep_piece(const float* eps, int64_t N, int64_t Cl, bool fixed_cl) {
+inline int prep_piece(const float* eps, int64_t N, int64_t Cl, int R, int estride, bool fixed_cl) {
   if (!fixed_cl || eps == nullptr) return 1;
   const uintptr_t a = reinterpret_cast<uintptr_t>(eps);
-  if (Cl % 2 == 0 && (a & 15) == 0 && (N * Cl) % 4 == 0) return 4;  // (shared rows of even class counts are 16-byte aligned)
-  if (Cl % 2 == 0 && (a & 7) == 0) return 2;
+  for (int p : {4, 2})
+    if ((a % (4 * p)) == 0 && (N * Cl) % p == 0 && (static_cast<int64_t>(R) * Cl) % p == 0 && estride % p == 0) return p;
   return 1;
 }
 
@@ -352,9 +355,9 @@ int launch_epig_prepare(PrepSide sa, PrepSide sb, int64_t K, int64_t Cl, cudaStr
   if (L.R <= 0) return BVLM_ENOTSUP;  // one row's tiles do not fit shared memory
   const unsigned blocks0 = static_cast<unsigned>(ceil_div_i64(sa.N, L.R));
   const unsigned grid = blocks0 + static_cast<unsigned>(sb.N > 0 ? ceil_div_i64(sb.N, L.R) : 0);
-  const bool fixed_cl = from_noise && Cl <= 16 && L.R == PREP_ROWS;
-  sa.piece = prep_piece(sa.eps, sa.N, Cl, fixed_cl);
-  sb.piece = prep_piece(sb.eps, sb.N, Cl, fixed_cl);
+  const bool fixed_cl = from_noise && Cl <= 16;
+  sa.piece = prep_piece(sa.eps, sa.N, Cl, L.R, L.estride, fixed_cl);
+  sb.piece = prep_piece(sb.eps, sb.N, Cl, L.R, L.estride, fixed_cl);
   const int Ki = static_cast<int>(K), Cli = static_cast<int>(Cl), Kpi = static_cast<int>(Kp);
   int rc = BVLM_OK;
 #define BVLM_PREP_CL(C)                                                                              \

@@ -120,6 +120,35 @@ def test_sample_probs_vs_torch_cuda(cl, k):
     assert bool((d <= ulp).all())
 
 
+@pytest.mark.parametrize("n,k,cl,misalign", [(7, 400, 10, 0), (1, 1, 1, 0), (13, 33, 3, 0), (130, 100, 10, 1), (130, 100, 10, 2),
+                                               (6, 64, 12, 3), (9, 130, 16, 0), (5, 20, 200, 0), (11, 257, 7, 1)])
+def test_prepare_kernel_odd_shapes_and_alignments(n, k, cl, misalign):
+    """The fused prepare kernel (E0 + E1 + operand layout) at shapes that exercise its tails and fallbacks: row counts that
+    are not a multiple of the 4-row block, K > 128 (several samples per thread) and K = 1, odd / large class counts (scalar and
+    generic paths), and noise whose base address is only 4- / 8- / 12-byte aligned (8- and 4-byte cp.async pieces)."""
+    from bayesvlm_b200 import epig as E
+
+    gen = torch.Generator().manual_seed(1000 * n + k + cl)
+    mean = (torch.randn(n, cl, generator=gen) * 2).cuda()
+    var = (torch.rand(n, cl, generator=gen) * 3 + 0.1).cuda()
+    buf = torch.randn(k * n * cl + 8, generator=gen).cuda()
+    eps = buf[misalign:misalign + k * n * cl].view(k, n, cl)
+    assert eps.data_ptr() % 16 == (4 * misalign) % 16
+    ref = torch.softmax((eps * var.sqrt() + mean).permute(1, 0, 2), dim=2).half()
+    assert E._prepare_fits(k, cl, True)
+    probs, oper, marg = E.prepare_from_noise(mean, var, eps, want_probs=True)
+    d = (probs.float() - ref.float()).abs()
+    assert bool((d == 0).all()) if cl <= 16 else float((d == 0).double().mean()) >= 0.999
+    kp = oper.shape[2]
+    assert kp % 64 == 0 and kp >= k
+    assert torch.equal(oper[:, :, :k], probs.permute(0, 2, 1)) and bool((oper[:, :, k:] == 0).all())
+    me = E.entropy_from_probs(torch.mean(ref, dim=1))  # torch's own Half sequence on the same probabilities
+    assert float((marg.float() - me.float()).abs().max()) <= float(np.spacing(np.float16(max(1.0, float(me.abs().max())))))
+    # the same operands from the fp16 probabilities (the [N, K, Cl] entry point)
+    oper2, marg2 = E.prepare_from_probs(probs)
+    assert torch.equal(oper2, oper) and torch.equal(marg2, marg)
+
+
 def test_sample_probs_golden(golden):
     from bayesvlm_b200.vlm import sample_probas_from_noise
 
