@@ -207,6 +207,8 @@ def test_marginal_entropy_golden_and_generic_dtype(golden):
                                  dict(Np=1000, Nt=700, K=100, Cl=10, chunk=4096),
                                  dict(Np=37, Nt=41, K=20, Cl=200, chunk=2048),         # a pool row spans CTAs (ImageNet-R: 200 classes)
                                  dict(Np=9, Nt=12, K=8, Cl=300, chunk=1024),           # ... and CTA pairs
+                                 dict(Np=50, Nt=61, K=400, Cl=10, chunk=256),          # K = 400 (7 K blocks), one tile per chunk
+                                 dict(Np=3, Nt=2, K=5, Cl=2, chunk=8192),              # one partial tile, chunk > all columns
                                  dict(Np=4096, Nt=10000, K=100, Cl=10, chunk=4096),    # config 5, primary
                                  dict(Np=4096, Nt=10000, K=100, Cl=65, chunk=4096)])   # config 5, secondary (OfficeHome)
 def test_epig_scores_vs_reference_sequence_on_same_gpu(cfg):
