@@ -225,12 +225,17 @@ def kfac_ggn(vlm, num_classes: int, batch_size: int, source_embeds: torch.Tensor
         with torch.cuda.stream(stage["stream"]):
             if stage["consumed"][slot] is not None:
                 stage["stream"].wait_event(stage["consumed"][slot])  # the kernels of two batches ago are done with this set
-            for dst, src_t in zip(stage["device"][slot], sources):
+            # targets and source embeddings first: the GGN pipeline starts as soon as they have landed, the activations
+            # (only the side-stream SYRK reads them) follow under its first kernels
+            events = []
+            for k, (dst, src_t) in enumerate(zip(stage["device"][slot], sources)):
                 dst.copy_(src_t, non_blocking=True)
-            ready = torch.cuda.Event()
-            ready.record(stage["stream"])
-        stage["loaded"][slot] = ready
-        return tuple(stage["device"][slot]) + (ready,)
+                if k >= 1:
+                    ev = torch.cuda.Event()
+                    ev.record(stage["stream"])
+                    events.append(ev)
+        stage["loaded"][slot] = events[-1]
+        return tuple(stage["device"][slot]) + (tuple(events),)
 
     schedule = list(class_batch_schedule(num_class_batches, rank, world))
     syrk_stream.wait_stream(main_stream)
@@ -246,10 +251,12 @@ def kfac_ggn(vlm, num_classes: int, batch_size: int, source_embeds: torch.Tensor
     for k, _ in enumerate(schedule):
         tgt, src, act, ready = pending
         pending = fetch(schedule[k + 1], (k + 1) % 2) if k + 1 < len(schedule) else None
-        if ready is not None:
-            main_stream.wait_event(ready)
+        if ready is not None:  # staged inputs: (embeddings landed, activations landed)
+            main_stream.wait_event(ready[0])
         if not whole_block:
-            syrk_stream.wait_stream(main_stream)  # (staged inputs: the copy has landed; also orders the staging-buffer reuse)
+            syrk_stream.wait_stream(main_stream)  # (orders the staging-buffer reuse of two batches ago as well)
+            if ready is not None:
+                syrk_stream.wait_event(ready[1])
             with torch.cuda.stream(syrk_stream):
                 syrk_accumulate(act, out=A, append_one=siglip, accumulate=True)
         used = (num_classes // batch_size) * batch_size  # data-batch remainder never reaches B
