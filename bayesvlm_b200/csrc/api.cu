@@ -157,7 +157,7 @@ int bvlm_gemm_tn_f32(const void* A16, int64_t M, const void* B16, int64_t N, int
       BVLM_CUDA_TRY(cudaMemset2DAsync(D, static_cast<size_t>(ldd) * 4, 0, static_cast<size_t>(N) * 4, static_cast<size_t>(M), st));
     }
     if (engine == 2) return launch_gemm2<BN, 6, 4, EpiStoreF32<BN>>(tmA, tmB, plan2, ep2, st, TAG_GEMM_DIAG);
-    return launch_gemm2<BN, 6, 8, EpiStoreF32<BN>>(tmA, tmB, plan2, ep2, st, TAG_GEMM_DIAG);
+    return launch_gemm2<BN, 5, 8, EpiStoreF32<BN>>(tmA, tmB, plan2, ep2, st, TAG_GEMM_DIAG);
   }
   GemmPlan plan = make_plan<BN>(static_cast<int>(M), static_cast<int>(N), static_cast<int>(k_pad), SCHED_TILES,
                                 split_k < 1 ? 1 : split_k, fmt, fmt);

@@ -66,24 +66,33 @@ __device__ __forceinline__ float warp_transpose_reduce32(float (&v)[32], int lan
 // ---------------------------------------------------------------------------------------------
 template <int BN>
 struct EpiStoreF32 {
-  static constexpr size_t scratch_bytes(int) { return 16; }
+  // two 4 KB staging slabs per epilogue warp for the bulk-reduction path (use_tma)
+  static constexpr size_t scratch_bytes(int warps) { return static_cast<size_t>(warps) * 2 * SLAB_BYTES; }
   struct Params {
     float* C;
     int64_t ldc;
     float alpha;
-    int atomic;              // 1: red.global.add (split-K / accumulate), 0: plain store
+    int atomic;              // 1: accumulate into C (split-K / accumulate), 0: plain store
     int lower_only;          // 1: only elements with row >= col are written (SYRK; mirrored by a later pass)
     const float* alpha_dev;  // optional device scalar multiplied into alpha
     const float* unscale;    // optional per-index multiplier u: C[i,j] (+)= alpha * u[i] * u[j] * acc (SYRK operand scaling)
+    // atomic accumulation as TMA bulk reductions (cp.reduce.async.bulk.tensor ... .add): 32 x 32 fp32 boxes staged in shared
+    // memory, the adds done by the L2 on whole 128-byte lines.  The per-element red.global.add of the first version made a
+    // warp instruction touch 32 rows (32 separate L2 atomics): the split-K SYRK of 65536 rows spent 2/3 of its time there.
+    int use_tma;             // 1: tm_c is valid (C 16-byte aligned, ldc * 4 a multiple of 16) and atomic == 1
+    CUtensorMap tm_c;        // [rows, cols] fp32, box {32 cols, 32 rows}, SWIZZLE_128B
   };
   struct State {
     float alpha;
+    int sidx;
   };
   static constexpr bool ALL_CHUNKS = false;
   static constexpr bool UNROLL_CHUNKS = true;
   static constexpr bool DRAIN_FIRST = false;
-  __device__ static void kernel_begin(State&, const Params&, const EpiCtx&) {}
-  __device__ static void kernel_end(State&, const Params&, const EpiCtx&) {}
+  __device__ static void kernel_begin(State& st, const Params&, const EpiCtx&) { st.sidx = 0; }
+  __device__ static void kernel_end(State&, const Params& p, const EpiCtx& ctx) {
+    if (p.use_tma && ctx.lane == 0) tma_store_wait_all<0>();
+  }
   __device__ static void item_begin(State& st, const Params& p, const EpiCtx&, const TileCoord&) {
     st.alpha = p.alpha_dev != nullptr ? p.alpha * (*p.alpha_dev) : p.alpha;
   }
@@ -92,6 +101,32 @@ struct EpiStoreF32 {
     const int row = epi_row(ctx, tc);
     const int col0 = tc.n * BN + c * 32;
     int n_valid = ctx.N - col0;
+    if (p.use_tma) {
+      // every lane takes part (warp-collective staging); rows / columns beyond the matrix are clipped by the tensor map,
+      // masked elements (upper triangle of a diagonal SYRK tile) add an exact zero
+      if (p.lower_only && col0 > tc.row0 + ctx.ew * 32 + 31) return;  // the whole 32 x 32 block lies above the diagonal (warp-uniform)
+      int lim = 32;
+      if (p.lower_only) {
+        lim = row - col0 + 1;
+        lim = lim < 0 ? 0 : lim;
+      }
+      float a = st.alpha;
+      if (p.unscale != nullptr) {
+        a *= row < ctx.M ? p.unscale[row] : 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] *= (j < lim && j < n_valid) ? a * p.unscale[col0 + j] : 0.f;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] *= j < lim ? a : 0.f;
+      }
+      const uint32_t slab = ctx.scratch_u32 + static_cast<uint32_t>(ctx.wid * 2 + st.sidx) * SLAB_BYTES;
+      slab_wait_free<1>(ctx.lane);  // the reduction issued two chunks ago has finished reading its slab
+      slab_write_f32(slab, ctx.lane, v);
+      slab_issue_add(&p.tm_c, slab, ctx.lane, col0, tc.row0 + ctx.ew * 32);
+      slab_commit(ctx.lane);
+      st.sidx ^= 1;
+      return;
+    }
     if (row >= ctx.M) return;
     if (p.lower_only) {
       const int lim = row - col0 + 1;  // columns col0 .. row

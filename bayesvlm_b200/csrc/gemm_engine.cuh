@@ -249,6 +249,17 @@ __device__ __forceinline__ void slab_issue(const CUtensorMap* tm, uint32_t slab,
                  : "memory");
   }
 }
+// same, as a bulk REDUCTION: global[box] += slab (fp32 add performed by the L2 on whole lines)
+__device__ __forceinline__ void slab_issue_add(const CUtensorMap* tm, uint32_t slab, int lane, int c0, int c1) {
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+                 :
+                 : "l"(reinterpret_cast<uint64_t>(tm)), "r"(slab), "r"(c0), "r"(c1)
+                 : "memory");
+  }
+}
 __device__ __forceinline__ void slab_commit(int lane) {
   if (lane == 0) tma_store_commit();
 }

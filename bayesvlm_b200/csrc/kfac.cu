@@ -271,6 +271,12 @@ int ggn_impl(const float* X, int64_t B, int64_t ldx, const float* Y, int64_t C, 
                                      FMT_F16);
     p4.idesc = make_idesc_f16(GEMM2_BM, GGN_BN, FMT_F16, FMT_F16, 1, 1);
     EpiStoreF32<GGN_BN>::Params e4{g.Hinc, D, 1.0f, 1, 0, nullptr, nullptr};
+    if ((D * 4) % 16 == 0 && (reinterpret_cast<uintptr_t>(g.Hinc) & 15) == 0) {  // split-K partials as TMA bulk reductions
+      if ((rc = make_tmap_2d(&e4.tm_c, g.Hinc, TM_F32, static_cast<uint64_t>(D), static_cast<uint64_t>(D),
+                             static_cast<uint64_t>(D) * 4, 32, 32, 1)))
+        return rc;
+      e4.use_tma = 1;
+    }
     if ((rc = launch_gemm2<GGN_BN, GGN_STAGES, 4, EpiStoreF32<GGN_BN>, true, true>(tmL, tmR, p4, e4, st, TAG_GGN_STACKED)))
       return rc;
   }
@@ -331,6 +337,12 @@ int bvlm_syrk_f32acc(const float* X, int64_t n, int64_t d, int64_t ldx, int appe
   plan.idesc = make_idesc_f16(GEMM2_BM, BN, FMT_F16, FMT_F16, 1, 1);
   // lower triangle accumulated with red.global.add, then mirrored: C stays exactly symmetric
   EpiStoreF32<BN>::Params ep{C, ldc, alpha, 1, 1, nullptr, unscale};
+  if ((ldc * 4) % 16 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0) {  // split-K partials as TMA bulk reductions
+    if ((rc = make_tmap_2d(&ep.tm_c, C, TM_F32, static_cast<uint64_t>(dA), static_cast<uint64_t>(dA),
+                           static_cast<uint64_t>(ldc) * 4, 32, 32, 1)))
+      return rc;
+    ep.use_tma = 1;
+  }
   if ((rc = launch_gemm2<BN, 6, 4, EpiStoreF32<BN>, true, true>(tm, tm, plan, ep, st, TAG_SYRK))) return rc;
   return launch_symmetrize_scale(C, dA, ldc, 1.0f, st);
 }
