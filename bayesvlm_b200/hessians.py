@@ -86,18 +86,19 @@ def syrk_accumulate(acts: torch.Tensor, out: Optional[torch.Tensor] = None, appe
     acts = _lib.rowmajor(_lib.require_cuda(acts, "activations"))
     n, d = acts.shape
     d_a = d + (1 if append_one else 0)
-    if out is None:
-        out = torch.zeros((d_a, d_a), dtype=torch.float32, device=acts.device)
+    own = out is None
+    if own:  # (row pitch a multiple of 16 bytes: split-K partials go through TMA bulk reductions; returned contiguous)
+        out = torch.zeros((d_a, (d_a + 3) // 4 * 4), dtype=torch.float32, device=acts.device)[:, :d_a]
         accumulate = False
     if n == 0:
         if not accumulate:
             out.zero_()
-        return out
+        return out.contiguous() if own else out
     ws = _lib.workspace(acts.device, lib.bvlm_syrk_workspace_bytes(n, d, int(append_one), _lib.PREC_X1), tag="syrk")
     _lib.run(acts.device, "bvlm_syrk_f32acc", _lib.ptr(acts), n, d, acts.stride(0), int(append_one), _lib.PREC_X1,
              _lib.ptr(out), out.stride(0), float(alpha), int(accumulate), _lib.ptr(ws), ws.numel(),
              _lib.stream_ptr(acts.device))
-    return out
+    return out.contiguous() if own else out
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -191,7 +192,9 @@ def kfac_ggn(vlm, num_classes: int, batch_size: int, source_embeds: torch.Tensor
     d_in = source_activations.shape[1] + (1 if siglip else 0)
     d_emb = source_embeds.shape[1]
     with torch.cuda.device(dev):
-        A = torch.zeros((d_in, d_in), dtype=torch.float32, device=dev)
+        # row pitch padded to a multiple of 16 bytes (the bias-augmented SigLIP factor is 769 / 3073 wide): the SYRK then adds
+        # its split-K partial tiles with TMA bulk reductions instead of per-element atomics; the result below is contiguous
+        A = torch.zeros((d_in, (d_in + 3) // 4 * 4), dtype=torch.float32, device=dev)[:, :d_in]
         B = torch.zeros((d_emb, d_emb), dtype=torch.float32, device=dev)
 
     # Host-resident inputs (the reference's calling convention) are staged one class batch AHEAD on a copy stream, so that
