@@ -19,7 +19,7 @@ cap pred_prep   'k_predictive_prep'                2 python scripts/run_pred_onc
 cap probit      'k_probit_softmax'                 0 python scripts/run_probit_once.py
 cap ggn_rowstats 'gemm2_tn_kernel.*EpiRowLse'      1 python scripts/run_ggn_once.py 2
 cap ggn_weights 'gemm2_tn_kernel.*EpiGgnWeights'   1 python scripts/run_ggn_once.py 2
-cap ggn_moments 'gemm2_tn_kernel.*EpiStoreF32.*false, .*true, ' 1 python scripts/run_ggn_once.py 2
+cap ggn_moments 'gemm2_tn_kernel.*EpiStoreF32.*bool.0, .bool.1' 1 python scripts/run_ggn_once.py 2
 cap epig_joint  'gemm2_tn_kernel.*EpiEpigJoint'    0 python scripts/run_epig_once.py 1
 cap epig_prepare 'k_epig_prepare'                  0 python scripts/run_epig_once.py 1
 ls -la $O/r2_*.ncu-rep
