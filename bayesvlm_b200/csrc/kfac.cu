@@ -32,7 +32,7 @@ namespace {
 
 constexpr int GGN_BN = 256;
 constexpr int GGN_STAGES = 6;    // CTA-pair engine: 32 KB per stage
-constexpr int GGN_W_STAGES = 4;  // the weights pass is epilogue bound: 3 operand stages + 96 KB of rotating output slabs
+constexpr int GGN_W_STAGES = 4;  // the weights pass is store / epilogue bound: 4 operand stages + 64 KB of output slabs (2 per warp)
 constexpr int GGN_ROWSTAT_SPLITS_MAX = 16;
 constexpr int SYRK_BN = 128;
 constexpr int SYRK_STAGES = 6;
@@ -55,14 +55,6 @@ struct Carver {
   }
   size_t used() const { return (off + 255) & ~static_cast<size_t>(255); }
 };
-
-inline int ggn_pairs_env() {
-  static const int v = [] {
-    const char* e = getenv("BVLM_GGN_PAIRS");
-    return e != nullptr ? atoi(e) : 1;
-  }();
-  return v;
-}
 
 struct GgnLayout {
   int64_t Dp, Cp, Bp, Bs, Ktot, Kst;
@@ -153,11 +145,7 @@ int ggn_impl(const float* X, int64_t B, int64_t ldx, const float* Y, int64_t C, 
     const int S = balanced_panel_splits(p1.m_tiles, p1.n_tiles, pairs, GGN_ROWSTAT_SPLITS_MAX);
     p1.splits = S;
     EpiRowLse<GGN_BN>::Params e1{g.rowmax2, g.rest, g.pivot, s * kLog2e / op2, S};
-    if (ggn_pairs_env() == 2 && prec != 3) {
-      plan_use_pairs(p1, 2);
-      if ((rc = launch_gemm2<GGN_BN, GGN_STAGES, 8, EpiRowLse<GGN_BN>, false, false, 2>(tmX, tmY, p1, e1, st, TAG_GGN_ROWSTATS)))
-        return rc;
-    } else if ((rc = launch_gemm2<GGN_BN, GGN_STAGES, 8, EpiRowLse<GGN_BN>>(tmX, tmY, p1, e1, st, TAG_GGN_ROWSTATS))) return rc;
+    if ((rc = launch_gemm2<GGN_BN, GGN_STAGES, 8, EpiRowLse<GGN_BN>>(tmX, tmY, p1, e1, st, TAG_GGN_ROWSTATS))) return rc;
     if (S > 1) {
       if ((rc = launch_merge_rowstats(g.rowmax2, g.rest, g.pivot, B, S, st))) return rc;
       rowmax2 += static_cast<size_t>(B) * S;
@@ -191,13 +179,9 @@ int ggn_impl(const float* X, int64_t B, int64_t ldx, const float* Y, int64_t C, 
         return rc;
     } else {
       EpiGgnWeights<GGN_BN, false>::Params e2{tmW, tmWL, g.rowinfo, g.q, s * kLog2e / op2, 1.0f / op2, 0.f};
-      if (ggn_pairs_env() == 2 && prec != 3) {
-        plan_use_pairs(p2, 2);
-        if (p2.splits > p2.m_tiles) p2.splits = p2.m_tiles;
-        if ((rc = launch_gemm2<GGN_BN, GGN_W_STAGES, 8, EpiGgnWeights<GGN_BN, false>, false, false, 2>(tmX, tmY, p2, e2, st,
-                                                                                                      TAG_GGN_WEIGHTS)))
-          return rc;
-      } else if ((rc = launch_gemm2<GGN_BN, GGN_W_STAGES, 8, EpiGgnWeights<GGN_BN, false>>(tmX, tmY, p2, e2, st, TAG_GGN_WEIGHTS)))
+      // (4-CTA clusters with the class tile multicast into two MMA pairs were measured for passes 1 and 2: slower, 0.82 vs
+      //  0.77 ms and 1.54 vs 1.38 ms -- the bytes delivered per SM do not change)
+      if ((rc = launch_gemm2<GGN_BN, GGN_W_STAGES, 8, EpiGgnWeights<GGN_BN, false>>(tmX, tmY, p2, e2, st, TAG_GGN_WEIGHTS)))
         return rc;
     }
   }
