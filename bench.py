@@ -552,6 +552,39 @@ def run_b200(args, rank, world, local_rank):
     del h_img, h_act, h_txt
     torch.cuda.empty_cache()
 
+    # K1 alone (nothing else on the GPU): the rank's config-2 block of activations through ONE syrk_accumulate call. The
+    # `syrk` entry of the KFAC legs above is timed while the SYRK shares the SMs with GGN pass 1 (side stream); this is the
+    # kernel by itself -- tensor-core launch and whole operator (absmax + fp16 conversion + GEMM + mirror) separately.
+    def syrk_leg(rows, d):
+        from bayesvlm_b200.hessians import syrk_accumulate
+
+        gs = torch.Generator(device=dev).manual_seed(KFAC["seed"] + 7 + rank)
+        X = torch.randn(rows, d, generator=gs, device=dev)
+        out_ = torch.zeros(d, d, device=dev)
+        fn = lambda: syrk_accumulate(X, out=out_)
+        fn()
+        ms_op = timed(fn, 5, settle=1)
+        _lib.timing_enable(True)
+        fn()
+        barrier_sync()
+        _lib.timing_enable(False)
+        kk = _lib.timing_collect()
+        ms_gemm = kk["syrk"][1] / kk["syrk"][0]
+        flop = float(rows) * d * (d + 1.0)
+        ref = (X[:4096].double().T @ X[:4096].double())
+        got = syrk_accumulate(X[:4096]).double()
+        return {"rows": rows, "d": d, "flops": "n d (d+1), symmetric count", "unit": "TFLOP/s", "peak": peak,
+                "gemm_launch_ms": ms_gemm, "gemm_tflops": flop / (ms_gemm * 1e-3) / 1e12, "frac": flop / (ms_gemm * 1e-3) / 1e12 / peak,
+                "operator_ms": ms_op, "operator_tflops": flop / (ms_op * 1e-3) / 1e12,
+                "operator_frac": flop / (ms_op * 1e-3) / 1e12 / peak,
+                "operator_hbm_bytes": rows * d * (4 + 4 + 2 + 2), "rel_err_4096_rows_vs_fp64": float((got - ref).norm() / ref.norm())}
+
+    try:
+        kfac["syrk_solo"] = syrk_leg(KFAC["total_class_batches"] * KFAC["num_classes"] // world // (4 if args.quick else 1), KFAC["d_img"])
+    except Exception as exc:
+        kfac["syrk_solo"] = {"error": repr(exc)[:300]}
+    torch.cuda.empty_cache()
+
     extra_legs = {}
     if not args.quick:
         for name, fn in (

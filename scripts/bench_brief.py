@@ -16,3 +16,5 @@ if e:
     if c: print("epig65", f"{c['value']:.4g}", "ms", round(c["ms"], 2), "mufu", round(c["joint_frac_of_mufu_roof"], 3), "red gbs", round(c["reductions"]["gbs"]))
 print("e2e", f"{d['e2e']['value']:.4g}", round(d["e2e"]["ms_per_step"], 3), "clocks", d["clocks"]["sm_mhz"], d["clocks"]["reasons"])
 print("parity_check", d.get("parity_check", {}).get("max_excess"))
+ss = d.get("kfac", {}).get("syrk_solo")
+if ss: print("syrk_solo", {k: (round(v, 4) if isinstance(v, float) else v) for k, v in ss.items() if k not in ("flops", "unit")})
