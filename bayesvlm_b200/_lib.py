@@ -14,7 +14,8 @@ from pathlib import Path
 import torch
 
 _PKG_DIR = Path(__file__).resolve().parent
-LIB_PATH = _PKG_DIR / "libbvlm.so"
+# BVLM_LIB: load another build of the same C ABI instead (the -DBVLM_DIAG ablation build, `python -m bayesvlm_b200.build --diag`)
+LIB_PATH = Path(os.environ["BVLM_LIB"]).resolve() if os.environ.get("BVLM_LIB") else _PKG_DIR / "libbvlm.so"
 
 PREC_X1 = 1
 PREC_X2F8 = 2

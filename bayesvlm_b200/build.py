@@ -54,16 +54,26 @@ def needs_build() -> bool:
     return not (LIB_PATH.exists() and stamp.exists() and stamp.read_text() == _signature())
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
+def build(force: bool = False, verbose: bool = False, diag: bool = False) -> Path:
+    """``diag=True`` builds ``libbvlm_diag.so`` with -DBVLM_DIAG (the ablation switches of predictive.cu / epilogues.cuh) next
+    to the product library; it is only ever loaded when ``BVLM_LIB`` points at it (scripts/diag_pred_epilogue.sh)."""
+    if diag:
+        return _build_to(PKG_DIR / "libbvlm_diag.so", REPO_ROOT / "build" / "bvlm_diag", ["-DBVLM_DIAG"], verbose)
     if not force and not needs_build():
         return LIB_PATH
-    BUILD_DIR.mkdir(parents=True, exist_ok=True)
+    _build_to(LIB_PATH, BUILD_DIR, [], verbose)
+    (BUILD_DIR / "signature.txt").write_text(_signature())
+    return LIB_PATH
+
+
+def _build_to(lib_path: Path, build_dir: Path, defines, verbose: bool) -> Path:
+    build_dir.mkdir(parents=True, exist_ok=True)
     nvcc = _nvcc()
-    extra = ["-Xptxas", "-v"] if verbose else []
+    extra = (["-Xptxas", "-v"] if verbose else []) + list(defines)
 
     def compile_one(name: str) -> Path:
         src = CSRC / name
-        obj = BUILD_DIR / (src.stem + ".o")
+        obj = build_dir / (src.stem + ".o")
         cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", str(src), "-o", str(obj)]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if verbose or res.returncode != 0:
@@ -75,15 +85,14 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     sources = [s for s in SOURCES if (CSRC / s).exists()]
     with ThreadPoolExecutor(max_workers=min(len(sources), os.cpu_count() or 4)) as ex:
         objs = list(ex.map(compile_one, sources))
-    cmd = [nvcc, "-shared", "-o", str(LIB_PATH), *map(str, objs), "-gencode", "arch=compute_100a,code=sm_100a"]
+    cmd = [nvcc, "-shared", "-o", str(lib_path), *map(str, objs), "-gencode", "arch=compute_100a,code=sm_100a"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
-        raise RuntimeError("link of libbvlm.so failed")
-    (BUILD_DIR / "signature.txt").write_text(_signature())
-    return LIB_PATH
+        raise RuntimeError(f"link of {lib_path.name} failed")
+    return lib_path
 
 
 if __name__ == "__main__":
-    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, diag="--diag" in sys.argv)
     print(path)

@@ -383,8 +383,22 @@ struct EpiPredictive {
     }
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] *= st.rm;
-#ifdef BVLM_DIAG
-    if (p.use_tma == 2) return;  // (diagnostic build only: main loop without output traffic, BVLM_DEBUG_NOSTORE=1)
+#ifdef BVLM_DIAG  // diagnostic build only (BVLM_DEBUG_EPI): which part of the output path costs the main loop its rate
+    if (p.use_tma == 2) return;  // 1: epilogue math only, no shared-memory staging, no stores
+    if (p.use_tma == 3) {        // 2: slabs written to shared memory, never stored
+      const uint32_t slab_m = ctx.scratch_u32 + static_cast<uint32_t>(ctx.wid) * (4 * SLAB_BYTES) + static_cast<uint32_t>(c & 1) * (2 * SLAB_BYTES);
+      slab_write_f32(slab_m, ctx.lane, v);
+      slab_write_f32(slab_m + SLAB_BYTES, ctx.lane, var);
+      return;
+    }
+    if (p.use_tma == 4) {        // 3: bulk stores of (stale) slabs, nothing written to shared memory
+      const uint32_t slab_m = ctx.scratch_u32 + static_cast<uint32_t>(ctx.wid) * (4 * SLAB_BYTES) + static_cast<uint32_t>(c & 1) * (2 * SLAB_BYTES);
+      slab_wait_free<1>(ctx.lane);
+      slab_issue(&p.tm_mean, slab_m, ctx.lane, col0, tc.row0 + ctx.ew * 32);
+      slab_issue(&p.tm_var, slab_m + SLAB_BYTES, ctx.lane, col0, tc.row0 + ctx.ew * 32);
+      slab_commit(ctx.lane);
+      return;
+    }
 #endif
     if (p.use_tma) {
       // rows beyond N and columns beyond C are clipped by the tensor map
