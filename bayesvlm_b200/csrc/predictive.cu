@@ -255,7 +255,8 @@ int bvlm_predictive(const float* E, int64_t N, int64_t D, int64_t lde, const flo
   }
 #ifdef BVLM_DIAG  // diagnostic builds only (python -m bayesvlm_b200.build --diag): never in the shipped library
   if (getenv("BVLM_DEBUG_NOSTORE") != nullptr) ep.use_tma = 2;  // main loop without output traffic
-  if (const char* de = getenv("BVLM_DEBUG_EPI"); de != nullptr && ep.use_tma) ep.use_tma = 1 + atoi(de);  // 1 / 2 / 3, see EpiPredictive::chunk
+  if (const char* de = getenv("BVLM_DEBUG_EPI"); de != nullptr && ep.use_tma)  // 1 / 2 / 3, see EpiPredictive::chunk; 4: direct stores
+    ep.use_tma = atoi(de) == 4 ? 0 : 1 + atoi(de);
   if (getenv("BVLM_DEBUG_SHORTK") != nullptr) {                 // one K block per tile -> the kernel is its epilogue
     plan.kb_total = 1;
     plan.kb_alt = 0x7fffffff;
