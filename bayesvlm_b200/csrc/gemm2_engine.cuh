@@ -12,6 +12,8 @@
 //     of the BN columns) and run the same pluggable epilogue functors as the one-CTA engine.
 // Schedules: SCHED_TILES (optionally split-K), SCHED_ROW_PANEL, SCHED_COL_PANEL, with M tiles of 256 rows.
 #pragma once
+#include <cstdlib>
+
 #include "gemm_engine.cuh"
 
 namespace bvlm {
@@ -457,6 +459,9 @@ inline int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ge
   const int items = plan_num_items<BN>(plan);
   int clusters = gemm2_max_clusters<BN, STAGES, EPI_WARPS, Epi, A_MN, B_MN, PAIRS>(smem);
   if (items < clusters) clusters = items;
+#ifdef BVLM_DIAG  // diagnostic build only: run on fewer CTA pairs (is a limit per SM or chip wide?)
+  if (const char* e = getenv("BVLM_DEBUG_CLUSTERS"); e != nullptr && atoi(e) > 0 && atoi(e) < clusters) clusters = atoi(e);
+#endif
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(static_cast<unsigned>(2 * PAIRS * clusters), 1, 1);
   cfg.blockDim = dim3(128 + 32 * EPI_WARPS, 1, 1);
