@@ -1,0 +1,159 @@
+"""Random-shape parity fuzz of the public API against the fp64 oracle (test infrastructure, not product code):
+    python scripts/fuzz_parity.py [seconds=120] [seed=0] [which=pred,ggn,syrk,epig]
+Shapes are drawn to hit ragged tiles, odd / unaligned widths, row pitches larger than the row, tiny and empty-ish inputs.
+Prints one line per failure and a summary; exit code 1 if anything failed."""
+import math, sys, time, traceback
+import numpy as np
+import torch
+
+sys.path.insert(0, ".")
+from oracle import laplace_oracle as O
+from oracle import torch_port as T
+from bayesvlm_b200.hessians import KroneckerFactorizedCovariance as KFC
+from bayesvlm_b200.hessians import compute_hessian_analytic_InfoNCE, compute_hessian_analytic_SigLIP, syrk_accumulate
+from bayesvlm_b200.vlm import CLIP, SIGLIP, EncoderResult, ProbabilisticLogits
+from bayesvlm_b200.epig import epig_from_logits_using_matmul, epig_from_probs_using_matmul
+
+budget = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
+seed = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+which = (sys.argv[3] if len(sys.argv) > 3 else "pred,ggn,syrk,epig").split(",")
+rng = np.random.default_rng(seed)
+fails, runs = [], {w: 0 for w in which}
+
+
+def pick(*choices):
+    return int(choices[rng.integers(len(choices))])
+
+
+def dim(lo, hi, specials=()):
+    if specials and rng.random() < 0.4:
+        return pick(*specials)
+    return int(rng.integers(lo, hi + 1))
+
+
+def spd_inv(gen, d, scale, lam):
+    w = torch.randn(4 * d, d, generator=gen, dtype=torch.float64)
+    F = (w.T @ w) / math.sqrt(4 * d) * scale
+    return torch.linalg.inv(F + math.sqrt(lam) * torch.eye(d, dtype=torch.float64)).float()
+
+
+def pitched(x, extra):
+    """The same values as a view with a row pitch larger than the row (non-contiguous rows)."""
+    if extra == 0:
+        return x
+    buf = torch.zeros(x.shape[0], x.shape[1] + extra, dtype=x.dtype, device=x.device)
+    buf[:, : x.shape[1]] = x
+    return buf[:, : x.shape[1]]
+
+
+def fuzz_pred(i):
+    gen = torch.Generator().manual_seed(seed * 100003 + i)
+    siglip = rng.random() < 0.3
+    N, C = dim(1, 700, (1, 127, 128, 129, 255, 256, 257, 513)), dim(1, 600, (1, 10, 255, 256, 257, 511, 513))
+    D = dim(2, 1100, (64, 65, 127, 128, 512, 768, 769, 1024, 1025))
+    d_i, d_t = dim(1, 1400, (63, 64, 65, 768, 1024, 1280)), dim(1, 900, (64, 512, 768, 769))
+    ls = float(rng.uniform(1.0, 4.8))
+    prec = ("fp16+fp8", "fp16x3", "fp16")[pick(0, 0, 1, 2)]
+    Ai, At = spd_inv(gen, d_i + int(siglip), 3e3, 600.0), spd_inv(gen, d_t + int(siglip), 3e3, 200.0)
+    Bi, Bt = spd_inv(gen, D, 20.0, 600.0), spd_inv(gen, D, 20.0, 200.0)
+    ie, ia = torch.randn(N, D, generator=gen) * float(rng.uniform(0.01, 30)), torch.randn(N, d_i, generator=gen) * float(rng.uniform(0.01, 30))
+    te, ta = torch.randn(C, D, generator=gen), torch.randn(C, d_t, generator=gen)
+    desc = f"pred N={N} C={C} D={D} d_i={d_i} d_t={d_t} siglip={siglip} prec={prec} ls={ls:.2f}"
+    cls = SIGLIP if siglip else CLIP
+    m = cls(logit_scale=ls, logit_bias=-3.0 if siglip else 0.0, device="cuda", precision=prec)
+    m.set_covariances(KFC(Ai.cuda(), Bi.cuda()), KFC(At.cuda(), Bt.cuda()))
+    ex = pick(0, 0, 1, 3, 4)
+    img = EncoderResult(pitched(ie.cuda(), ex), pitched(ia.cuda(), pick(0, 0, 2, 4)))
+    txt = EncoderResult(te.cuda(), ta.cuda())
+    with torch.no_grad():
+        out = m(img, txt)
+    rm, rv = O.predictive(ie.numpy(), ia.numpy(), te.numpy(), ta.numpy(), Ai.numpy(), Bi.numpy(), At.numpy(), Bt.numpy(), ls,
+                          src_bias=siglip, tgt_bias=siglip, dtype=np.float64)
+    s = math.exp(ls)
+    mean, var = out.mean.double().cpu().numpy(), out.var.double().cpu().numpy()
+    floor = (0.01 if prec != "fp16" else 0.2) * s
+    em = (np.abs(mean - rm) / (1e-3 * np.maximum(np.abs(rm), floor))).max()
+    ev = (np.abs(var - rv) / (1e-3 * np.abs(rv))).max()
+    if not (em <= 1.0 and ev <= 1.0 and np.isfinite(mean).all() and np.isfinite(var).all()):
+        fails.append(f"{desc}: mean excess {em:.3g}, var excess {ev:.3g}")
+    pr = out.probit().double().cpu().numpy()
+    rp = O.probit_softmax(mean, var, dtype=np.float64)
+    if np.abs(pr - rp).max() > 1e-4:
+        fails.append(f"{desc}: probit max abs {np.abs(pr - rp).max():.3g}")
+
+
+def fuzz_ggn(i):
+    gen = torch.Generator().manual_seed(seed * 100019 + i)
+    siglip = rng.random() < 0.5
+    B, C = dim(1, 900, (1, 5, 127, 128, 129, 256, 257)), dim(2, 1500, (2, 64, 255, 256, 257, 1024))
+    D = dim(2, 800, (8, 24, 64, 65, 256, 257, 512, 768))
+    z = torch.randn(max(B, C), D, generator=gen)
+    X = ((z + 1.5 * torch.randn(max(B, C), D, generator=gen))[:B] * float(rng.uniform(0.1, 20))).contiguous()
+    Y = (z + 1.5 * torch.randn(max(B, C), D, generator=gen))[:C].contiguous()
+    desc = f"ggn B={B} C={C} D={D} siglip={siglip}"
+    if siglip:
+        ls, lb = float(rng.uniform(2.0, 4.8)), float(rng.uniform(-13, 0))
+        H = compute_hessian_analytic_SigLIP(pitched(X.cuda(), pick(0, 0, 3)), torch.arange(B).cuda(), Y.cuda(), torch.tensor(ls), torch.tensor(lb))
+        ref = O.siglip_ggn_collapsed(X.numpy(), Y.numpy(), ls, lb)
+    else:
+        ls = float(rng.uniform(1.0, 4.7))
+        H = compute_hessian_analytic_InfoNCE(pitched(X.cuda(), pick(0, 0, 3)), Y.cuda(), torch.tensor(ls))
+        ref = O.infonce_ggn_collapsed(X.numpy(), Y.numpy(), ls)
+    Hn = H.double().cpu().numpy()
+    scale = max(np.abs(ref).max(), 1e-300)
+    rel_f = np.linalg.norm(Hn - ref) / max(np.linalg.norm(ref), 1e-300)
+    rel_m = np.abs(Hn - ref).max() / scale
+    if not (np.isfinite(Hn).all() and rel_f <= 1e-3 and rel_m <= 1e-3):
+        fails.append(f"{desc} ls={ls:.2f}: frob {rel_f:.3g}, max {rel_m:.3g}")
+
+
+def fuzz_syrk(i):
+    gen = torch.Generator().manual_seed(seed * 100043 + i)
+    n, d = dim(1, 5000, (1, 63, 64, 65, 4096)), dim(1, 1400, (1, 24, 255, 256, 257, 768, 769, 1280))
+    one = rng.random() < 0.4
+    X = torch.randn(n, d, generator=gen) * torch.exp(torch.randn(d, generator=gen) * 2.0)  # features of very different magnitude
+    A = syrk_accumulate(pitched(X.cuda(), pick(0, 0, 1, 4)), append_one=one).double().cpu().numpy()
+    Xd = X.double().numpy()
+    if one:
+        Xd = np.concatenate([Xd, np.ones((n, 1))], 1)
+    ref = Xd.T @ Xd
+    # relative to the natural scale of each entry (the features differ by orders of magnitude)
+    sc = np.sqrt(np.outer(np.diag(ref), np.diag(ref))) + 1e-300
+    err = (np.abs(A - ref) / sc).max()
+    if not (np.isfinite(A).all() and err <= 1e-3 and np.abs(A - A.T).max() == 0):
+        fails.append(f"syrk n={n} d={d} one={one}: scaled max err {err:.3g}, asym {np.abs(A - A.T).max():.3g}")
+
+
+def fuzz_epig(i):
+    torch.manual_seed(seed * 7 + i)
+    Np, Nt = dim(1, 700, (1, 127, 128, 129, 256)), dim(1, 500, (1, 10, 128, 257))
+    Cl, K = dim(1, 70, (1, 2, 10, 16, 17, 65)), dim(1, 130, (1, 33, 64, 100, 128))
+    chunk = pick(64, 256, 512, 4096, 8192)
+    mp, vp = torch.randn(Np, Cl, device="cuda") * 2, torch.rand(Np, Cl, device="cuda") * 3 + 0.1
+    mt, vt = torch.randn(Nt, Cl, device="cuda") * 2, torch.rand(Nt, Cl, device="cuda") * 3 + 0.1
+    desc = f"epig Np={Np} Nt={Nt} Cl={Cl} K={K} chunk={chunk}"
+    ours = epig_from_logits_using_matmul(ProbabilisticLogits(mp, vp), ProbabilisticLogits(mt, vt), seed=3, num_samples=K, chunk_size=chunk)
+    ref = T.epig_from_logits(mp, vp, mt, vt, seed=3, num_samples=K, chunk_size=chunk)
+    d = (ours - ref).abs()
+    quantum = 2.0 ** -11 * max(1.0, float(ref.abs().max()))  # one fp16 step of a per-chunk partial, times the chunks
+    n_chunks = math.ceil(Nt * Cl / chunk)
+    if not (torch.isfinite(ours).all() and float(d.max()) <= 2 * quantum * max(1, n_chunks) and float((d == 0).float().mean()) >= 0.9):
+        fails.append(f"{desc}: exact {float((d == 0).float().mean()):.3f}, max diff {float(d.max()):.3g} (quantum {quantum:.3g})")
+
+
+FUZZ = {"pred": fuzz_pred, "ggn": fuzz_ggn, "syrk": fuzz_syrk, "epig": fuzz_epig}
+t0 = time.time()
+i = 0
+while time.time() - t0 < budget:
+    w = which[i % len(which)]
+    try:
+        FUZZ[w](i)
+    except Exception as exc:  # an exception is a failure too (unless it is a documented refusal)
+        fails.append(f"{w} case {i}: EXCEPTION {type(exc).__name__}: {str(exc)[:200]} | {traceback.format_exc().splitlines()[-3].strip()[:160]}")
+    runs[w] += 1
+    i += 1
+    torch.cuda.synchronize()
+for f in fails:
+    print("FAIL", f)
+print("runs", runs, "failures", len(fails))
+sys.exit(1 if fails else 0)
