@@ -22,6 +22,7 @@ from .hessians import KroneckerFactorizedCovariance
 # error-compensation products in FP8 at twice the rate (~2^-15, 2/3 of the cost); "fp16" = single pass (~2^-11)
 _PRECISIONS = {"fp16x3": _lib.PREC_X3, "fp16+fp8": _lib.PREC_X2F8, "fp16": _lib.PREC_X1, "x3": _lib.PREC_X3,
                "x2f8": _lib.PREC_X2F8, "x1": _lib.PREC_X1}
+_MIN_D_REDUCED_PRECISION = 128  # embedding widths below this always take the hi/lo split mean GEMM
 
 
 class EncoderResult:
@@ -443,9 +444,14 @@ class CLIP(torch.nn.Module):
         """Enqueue the predictive kernels for CUDA `emb` [n, D] / `act` [n, d_in] into preallocated `mean` / `var`
         ([n, C] fp32 views with unit column stride) on the current stream."""
         prec = _PRECISIONS[self.precision]
+        n, d = emb.shape
+        if d < _MIN_D_REDUCED_PRECISION:
+            # the ~2^-15 / ~2^-11 products rely on their rounding errors averaging over the embedding dimension (error ~ s 2^-p /
+            # sqrt(D)); below 128 dimensions nothing averages (scripts/fuzz_parity.py: up to 2x the logit tolerance at D = 3 .. 21)
+            # and the third tensor-core pass costs nothing at that size
+            prec = _lib.PREC_X3
         src, tgt, (sum_beta, sum_delta, kappa) = self._sides()
         t16, t8, col_a, col_b = self._target_side(target_results, prec)
-        n, d = emb.shape
         c = target_results.embeds.shape[0]
         if target_results.embeds.shape[1] != d:
             raise ValueError("source and target embeddings must share the embedding dimension")
