@@ -1,5 +1,5 @@
 """Random-shape parity fuzz of the public API against the fp64 oracle (test infrastructure, not product code):
-    python scripts/fuzz_parity.py [seconds=120 | n=CASES] [seed=0] [which=pred,ggn,syrk,epig]
+    python scripts/fuzz_parity.py [seconds=120 | n=CASES] [seed=0] [which=pred,ggn,syrk,epig,kfac,host,mc]
 Shapes are drawn to hit ragged tiles, odd / unaligned widths, row pitches larger than the row, tiny and empty-ish inputs.
 Prints one line per failure and a summary; exit code 1 if anything failed."""
 import math, sys, time, traceback
@@ -13,12 +13,14 @@ from bayesvlm_b200.hessians import KroneckerFactorizedCovariance as KFC
 from bayesvlm_b200.hessians import compute_hessian_analytic_InfoNCE, compute_hessian_analytic_SigLIP, syrk_accumulate
 from bayesvlm_b200.vlm import CLIP, SIGLIP, EncoderResult, ProbabilisticLogits
 from bayesvlm_b200.epig import epig_from_logits_using_matmul, epig_from_probs_using_matmul
+from bayesvlm_b200.hessians import kfac_ggn
+from bayesvlm_b200.precompute import make_predictions
 
 arg1 = sys.argv[1] if len(sys.argv) > 1 else "120"
 max_cases = int(arg1[2:]) if arg1.startswith("n=") else None  # a fixed number of cases (deterministic for a seed) ...
 budget = float("inf") if max_cases is not None else float(arg1)  # ... or a time budget
 seed = int(sys.argv[2]) if len(sys.argv) > 2 else 0
-which = (sys.argv[3] if len(sys.argv) > 3 else "pred,ggn,syrk,epig").split(",")
+which = (sys.argv[3] if len(sys.argv) > 3 else "pred,ggn,syrk,epig,kfac,host,mc").split(",")
 rng = np.random.default_rng(seed)
 fails, runs = [], {w: 0 for w in which}
 
@@ -149,7 +151,85 @@ def fuzz_epig(i):
         fails.append(f"{desc}: exact {float((d == 0).float().mean()):.3f}, max diff {float(d.max()):.3g} (quantum {quantum:.3g})")
 
 
-FUZZ = {"pred": fuzz_pred, "ggn": fuzz_ggn, "syrk": fuzz_syrk, "epig": fuzz_epig}
+def fuzz_kfac(i):
+    """K0: the estimation loop with its dropped remainders (hessian_estimation.py:55,71), any input placement."""
+    gen = torch.Generator().manual_seed(seed * 100057 + i)
+    siglip = rng.random() < 0.4
+    ncls, bs = dim(16, 700, (16, 64, 127, 128, 129, 256, 512)), dim(1, 9, (1, 5))
+    ncb = dim(1, 4)
+    n = ncb * ncls + int(rng.integers(0, ncls))  # ragged tail: dropped by the reference
+    D, d_in = dim(32, 300, (32, 64, 65, 128, 256)), dim(64, 400, (64, 65, 128, 257))
+    z = torch.randn(n, D, generator=gen)
+    src_e, tgt_e = z + 1.5 * torch.randn(n, D, generator=gen), z + 1.5 * torch.randn(n, D, generator=gen)
+    src_a = torch.randn(n, d_in, generator=gen)
+    ls, lb = (float(rng.uniform(2.0, 4.8)), float(rng.uniform(-13, 0))) if siglip else (float(rng.uniform(1.0, 4.7)), 0.0)
+    like = "siglip" if siglip else "info_nce"
+    vlm = SIGLIP(logit_scale=ls, logit_bias=lb, device="cuda") if siglip else CLIP(logit_scale=ls, device="cuda")
+    place = (lambda t: t, lambda t: t.pin_memory(), lambda t: t.cuda())[pick(0, 1, 2)]
+    desc = f"kfac n={n} ncls={ncls} bs={bs} D={D} d_in={d_in} {like} ls={ls:.2f}"
+    A, B = kfac_ggn(vlm, ncls, bs, place(src_e), place(src_a), place(tgt_e), "cuda", like)
+    Ar, Br = O.kfac_ggn(src_e.numpy(), src_a.numpy(), tgt_e.numpy(), ncls, bs, ls, lb, likelihood=like)
+    for name, got, ref in (("A", A, Ar), ("B", B, Br)):
+        g = got.double().cpu().numpy()
+        rf = np.linalg.norm(g - ref) / max(np.linalg.norm(ref), 1e-300)
+        rm = np.abs(g - ref).max() / max(np.abs(ref).max(), 1e-300)
+        if not (g.shape == ref.shape and np.isfinite(g).all() and rf <= 1e-3 and rm <= 1e-3):
+            fails.append(f"{desc}: {name} frob {rf:.3g}, max {rm:.3g}")
+    if B.device.type != "cpu" or A.device.type != "cuda":
+        fails.append(f"{desc}: placement A on {A.device}, B on {B.device}")
+
+
+def fuzz_host(i):
+    """make_predictions / predict_host (pinned or pageable host buffers, odd batch sizes) == forward on device tensors."""
+    gen = torch.Generator().manual_seed(seed * 100069 + i)
+    N, C, D = dim(1, 900, (1, 255, 257)), dim(1, 300, (1, 10, 257)), dim(128, 600, (128, 512, 513))
+    d_i, d_t = dim(64, 700, (64, 768)), dim(64, 600, (64, 512))
+    bsz = dim(1, 1200, (1, 7, 64, 1000))
+    Ai, At = spd_inv(gen, d_i, 3e3, 600.0), spd_inv(gen, d_t, 3e3, 200.0)
+    Bi, Bt = spd_inv(gen, D, 20.0, 600.0), spd_inv(gen, D, 20.0, 200.0)
+    ie, ia = torch.randn(N, D, generator=gen), torch.randn(N, d_i, generator=gen)
+    te, ta = torch.randn(C, D, generator=gen), torch.randn(C, d_t, generator=gen)
+    m = CLIP(logit_scale=math.log(100.0), device="cuda")
+    m.set_covariances(KFC(Ai.cuda(), Bi.cuda()), KFC(At.cuda(), Bt.cuda()))
+    place = (lambda t: t, lambda t: t.pin_memory())[pick(0, 1)]
+    out = make_predictions(m, EncoderResult(place(ie), place(ia)), EncoderResult(te, ta), batch_size=bsz, device="cuda")
+    with torch.no_grad():
+        ref = m(EncoderResult(ie.cuda(), ia.cuda()), EncoderResult(te.cuda(), ta.cuda()))
+    desc = f"host N={N} C={C} D={D} d_i={d_i} d_t={d_t} batch={bsz}"
+    if out.mean.device.type != "cpu" or out.mean.shape != (N, C):
+        fails.append(f"{desc}: result on {out.mean.device} with shape {tuple(out.mean.shape)}")
+    # rows are independent: the batched host pipeline and one device call run the same kernels on the same rows
+    if not (torch.equal(out.mean, ref.mean.cpu()) and torch.equal(out.var, ref.var.cpu())):
+        fails.append(f"{desc}: differs from the device call by {float((out.mean - ref.mean.cpu()).abs().max()):.3g} / "
+                     f"{float((out.var - ref.var.cpu()).abs().max()):.3g}")
+
+
+def fuzz_mc(i):
+    """Monte-Carlo softmax / aleatoric entropy on the fused kernel == the reference's torch sequence under a shared seed."""
+    n, c, k = dim(1, 600, (1, 33, 257)), dim(1, 1100, (1, 10, 1000, 1024, 1025)), dim(1, 12)
+    torch.manual_seed(seed * 13 + i)
+    mean, var = torch.randn(n, c, device="cuda") * 3, torch.rand(n, c, device="cuda") * 4 + 0.05
+    pl = ProbabilisticLogits(mean, var)
+    p = pl.softmax(num_samples=k, seed=17)
+    torch.manual_seed(17)
+    std, ref = torch.sqrt(var), torch.zeros_like(mean)
+    for _ in range(k):  # vlm.py:86-89
+        ref += torch.nn.functional.softmax(mean + torch.randn(std.shape, device="cuda") * std, dim=-1)
+    ref /= k
+    torch.manual_seed(23)
+    h = pl.expected_aleatoric_entropy(num_samples=k)
+    torch.manual_seed(23)
+    href = 0
+    for _ in range(k):  # vlm.py:145-149
+        pr = torch.nn.functional.softmax(mean + torch.randn(var.shape, device="cuda") * torch.sqrt(var), dim=-1)
+        href = href + -(pr * pr.log()).sum(dim=-1)
+    href = href / k
+    ep, eh = float((p - ref).abs().max()), float(((h - href).abs() / href.abs().clamp_min(1e-3)).max())
+    if not (ep <= 2e-6 and eh <= 5e-5):
+        fails.append(f"mc n={n} c={c} k={k}: probs {ep:.3g}, entropy rel {eh:.3g}")
+
+
+FUZZ = {"pred": fuzz_pred, "ggn": fuzz_ggn, "syrk": fuzz_syrk, "epig": fuzz_epig, "kfac": fuzz_kfac, "host": fuzz_host, "mc": fuzz_mc}
 t0 = time.time()
 i = 0
 while time.time() - t0 < budget and (max_cases is None or i < max_cases):
