@@ -315,7 +315,22 @@ int bvlm_syrk_f32acc(const float* X, int64_t n, int64_t d, int64_t ldx, int appe
   // partial tile costs one red.global.add pass (200 MB at n = 2^20, d = 768).
   constexpr int SYRK_MAX_CHAIN_KB = 128;
   const int min_splits = (plan.kb_total + SYRK_MAX_CHAIN_KB - 1) / SYRK_MAX_CHAIN_KB;
-  if (splits < min_splits) splits = min_splits;
+  if (splits < min_splits) {
+    // more chains than CTA pairs: pick the count (from min_splits up) whose tri * splits items fill whole rounds of the pairs --
+    // 131072 rows at d = 768: 16 chains make 96 items = 1.3 rounds of 74 pairs (65 % of the machine busy), 24 make 1.95 (97 %)
+    const int pairs = device_sm_count() / 2;
+    double best = 0.0;
+    int best_s = min_splits;
+    for (int sp = min_splits; sp <= 2 * min_splits; ++sp) {
+      const long long items = static_cast<long long>(tri) * sp, rounds = (items + pairs - 1) / pairs;
+      const double eff = static_cast<double>(items) / static_cast<double>(rounds * pairs);
+      if (eff > best + 0.02) {
+        best = eff;
+        best_s = sp;
+      }
+    }
+    splits = best_s;
+  }
   if (splits > plan.kb_total) splits = plan.kb_total;
   plan.splits = splits;
   plan.idesc = make_idesc_f16(GEMM2_BM, BN, FMT_F16, FMT_F16, 1, 1);
