@@ -101,5 +101,7 @@ def test_entry_points_on_a_non_current_device():
         assert out.mean.device == torch.device(dev) and H.device == torch.device(dev)
         res[dev] = [x.float().cpu() for x in (out.mean, out.var, H, A, s)]
     assert torch.cuda.current_device() == 0
-    for a, b in zip(res["cuda:0"], res["cuda:1"]):
-        assert torch.equal(a, b) or float((a - b).abs().max() / a.abs().max()) <= 1e-5
+    # (the GGN's column sums q are accumulated with atomics, and q / max q is then rounded into the fp16 operands of the final
+    #  GEMM: the order of those fp32 adds moves H by up to ~2e-5 of its largest entry from run to run, on one device as well)
+    for name, tol, a, b in zip(("mean", "var", "H", "A", "epig"), (1e-5, 1e-5, 1e-4, 1e-5, 1e-5), res["cuda:0"], res["cuda:1"]):
+        assert torch.equal(a, b) or float((a - b).abs().max() / a.abs().max()) <= tol, name
