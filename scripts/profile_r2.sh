@@ -20,6 +20,7 @@ cap probit      'k_probit_softmax'                 0 python scripts/run_probit_o
 cap ggn_rowstats 'gemm2_tn_kernel.*EpiRowLse'      1 python scripts/run_ggn_once.py 2
 cap ggn_weights 'gemm2_tn_kernel.*EpiGgnWeights'   1 python scripts/run_ggn_once.py 2
 cap ggn_moments 'gemm2_tn_kernel.*EpiStoreF32.*bool.0, .bool.1' 1 python scripts/run_ggn_once.py 2
+cap syrk        'gemm2_tn_kernel.*EpiStoreF32.*bool.1, .bool.1' 1 python scripts/run_syrk_once.py 2
 cap epig_joint  'gemm2_tn_kernel.*EpiEpigJoint'    0 python scripts/run_epig_once.py 1
 cap epig_prepare 'k_epig_prepare'                  0 python scripts/run_epig_once.py 1
 ls -la $O/r2_*.ncu-rep
