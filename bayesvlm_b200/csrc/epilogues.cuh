@@ -391,6 +391,18 @@ struct EpiPredictive {
       slab_write_f32(slab_m + SLAB_BYTES, ctx.lane, var);
       return;
     }
+    if (p.use_tma == 6) {        // 5: as 3, but every 32 x 32 box leaves as TWO 32 x 16 boxes (tm_mean / tm_var encoded with 16 rows): is the
+                                 //    output path sensitive to the NUMBER of bulk stores or to their bytes?
+      const uint32_t slab_m = ctx.scratch_u32 + static_cast<uint32_t>(ctx.wid) * (4 * SLAB_BYTES) + static_cast<uint32_t>(c & 1) * (2 * SLAB_BYTES);
+      slab_wait_free<1>(ctx.lane);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        slab_issue(&p.tm_mean, slab_m + h * (SLAB_BYTES / 2), ctx.lane, col0, tc.row0 + ctx.ew * 32 + 16 * h);
+        slab_issue(&p.tm_var, slab_m + SLAB_BYTES + h * (SLAB_BYTES / 2), ctx.lane, col0, tc.row0 + ctx.ew * 32 + 16 * h);
+      }
+      slab_commit(ctx.lane);
+      return;
+    }
     if (p.use_tma == 4) {        // 3: bulk stores of (stale) slabs, nothing written to shared memory
       const uint32_t slab_m = ctx.scratch_u32 + static_cast<uint32_t>(ctx.wid) * (4 * SLAB_BYTES) + static_cast<uint32_t>(c & 1) * (2 * SLAB_BYTES);
       slab_wait_free<1>(ctx.lane);

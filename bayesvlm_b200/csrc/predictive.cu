@@ -246,11 +246,15 @@ int bvlm_predictive(const float* E, int64_t N, int64_t D, int64_t lde, const flo
   ep.use_tma = ((ldo * 4) % 16 == 0 && (reinterpret_cast<uintptr_t>(mean) & 15) == 0 &&
                 (reinterpret_cast<uintptr_t>(var) & 15) == 0) ? 1 : 0;
   if (ep.use_tma) {
+    int box_rows = 32;
+#ifdef BVLM_DIAG
+    if (const char* de = getenv("BVLM_DEBUG_EPI"); de != nullptr && atoi(de) == 5) box_rows = 16;
+#endif
     if ((rc = make_tmap_2d(&ep.tm_mean, mean, TM_F32, static_cast<uint64_t>(C), static_cast<uint64_t>(N),
-                           static_cast<uint64_t>(ldo) * 4, 32, 32, 1)))
+                           static_cast<uint64_t>(ldo) * 4, 32, box_rows, 1)))
       return rc;
     if ((rc = make_tmap_2d(&ep.tm_var, var, TM_F32, static_cast<uint64_t>(C), static_cast<uint64_t>(N),
-                           static_cast<uint64_t>(ldo) * 4, 32, 32, 1)))
+                           static_cast<uint64_t>(ldo) * 4, 32, box_rows, 1)))
       return rc;
   }
 #ifdef BVLM_DIAG  // diagnostic builds only (python -m bayesvlm_b200.build --diag): never in the shipped library
