@@ -366,7 +366,16 @@ class CLIP(torch.nn.Module):
         key = (self._cov_version, prec, emb._version, act._version)
         tc = self._target_cache
         if tc is not None and tc[0] == key and tc[1] is emb and tc[2] is act:
-            return tc[3:]
+            ready, made_on = tc[7], tc[8]
+            cur = torch.cuda.current_stream(tc[3].device)
+            if cur.cuda_stream != made_on:
+                # prepared (asynchronously) on another stream: order this stream behind it and tell the caching allocator
+                # that the operands are in use here too
+                cur.wait_event(ready)
+                for t in tc[3:7]:
+                    if t is not None:
+                        t.record_stream(cur)
+            return tc[3:7]
         emb = _lib.rowmajor(_lib.require_cuda(emb.detach(), "target embeds"))
         act = _lib.rowmajor(_lib.require_cuda(act.detach(), "target activations"))
         c, d = emb.shape
@@ -388,7 +397,10 @@ class CLIP(torch.nn.Module):
             tgt.factor.dA, tgt.factor.k_pad, tgt.factor.scale, _lib.ptr(src.diag_b), sum_delta, kappa, prec,
             _lib.ptr(t16), _lib.ptr(t8), _lib.ptr(col_a), _lib.ptr(col_b), _lib.ptr(ws), ws.numel(),
             _lib.stream_ptr(emb.device))
-        self._target_cache = (key, target.embeds, target.activations, t16, t8, col_a, col_b)
+        cur = torch.cuda.current_stream(emb.device)
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        self._target_cache = (key, target.embeds, target.activations, t16, t8, col_a, col_b, ready, cur.cuda_stream)
         return t16, t8, col_a, col_b
 
     def _smith_torch(self, source_results: EncoderResult, target_results: EncoderResult):
