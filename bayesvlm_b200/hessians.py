@@ -250,6 +250,8 @@ def kfac_ggn(vlm, num_classes: int, batch_size: int, source_embeds: torch.Tensor
                             append_one=siglip, accumulate=True)
     if staged:
         stage["stream"].wait_stream(main_stream)
+        if stage.get("last_call_done") is not None:  # a previous call (possibly on another stream) may still read the buffers
+            stage["stream"].wait_event(stage["last_call_done"])
     pending = fetch(schedule[0], 0) if schedule else None
     for k, _ in enumerate(schedule):
         tgt, src, act, ready = pending
@@ -271,6 +273,9 @@ def kfac_ggn(vlm, num_classes: int, batch_size: int, source_embeds: torch.Tensor
             done.record(main_stream)
             stage["consumed"][k % 2] = done
     main_stream.wait_stream(syrk_stream)
+    if staged:
+        stage["last_call_done"] = torch.cuda.Event()
+        stage["last_call_done"].record(main_stream)
 
     if use_dist and world > 1:
         A, B = reduce_factors(A, B, group)
