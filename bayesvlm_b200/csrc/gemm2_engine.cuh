@@ -176,6 +176,9 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   cluster_sync_all();  // barriers of BOTH CTAs are initialised before anyone arrives remotely
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // (programmatic dependent launch: everything above overlapped the tail of the preceding kernel; no-ops for a normal launch)
+  grid_launch_dependents();
+  grid_dependency_wait();
 
   const int n_items = plan_num_items<BN>(plan);
   const int cluster_id = blockIdx.x / (2 * PAIRS);
@@ -445,7 +448,7 @@ inline int gemm2_max_clusters(size_t smem) {
 template <int BN, int STAGES, int EPI_WARPS, class Epi, bool A_MN = false, bool B_MN = false, int PAIRS = 1>
 inline int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmPlan& plan,
                         const typename Epi::Params& ep, cudaStream_t stream, int tag, const CUtensorMap* tmA8 = nullptr,
-                        const CUtensorMap* tmB8 = nullptr) {
+                        const CUtensorMap* tmB8 = nullptr, bool pdl = false) {
   if (plan.kb_total <= 0 || plan.M <= 0 || plan.N <= 0) return BVLM_EINVAL;
   constexpr size_t smem = gemm2_smem_bytes<BN, STAGES, EPI_WARPS, Epi>();
   static_assert(smem <= 232448, "shared memory budget exceeded");
@@ -467,13 +470,15 @@ inline int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ge
   cfg.blockDim = dim3(128 + 32 * EPI_WARPS, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2 * PAIRS;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl ? 2 : 1;
   timing_begin(tag, stream);
   const cudaError_t le = cudaLaunchKernelEx(&cfg, kfn, tmA, tmB, tmA8 != nullptr ? *tmA8 : tmA, tmB8 != nullptr ? *tmB8 : tmB,
                                             plan, ep);

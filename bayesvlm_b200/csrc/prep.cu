@@ -222,6 +222,10 @@ k_predictive_prep_vec(const float* __restrict__ x, int64_t R, int64_t D, int64_t
                       uint8_t* __restrict__ packed8, int64_t seg8, float* __restrict__ n2_out, float* __restrict__ pd_out,
                       float* __restrict__ unscale_out, const float* __restrict__ act, int64_t d_act, int64_t ld_act,
                       int append_one, __half* __restrict__ act16, int64_t act_kpad, float* __restrict__ act_unscale) {
+  // the quadratic-form GEMM is launched programmatically behind this kernel: its CTAs may become resident under this kernel's tail.
+  // (Launching THIS kernel programmatically behind the previous step's GEMM as well was measured: its resident, waiting blocks
+  //  cost the GEMM more than the overlap gains -- 0.2966 vs 0.2913 ms per step.)
+  grid_launch_dependents();
   const int64_t row = static_cast<int64_t>(blockIdx.x) * WARPS_PER_BLOCK + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= R) return;
